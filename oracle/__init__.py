@@ -1,0 +1,253 @@
+"""ctypes front-end of the CPU oracle (oracle/oracle.c) and of the compiled
+reference CPU code (oracle/_ref/libref_cpu.so, built from /root/reference).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / ``--impl reference`` legs of bench.py.  The product package
+(mini_b200) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import time
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+_REF = os.path.join(_HERE, "_ref", "libref_cpu.so")
+
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> None:
+    """Compile liboracle.so (and _ref/libref_cpu.so when /root/reference exists)."""
+    src = os.path.join(_HERE, "oracle.c")
+    stale = (not os.path.exists(_LIB)) or os.path.getmtime(_LIB) < os.path.getmtime(src)
+    need_ref = os.path.isdir("/root/reference/gunrock/src") and (
+        not os.path.exists(_REF)
+        or os.path.getmtime(_REF) < os.path.getmtime(os.path.join(_HERE, "ref_shim.cu")))
+    if force or stale or need_ref:
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        L.orc_rmat_pairs.argtypes = [C.c_int, C.c_int64, C.c_uint64, _i32p, _i32p]
+        L.orc_rmat_pairs.restype = None
+        L.orc_build_csr.argtypes = [C.c_int64, C.c_int64, _i32p, _i32p, C.c_int, _i64p, _i32p,
+                                    C.c_void_p, C.c_uint64]
+        L.orc_build_csr.restype = None
+        L.orc_bfs.argtypes = [C.c_int64, _i64p, _i32p, C.c_int32, _i32p]
+        L.orc_bfs.restype = None
+        L.orc_sssp_ref_preds.argtypes = [C.c_int64, _i64p, _i32p, _f32p, C.c_int32, _i32p, C.c_void_p]
+        L.orc_sssp_ref_preds.restype = None
+        L.orc_sssp_dist.argtypes = [C.c_int64, _i64p, _i32p, _f32p, C.c_int32, _f32p]
+        L.orc_sssp_dist.restype = None
+        L.orc_neighborhood_reduce_f64.argtypes = [C.c_int64, _i32p, _i64p, _i32p, _f64p, C.c_int,
+                                                  C.c_double, _f64p, C.c_void_p]
+        L.orc_neighborhood_reduce_f64.restype = None
+        L.orc_pr.argtypes = [C.c_int64, _i64p, _i32p, C.c_int, C.c_int, _f32p, _f32p, _i64p]
+        L.orc_pr.restype = C.c_int
+        L.orc_bfs_push_level.argtypes = [_i64p, _i32p, _i32p, C.c_int64, C.c_int32, _i32p, _i32p]
+        L.orc_bfs_push_level.restype = C.c_int64
+        L.orc_reached_arcs_i32.argtypes = [C.c_int64, _i64p, _i32p]
+        L.orc_reached_arcs_i32.restype = C.c_int64
+        L.orc_num_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def have_ref() -> bool:
+    build()
+    return os.path.exists(_REF)
+
+
+def ref():
+    """The unmodified reference CPU code (None if it was never built)."""
+    global _ref
+    if _ref is None:
+        if not have_ref():
+            return None
+        R = C.CDLL(_REF)
+        R.ref_bfs_cpu.argtypes = [C.c_int, C.c_int, _i32p, _i32p, C.c_int, _i32p]
+        R.ref_bfs_cpu.restype = C.c_double
+        R.ref_sssp_cpu.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _f32p, C.c_int, _i32p]
+        R.ref_sssp_cpu.restype = C.c_double
+        R.ref_load_graph.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        R.ref_load_graph.restype = C.c_int
+        _ref = R
+    return _ref
+
+
+# --------------------------------------------------------------------------- graphs
+class CSR:
+    """Host CSR: int64 offsets[n+1], int32 indices[m], optional float32 weights[m]."""
+
+    def __init__(self, n, offsets, indices, weights=None):
+        self.n = int(n)
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.indices = np.ascontiguousarray(indices, dtype=np.int32)
+        self.weights = None if weights is None else np.ascontiguousarray(weights, dtype=np.float32)
+        self.m = int(self.offsets[-1])
+        assert self.indices.shape[0] == self.m
+
+
+def rmat_pairs(scale: int, edge_factor: int = 16, seed: int = 1):
+    npairs = edge_factor << scale
+    src = np.empty(npairs, np.int32)
+    dst = np.empty(npairs, np.int32)
+    lib().orc_rmat_pairs(scale, npairs, seed, src, dst)
+    return src, dst
+
+
+def build_csr(n: int, src, dst, symmetrize: bool = True, weighted: bool = False, wseed: int = 7) -> CSR:
+    src = np.ascontiguousarray(src, np.int32)
+    dst = np.ascontiguousarray(dst, np.int32)
+    m = src.shape[0] * (2 if symmetrize else 1)
+    offsets = np.empty(n + 1, np.int64)
+    indices = np.empty(m, np.int32)
+    weights = np.empty(m, np.float32) if weighted else None
+    lib().orc_build_csr(n, src.shape[0], src, dst, int(symmetrize), offsets, indices,
+                        None if weights is None else weights.ctypes.data, wseed)
+    return CSR(n, offsets, indices, weights)
+
+
+def rmat_csr(scale: int, edge_factor: int = 16, seed: int = 1, weighted: bool = False, wseed: int = 7) -> CSR:
+    """Symmetrised RMAT CSR of SURVEY.md §8d (duplicates and self loops kept, m = 2*ef*2^scale)."""
+    s, d = rmat_pairs(scale, edge_factor, seed)
+    return build_csr(1 << scale, s, d, True, weighted, wseed)
+
+
+def load_mtx(path: str, undirected: bool) -> CSR:
+    """Restates gunrock/src/graph.hxx:96-223 (load_graph): a line ``i j [w]`` becomes arc
+    j-1 -> i-1 (CSR rows are built over mtx column 2, :139-172), weight 1.0 if absent
+    (:120-127, _random_edge_value=false), ``undirected`` appends every reverse (:130-137),
+    arcs sorted by (row, col).  Valid for files without duplicate edges (the reference's
+    comparator is UB otherwise)."""
+    with open(path) as f:
+        lines = [ln for ln in f.read().splitlines() if ln.strip()]
+    k = 0
+    while lines[k].startswith("%"):
+        k += 1
+    h, _w, ne = (int(x) for x in lines[k].split()[:3])
+    a, b, w = [], [], []
+    for ln in lines[k + 1:k + 1 + ne]:
+        t = ln.split()
+        a.append(int(t[0]) - 1)
+        b.append(int(t[1]) - 1)
+        w.append(float(t[2]) if len(t) > 2 else 1.0)
+    a, b, w = np.array(a, np.int64), np.array(b, np.int64), np.array(w, np.float32)
+    if undirected:
+        a, b, w = np.concatenate([a, b]), np.concatenate([b, a]), np.concatenate([w, w])
+    order = np.lexsort((a, b))          # primary key: column 2 (b), secondary: column 1 (a)
+    rows, cols, w = b[order], a[order], w[order]
+    offsets = np.zeros(h + 1, np.int64)
+    np.add.at(offsets, rows + 1, 1)
+    offsets = np.cumsum(offsets)
+    return CSR(h, offsets, cols.astype(np.int32), w)
+
+
+# --------------------------------------------------------------------------- algorithms
+def bfs(g: CSR, src: int = 0) -> np.ndarray:
+    labels = np.full(g.n, -1, np.int32)
+    lib().orc_bfs(g.n, g.offsets, g.indices, src, labels)
+    return labels
+
+
+def bfs_timed(g: CSR, src: int = 0):
+    labels = np.full(g.n, -1, np.int32)
+    t0 = time.perf_counter()
+    lib().orc_bfs(g.n, g.offsets, g.indices, src, labels)
+    return labels, time.perf_counter() - t0
+
+
+def sssp_dist(g: CSR, src: int = 0) -> np.ndarray:
+    out = np.empty(g.n, np.float32)
+    lib().orc_sssp_dist(g.n, g.offsets, g.indices, g.weights, src, out)
+    return out
+
+
+def sssp_ref_preds(g: CSR, src: int = 0):
+    preds = np.full(g.n, -1, np.int32)
+    dist = np.empty(g.n, np.int32)
+    lib().orc_sssp_ref_preds(g.n, g.offsets, g.indices, g.weights, src, preds, dist.ctypes.data)
+    return preds, dist
+
+
+def neighborhood_reduce(g: CSR, frontier, values, op: str = "plus", identity: float = 0.0):
+    frontier = np.ascontiguousarray(frontier, np.int32)
+    values = np.ascontiguousarray(values, np.float64)
+    red = np.empty(frontier.shape[0], np.float64)
+    asum = np.empty(frontier.shape[0], np.float64)
+    lib().orc_neighborhood_reduce_f64(frontier.shape[0], frontier, g.offsets, g.indices, values,
+                                      {"plus": 0, "min": 1, "max": 2}[op], identity, red,
+                                      asum.ctypes.data)
+    return red, asum
+
+
+def pr(g: CSR, max_iter: int = 10, scatter: bool = False):
+    cur = np.empty(g.n, np.float32)
+    red = np.empty(g.n, np.float32)
+    lens = np.zeros(max(max_iter, 1), np.int64)
+    it = lib().orc_pr(g.n, g.offsets, g.indices, max_iter, int(scatter), cur, red, lens)
+    return cur, red, lens[:it]
+
+
+def bfs_push_level(g: CSR, frontier, iteration: int, labels: np.ndarray):
+    frontier = np.ascontiguousarray(frontier, np.int32)
+    nxt = np.empty(g.n, np.int32)
+    k = lib().orc_bfs_push_level(g.offsets, g.indices, frontier, frontier.shape[0], iteration, labels, nxt)
+    return nxt[:k].copy()
+
+
+def reached_arcs(g: CSR, labels) -> int:
+    return int(lib().orc_reached_arcs_i32(g.n, g.offsets, np.ascontiguousarray(labels, np.int32)))
+
+
+def num_threads() -> int:
+    return int(lib().orc_num_threads())
+
+
+# --------------------------------------------------------------------------- reference wrappers
+def ref_bfs(g: CSR, src: int = 0):
+    """Unmodified bfs_problem_t::cpu (int32 CSR only). Returns (labels, seconds)."""
+    R = ref()
+    assert R is not None and g.m < 2 ** 31
+    labels = np.empty(g.n, np.int32)
+    t = R.ref_bfs_cpu(g.n, g.m, g.offsets.astype(np.int32), g.indices, src, labels)
+    return labels, t
+
+
+def ref_sssp_preds(g: CSR, src: int = 0):
+    R = ref()
+    assert R is not None and g.m < 2 ** 31
+    preds = np.empty(g.n, np.int32)
+    t = R.ref_sssp_cpu(g.n, g.m, g.offsets.astype(np.int32), g.indices, g.weights, src, preds)
+    return preds, t
+
+
+def ref_load_graph(path: str, undirected: bool):
+    R = ref()
+    assert R is not None
+    n, m, eq = C.c_int(), C.c_int(), C.c_int()
+    rc = R.ref_load_graph(path.encode(), int(undirected), C.byref(n), C.byref(m), None, None, None, None)
+    assert rc == 0, path
+    off = np.empty(n.value + 1, np.int32)
+    ind = np.empty(m.value, np.int32)
+    w = np.empty(m.value, np.float32)
+    R.ref_load_graph(path.encode(), int(undirected), C.byref(n), C.byref(m),
+                     off.ctypes.data, ind.ctypes.data, w.ctypes.data, C.byref(eq))
+    return CSR(n.value, off, ind, w), bool(eq.value)

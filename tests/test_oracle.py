@@ -1,0 +1,153 @@
+"""Pins the CPU oracle (oracle/oracle.c) against
+ (a) the committed golden vectors produced by the reference's own CPU code
+     (tests/golden/make_golden.py), and
+ (b) when oracle/_ref/libref_cpu.so is present, the reference code itself, live.
+Reference: gunrock/src/bfs/bfs_problem.hxx:52-72, gunrock/src/sssp/sssp_problem.hxx:59-88,
+gunrock/src/graph.hxx:96-223, gunrock/tests/{bfs,sssp}/test_*.cu:44-52."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+FIXTURES = ["ref_fixture_bfs.json", "ref_fixture_sssp_directed.json",
+            "ref_fixture_sssp_undirected.json", "ref_fixture_pr.json"]
+RMATS = ["ref_rmat_s8.json", "ref_rmat_s10.json", "ref_rmat_s16.json", "ref_rmat_s12_seed3.json"]
+
+
+def _write_mtx(tmp_path, rec):
+    p = tmp_path / "g.mtx"
+    with open(p, "w") as f:
+        f.write(" ".join(str(x) for x in rec["mtx_header"]) + "\n")
+        for e in rec["mtx_edges"]:
+            f.write(" ".join(str(int(x)) if k < 2 else repr(x) for k, x in enumerate(e)) + "\n")
+    return str(p)
+
+
+def _csr_from(rec):
+    return oracle.CSR(rec["n"], rec["offsets"], rec["indices"], rec["weights"])
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_load_mtx_matches_reference_load_graph(name, golden, tmp_path):
+    rec = golden(name)
+    g = oracle.load_mtx(_write_mtx(tmp_path, rec), rec["undirected"])
+    assert g.n == rec["n"] and g.m == rec["m"]
+    assert g.offsets.tolist() == rec["offsets"]
+    assert g.indices.tolist() == rec["indices"]
+    assert g.weights.tolist() == rec["weights"]
+    assert rec["csc_equals_csr"]          # device CSC is always a copy of CSR
+
+
+def test_survey_known_answers(golden):
+    """The §4 table of SURVEY.md (produced with the reference's own code)."""
+    r = golden("ref_fixture_bfs.json")
+    assert r["offsets"] == [0, 4, 8, 14, 18, 23, 27, 30] and r["bfs_labels"] == [0, 1, 1, 1, 2, 2, 2]
+    r = golden("ref_fixture_sssp_directed.json")
+    assert r["indices"] == [1, 2, 3, 2, 4, 3, 4, 5, 5, 6, 5, 6, 6]
+    assert r["weights"] == [3, 1, 3, 2, 7, 1, 5, 2, 4, 3, 1, 2, 1]
+    assert r["sssp_preds"] == [-1, 0, 0, 2, 2, 2, 5]
+    assert golden("ref_fixture_sssp_undirected.json")["sssp_preds"] == [-1, 0, 0, 2, 5, 2, 5]
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_bfs_and_sssp_on_reference_fixtures(name, golden):
+    rec = golden(name)
+    g = _csr_from(rec)
+    assert oracle.bfs(g, rec["src"]).tolist() == rec["bfs_labels"]
+    preds, dist_i = oracle.sssp_ref_preds(g, rec["src"])
+    assert preds.tolist() == rec["sssp_preds"]
+    # distances: Dijkstra under the GPU functor's rule == the reference cpu()'s int distances
+    d = oracle.sssp_dist(g, rec["src"])
+    reach = dist_i != np.iinfo(np.int32).max
+    assert np.array_equal(d[reach], dist_i[reach].astype(np.float32))
+    assert np.all(d[~reach] == np.finfo(np.float32).max)
+
+
+def test_sssp_distances_known(golden):
+    g = _csr_from(golden("ref_fixture_sssp_directed.json"))
+    assert oracle.sssp_dist(g, 0).tolist() == [0, 3, 1, 2, 6, 3, 4]
+    g = _csr_from(golden("ref_fixture_sssp_undirected.json"))
+    assert oracle.sssp_dist(g, 0).tolist() == [0, 3, 1, 2, 4, 3, 4]
+
+
+@pytest.mark.parametrize("name", RMATS)
+def test_rmat_generator_and_traversals_match_golden(name, golden):
+    rec = golden(name)
+    g = oracle.rmat_csr(rec["scale"], rec["edge_factor"], rec["seed"], weighted=True, wseed=rec["wseed"])
+    assert g.n == rec["n"] and g.m == rec["m"] == 2 * rec["edge_factor"] << rec["scale"]
+    sha = hashlib.sha256(g.offsets.tobytes() + g.indices.tobytes() + g.weights.tobytes()).hexdigest()
+    assert sha == rec["csr_sha256"]
+    labels = oracle.bfs(g, rec["src"])
+    assert hashlib.sha256(labels.tobytes()).hexdigest() == rec["bfs_labels_sha256"]
+    assert np.bincount(labels + 1).tolist() == rec["bfs_labels_hist"]
+    preds, _ = oracle.sssp_ref_preds(g, rec["src"])
+    assert hashlib.sha256(preds.tobytes()).hexdigest() == rec["sssp_preds_sha256"]
+    if rec["bfs_labels"] is not None:
+        assert labels.tolist() == rec["bfs_labels"] and preds.tolist() == rec["sssp_preds"]
+
+
+def test_rmat_csr_structure():
+    g = oracle.rmat_csr(9, 16, 1, weighted=True)
+    n, m = g.n, g.m
+    assert g.offsets[0] == 0 and g.offsets[-1] == m and np.all(np.diff(g.offsets) >= 0)
+    rows = np.repeat(np.arange(n), np.diff(g.offsets))
+    key = rows.astype(np.int64) << 32 | g.indices
+    assert np.all(np.diff(key) >= 0)                              # sorted by (src, dst)
+    rkey = np.sort(g.indices.astype(np.int64) << 32 | rows)
+    assert np.array_equal(np.sort(key), rkey)                     # symmetric multiset
+    assert g.weights.min() >= 1 and g.weights.max() <= 64 and np.all(g.weights == np.floor(g.weights))
+    # same weight both directions
+    w_fwd = dict(zip(key.tolist(), g.weights.tolist()))
+    for k in list(w_fwd)[:2000]:
+        assert w_fwd[k] == w_fwd[(k & 0xFFFFFFFF) << 32 | k >> 32]
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_live_against_compiled_reference(seed):
+    g = oracle.rmat_csr(11, 8, seed, weighted=True)
+    for src in (0, 1, 17):
+        ref_labels, _ = oracle.ref_bfs(g, src)
+        assert np.array_equal(oracle.bfs(g, src), ref_labels)
+        ref_preds, _ = oracle.ref_sssp_preds(g, src)
+        assert np.array_equal(oracle.sssp_ref_preds(g, src)[0], ref_preds)
+
+
+def test_neighborhood_reduce_semantics():
+    """mgpu tests/test_segreduce.cu:40-58: empty segment => init, init not folded into non-empty."""
+    g = oracle.CSR(4, [0, 2, 2, 5, 6], [1, 2, 0, 1, 3, 3])
+    vals = np.array([1.0, 10.0, 100.0, 1000.0])
+    red, asum = oracle.neighborhood_reduce(g, [0, 1, 2, 3, 1], vals, "plus", identity=-1.0)
+    assert red.tolist() == [110.0, -1.0, 1011.0, 1000.0, -1.0]
+    red, _ = oracle.neighborhood_reduce(g, [2, 0], vals, "min", identity=7.0)
+    assert red.tolist() == [1.0, 10.0]
+    red, _ = oracle.neighborhood_reduce(g, [2, 1], vals, "max", identity=7.0)
+    assert red.tolist() == [1000.0, 7.0]
+
+
+def test_pr_driver_on_fixture(golden):
+    """pr_enactor.hxx:41-77 restated; iteration 0 (frontier = iota) is mode independent."""
+    g = _csr_from(golden("ref_fixture_pr.json"))
+    cur_a, red_a, lens_a = oracle.pr(g, 1, scatter=False)
+    cur_b, red_b, lens_b = oracle.pr(g, 1, scatter=True)
+    assert np.array_equal(cur_a, cur_b) and np.array_equal(red_a, red_b)
+    deg = np.diff(g.offsets).astype(np.float32)
+    assert np.allclose(red_a, 0.15 * deg)
+    assert np.allclose(cur_a, 0.15 + 0.85 * 0.15)
+    cur, red, lens = oracle.pr(g, 50, scatter=True)
+    assert len(lens) <= 50 and np.all(np.isfinite(cur))
+
+
+def test_push_level_restates_bfs():
+    g = oracle.rmat_csr(10, 16, 1)
+    labels = np.full(g.n, -1, np.int32)
+    labels[0] = 0
+    f = np.array([0], np.int32)
+    it = 0
+    while len(f):
+        f = oracle.bfs_push_level(g, f, it, labels)
+        it += 1
+    assert np.array_equal(labels, oracle.bfs(g, 0))
