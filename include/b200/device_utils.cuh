@@ -1,0 +1,57 @@
+// device_utils.cuh -- warp / memory helpers shared by the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+__device__ __forceinline__ unsigned lane_id() {
+    unsigned r;
+    asm("mov.u32 %0, %%laneid;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned r;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(r));
+    return r;
+}
+
+// Streaming read of data touched once per kernel (column indices, weights):
+// read-only path, do not allocate in L1 so the probe working set keeps it.
+__device__ __forceinline__ int ld_stream(const int *p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int4 ld_stream_v4(const int4 *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL_MASK, v, d);
+    return v;
+}
+
+template <typename T>
+__host__ __device__ __forceinline__ T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+}  // namespace b200

@@ -1,0 +1,116 @@
+// lbs.cuh -- merge-path load-balanced search over (arcs x frontier segments).
+//
+// Replaces mgpu load_balance_partitions + transform_lbs
+// (kernel_load_balance.hxx:10-62, cta_load_balance.hxx:17-183, search.hxx:14-37):
+//   * the work list is the merge of the arc indices 0..m_F-1 with the scanned
+//     segment starts; it is cut into gridDim.x equal CONTIGUOUS chunks, so a CTA
+//     does one merge-path binary search for each end of its chunk (no separate
+//     partition kernel, no `mp` allocation) and then walks its chunk tile by tile;
+//   * per tile the segment starts, the source vertex and (row_offset - start) of
+//     up to SEG_T segments are staged in shared memory; an arc finds its segment
+//     with a binary search over that staged slice;
+//   * arcs are assigned to threads strided by NT, so the 32 lanes of a warp read
+//     32 consecutive column indices (one 128-byte line) whenever they sit in the
+//     same segment;
+//   * m_F is read from device memory (written by the degree scan), so the host
+//     never has to know it to size the launch: the grid is persistent.
+#pragma once
+#include "device_utils.cuh"
+
+namespace b200 {
+
+struct LbsArgs {
+    const int *frontier;               // [num_segments] vertex ids
+    uint32_t num_segments;             // |F|
+    const uint32_t *scanned;           // [num_segments] exclusive scan of degrees
+    const unsigned long long *total;   // device: m_F
+    const uint32_t *offsets;           // row (push) or column (pull) offsets [n+1]
+    const int *indices;                // col (push) or row (pull) indices [m]
+    uint32_t min_chunk;                // lower bound on the work items per CTA
+};
+
+template <int NT, int VT, int SEG_T>
+struct LbsSmem {
+    uint32_t start[SEG_T];   // scanned start of staged segment j
+    uint32_t base[SEG_T];    // offsets[vertex_j] - start_j  (so edge_id = base + arc)
+    int vert[SEG_T];         // vertex_j
+    uint32_t bounds[4];      // s0, a0, s1, a1
+    uint32_t a_end, s_next;
+};
+
+// Number of segment starts that precede diagonal d in the merged order
+// ("segment start s goes before arc a iff scanned[s] <= a").
+__device__ __forceinline__ uint32_t merge_path_segments(const uint32_t *scanned, uint32_t num_segments,
+                                                        unsigned long long m, unsigned long long d) {
+    unsigned long long lo = d > m ? d - m : 0ull;
+    unsigned long long hi = d < (unsigned long long)num_segments ? d : (unsigned long long)num_segments;
+    while (lo < hi) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if ((unsigned long long)__ldg(scanned + mid) <= d - 1 - mid) lo = mid + 1;
+        else hi = mid;
+    }
+    return (uint32_t)lo;
+}
+
+// Largest j in [0, ns) with start[j] <= arc.  Requires start[0] <= arc.
+__device__ __forceinline__ int lbs_locate(const uint32_t *start, int ns, uint32_t arc) {
+    int lo = 0, hi = ns;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (start[mid] <= arc) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// Walks this CTA's chunk.  For every tile calls
+//     body(first_arc, n_arcs (<= NT*VT), ns (staged segments), first_seg)
+// with the staged slice valid in `sm`; body is called by ALL threads and must
+// end with the CTA converged (it may __syncthreads()).
+template <int NT, int VT, int SEG_T, class Body>
+__device__ __forceinline__ void lbs_for_each_tile(const LbsArgs &a, LbsSmem<NT, VT, SEG_T> &sm, Body body) {
+    constexpr uint32_t ARC_T = NT * VT;
+    const unsigned long long m = *a.total;
+    const unsigned long long work = m + a.num_segments;
+    unsigned long long chunk = ceil_div<unsigned long long>(work, gridDim.x);
+    if (chunk < a.min_chunk) chunk = a.min_chunk;
+    const unsigned long long d0 = (unsigned long long)blockIdx.x * chunk;
+    if (d0 >= work || m == 0) return;
+    const unsigned long long d1 = d0 + chunk < work ? d0 + chunk : work;
+    if (threadIdx.x == 0 || threadIdx.x == 32) {
+        const unsigned long long d = threadIdx.x == 0 ? d0 : d1;
+        const uint32_t s = merge_path_segments(a.scanned, a.num_segments, m, d);
+        sm.bounds[threadIdx.x ? 2 : 0] = s;
+        sm.bounds[threadIdx.x ? 3 : 1] = (uint32_t)(d - s);
+    }
+    __syncthreads();
+    const uint32_t s0 = sm.bounds[0], a0 = sm.bounds[1], s1 = sm.bounds[2], a1 = sm.bounds[3];
+    if (a0 >= a1) return;
+    uint32_t cur_s = s0 > 0 ? s0 - 1 : 0;   // segment that contains arc a0
+    uint32_t cur_a = a0;
+    while (cur_a < a1) {
+        const int ns = (int)min((uint32_t)SEG_T, s1 - cur_s);
+        for (int j = threadIdx.x; j < ns; j += NT) {
+            const uint32_t st = __ldg(a.scanned + cur_s + j);
+            const int v = __ldg(a.frontier + cur_s + j);
+            sm.start[j] = st;
+            sm.vert[j] = v;
+            sm.base[j] = __ldg(a.offsets + v) - st;
+        }
+        if (threadIdx.x == 0) {
+            // arcs of segments that are not staged must wait for the next tile
+            uint32_t lim = (cur_s + (uint32_t)ns < s1) ? __ldg(a.scanned + cur_s + ns) : a1;
+            uint32_t e = a1 - cur_a > ARC_T ? cur_a + ARC_T : a1;
+            sm.a_end = e < lim ? e : lim;
+        }
+        __syncthreads();
+        const uint32_t a_end = sm.a_end;
+        body(cur_a, a_end - cur_a, ns, cur_s);
+        if (threadIdx.x == 0) sm.s_next = cur_s + (uint32_t)lbs_locate(sm.start, ns, a_end);
+        __syncthreads();
+        cur_s = sm.s_next;   // (the next write of s_next / a_end / start[] is ordered by the sync above
+        cur_a = a_end;       //  and by the staging sync of the next iteration)
+    }
+}
+
+}  // namespace b200

@@ -1,0 +1,134 @@
+// operators.cuh -- host-side launchers of the kernel templates.
+//
+// Instantiated (a) inside libb200_frontier.so with the built-in functors behind
+// the C ABI and (b) in the caller's translation unit by include/gunrock/*.hxx
+// with user functors (device functors cannot cross a C ABI).  Both use the
+// ctx-owned b200_workspace, so no launcher allocates.
+#pragma once
+#include <cuda_runtime.h>
+#include "advance.cuh"
+#include "segreduce.cuh"
+#include "tile_scan.cuh"
+#include "workspace.h"
+
+namespace b200 {
+
+constexpr int SCAN_NT = 256, SCAN_VT = 4;
+constexpr int COMPACT_NT = 256, COMPACT_VT = 8;
+constexpr int LBS_NT = 256, LBS_VT = 8, LBS_SEG_T = 512;
+constexpr uint32_t LBS_MIN_CHUNK = 2048;
+
+inline cudaStream_t ws_stream(const b200_workspace *ws) { return (cudaStream_t)ws->stream; }
+
+inline cudaError_t reset_counters(b200_workspace *ws) {
+    return cudaMemsetAsync(ws->d_counters, 0, sizeof(unsigned long long) * B200_NUM_COUNTERS, ws_stream(ws));
+}
+// Device counters -> pinned host mirror; synchronises the ctx stream.
+inline cudaError_t read_counters(b200_workspace *ws) {
+    cudaError_t e = cudaMemcpyAsync(ws->h_counters, ws->d_counters, sizeof(unsigned long long) * B200_NUM_COUNTERS,
+                                    cudaMemcpyDeviceToHost, ws_stream(ws));
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(ws_stream(ws));
+}
+
+inline LookbackState next_lookback(b200_workspace *ws, uint32_t num_tiles) {
+    ws->epoch = (ws->epoch + 1) & 0x3FFFFFFFu;
+    if (ws->epoch == 0) {   // wrapped: stale entries could alias, wipe them
+        cudaMemsetAsync(ws->d_status, 0, sizeof(unsigned long long) * (size_t)ws->status_tiles, ws_stream(ws));
+        ws->epoch = 1;
+    }
+    LookbackState st;
+    st.status = ws->d_status;
+    st.tile_counter = ws->d_tile_counter;
+    st.epoch = ws->epoch;
+    st.num_tiles = num_tiles;
+    return st;
+}
+
+// exclusive scan of fn(0..count) -> out, total -> *d_total.  count > 0.
+template <class SizeFn>
+cudaError_t launch_scan(b200_workspace *ws, SizeFn fn, uint32_t count, uint32_t *d_out, unsigned long long *d_total) {
+    const uint32_t tiles = ceil_div<uint32_t>(count, SCAN_NT * SCAN_VT);
+    if ((int64_t)tiles > ws->status_tiles) return cudaErrorInvalidValue;
+    scan_sizes_kernel<SCAN_NT, SCAN_VT><<<tiles, SCAN_NT, 0, ws_stream(ws)>>>(fn, count, d_out, next_lookback(ws, tiles), d_total);
+    ws->launches++;
+    return cudaGetLastError();
+}
+
+template <class Pred>
+cudaError_t launch_compact(b200_workspace *ws, Pred pred, uint32_t count, int *d_out, unsigned long long capacity,
+                           unsigned long long *d_total, unsigned long long *d_overflow) {
+    const uint32_t tiles = ceil_div<uint32_t>(count, COMPACT_NT * COMPACT_VT);
+    if ((int64_t)tiles > ws->status_tiles) return cudaErrorInvalidValue;
+    compact_kernel<COMPACT_NT, COMPACT_VT><<<tiles, COMPACT_NT, 0, ws_stream(ws)>>>(
+        pred, count, d_out, capacity, next_lookback(ws, tiles), d_total, d_overflow);
+    ws->launches++;
+    return cudaGetLastError();
+}
+
+// Persistent grid: resident CTAs per SM (queried once per instantiation) x SMs.
+// Tag makes the cached occupancy unique per kernel instantiation (kernels that differ
+// only in non-type template arguments share one function-pointer type).
+template <class Tag, class Kernel>
+int persistent_grid(Kernel k, int nt, const b200_workspace *ws) {
+    static int per_sm = 0;   // per <Tag, Kernel> instantiation
+    if (per_sm == 0) {
+        int b = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k, nt, 0) != cudaSuccess || b < 1) b = 1;
+        per_sm = b;
+    }
+    return per_sm * ws->num_sms;
+}
+
+template <class Op, int OUT_MODE, bool DEG_SUM> struct AdvTag {};
+template <class Value, class ROp, class ValueFn> struct SegTag {};
+
+struct FrontierDegree {
+    const int *frontier;
+    const uint32_t *offsets;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
+        const int v = frontier[i];
+        return v >= 0 ? __ldg(offsets + v + 1) - __ldg(offsets + v) : 0u;
+    }
+};
+
+inline LbsArgs make_lbs_args(const b200_workspace *ws, const int *d_frontier, uint32_t len,
+                             const uint32_t *offsets, const int *indices) {
+    LbsArgs a;
+    a.frontier = d_frontier;
+    a.num_segments = len;
+    a.scanned = ws->d_scanned;
+    a.total = ws->d_counters + B200_CNT_TOTAL;
+    a.offsets = offsets;
+    a.indices = indices;
+    a.min_chunk = LBS_MIN_CHUNK;
+    return a;
+}
+
+// degree scan of the frontier into ws->d_scanned, m_F into counters[TOTAL].
+inline cudaError_t launch_frontier_scan(b200_workspace *ws, const int *d_frontier, uint32_t len, const uint32_t *offsets) {
+    if ((int64_t)len > ws->scanned_capacity) return cudaErrorInvalidValue;
+    FrontierDegree fn{d_frontier, offsets};
+    return launch_scan(ws, fn, len, ws->d_scanned, ws->d_counters + B200_CNT_TOTAL);
+}
+
+// LBS advance over a frontier whose degree scan is already in the workspace.
+template <int OUT_MODE, bool DEG_SUM, class Op>
+cudaError_t launch_lbs_advance(b200_workspace *ws, const LbsArgs &a, Op op, int *d_out, unsigned long long capacity) {
+    auto k = lbs_advance_kernel<Op, OUT_MODE, DEG_SUM, LBS_NT, LBS_VT, LBS_SEG_T>;
+    const int grid = persistent_grid<AdvTag<Op, OUT_MODE, DEG_SUM>>(k, LBS_NT, ws);
+    k<<<grid, LBS_NT, 0, ws_stream(ws)>>>(a, op, d_out, capacity, ws->d_counters);
+    ws->launches++;
+    return cudaGetLastError();
+}
+
+template <class Value, class ROp, class ValueFn>
+cudaError_t launch_lbs_segreduce(b200_workspace *ws, const LbsArgs &a, ValueFn vf, Value *d_reduced, int scatter) {
+    auto k = lbs_segreduce_kernel<Value, ROp, ValueFn, LBS_NT, LBS_VT, LBS_SEG_T>;
+    const int grid = persistent_grid<SegTag<Value, ROp, ValueFn>>(k, LBS_NT, ws);
+    k<<<grid, LBS_NT, 0, ws_stream(ws)>>>(a, vf, d_reduced, scatter);
+    ws->launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace b200

@@ -1,0 +1,242 @@
+/*
+ * b200_frontier.h -- thin C ABI of the B200-native frontier-traversal engine.
+ *
+ * This is the drop-in boundary for the one hot path of gunrock/mini: the
+ * advance / filter / neighborhood_reduce operators and the BFS / SSSP / PR-style
+ * primitives built on them.  The reference has NO FFI: its boundary is the
+ * header-only C++ template API in namespace gunrock::oprtr.  The
+ * C++ mirror of that API lives in include/gunrock/ (same type and function
+ * names, so tests/bfs/test_bfs.cu-style drivers compile unchanged) and calls
+ * down into this C ABI; Python (ctypes), the tests and bench.py bind the same
+ * symbols.  Each entry point cites the reference interface it replaces
+ * (file:line relative to the reference tree).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every d_* pointer is DEVICE memory owned
+ *     by the caller, every h_* pointer is HOST memory owned by the caller;
+ *   - every function returns an int status (B200_OK == 0); nothing throws or
+ *     calls exit() across the ABI (the reference printf+exit(0)s on frontier
+ *     overflow, frontier.hxx:53-59,84-89: here that is B200_ERR_OVERFLOW);
+ *   - calls are synchronous at return with respect to their host outputs
+ *     (the reference contract: enactors branch on the returned count,
+ *     advance.hxx:43, kernel_compact.hxx:75-81) and are issued on the ctx
+ *     stream; a ctx is not thread-safe (neither is standard_context_t);
+ *   - row offsets are 4-byte UNSIGNED (bit-compatible with the reference's
+ *     non-negative `int` offsets, graph.hxx:19-26, and able to hold RMAT
+ *     scale-26's 2^31 arcs, which the reference cannot); vertex ids are int32.
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point returns B200_ERR_CUDA.
+ */
+#ifndef B200_FRONTIER_H
+#define B200_FRONTIER_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+
+enum {
+    B200_OK = 0,
+    B200_ERR_CUDA = 1,      /* a CUDA runtime call failed: see b200_last_cuda_error() */
+    B200_ERR_INVALID = 2,   /* bad argument */
+    B200_ERR_OVERFLOW = 3,  /* an output frontier exceeded the capacity the caller gave */
+    B200_ERR_NOMEM = 4,
+    B200_ERR_UNSUPPORTED = 5
+};
+
+typedef struct b200_ctx b200_ctx; /* replaces mgpu::standard_context_t (context.hxx:103-219) + per-call mem_t scratch */
+
+/* Device CSR / CSC view.  Mirrors gunrock::graph_device_t (graph.hxx:37-58);
+ * col_offsets/row_indices/row_values may alias the CSR arrays exactly as
+ * graph_to_device does for symmetric graphs (graph.hxx:75-80). */
+typedef struct b200_graph {
+    int64_t n;                   /* num_nodes */
+    int64_t m;                   /* num_edges (arcs), < 2^32 */
+    const uint32_t *row_offsets; /* d_row_offsets  [n+1] */
+    const int32_t *col_indices;  /* d_col_indices  [m]   */
+    const float *col_values;     /* d_col_values   [m] or NULL */
+    const uint32_t *col_offsets; /* d_col_offsets  [n+1] (CSC) */
+    const int32_t *row_indices;  /* d_row_indices  [m]   (CSC) */
+    const float *row_values;     /* d_row_values   [m] or NULL */
+} b200_graph;
+
+/* Built-in problems = the reference's data_slice_t structs, as one POD.
+ * kind selects the functor the operator entry points apply. */
+enum { B200_PROBLEM_BFS = 1, B200_PROBLEM_SSSP = 2, B200_PROBLEM_PR = 3 };
+typedef struct b200_problem {
+    int32_t kind;
+    int32_t reserved;
+    /* BFS: bfs_problem_t::data_slice_t (bfs_problem.hxx:16-27) */
+    int32_t *labels;        /* d_labels: -1 unvisited, else depth */
+    int32_t *preds;         /* d_preds (BFS: never written by the reference; SSSP: racy last writer) */
+    /* SSSP: sssp_problem_t::data_slice_t (sssp_problem.hxx:19-33) */
+    float *dist;            /* d_labels (float): FLT_MAX unreached */
+    const float *weights;   /* d_weights = gslice->d_col_values */
+    int32_t *visited;       /* d_visited iteration stamps, init -1 */
+    /* PR: pr_problem_t::data_slice_t (pr_problem.hxx:14-25) */
+    float *current_ranks;
+    float *reduced_ranks;
+    float *degrees;
+    /* engine-side visited bitmap (n/32 words, 1 bit per vertex), optional:
+     * the "flexible uniquification" state of filter.hxx:33-119 done right */
+    uint32_t *visited_bitmap;
+} b200_problem;
+
+/* Per-run statistics (new; the reference only prints wall clock, test_bfs.cu:38-42). */
+#define B200_MAX_LEVELS 512
+typedef struct b200_level_stat {
+    int32_t direction;     /* 0 = push, 1 = pull */
+    int32_t reserved;
+    int64_t frontier_len;  /* |F_l| (push) or |U_l| (pull) */
+    int64_t arcs;          /* m_l expanded (push) / in-arcs inspected (pull; counted in-kernel) */
+    int64_t discovered;    /* |F_{l+1}| */
+    float advance_ms;      /* device time of the advance (LBS or pull) kernel alone */
+    float level_ms;        /* device time of the whole level (scan + advance + bookkeeping) */
+} b200_level_stat;
+typedef struct b200_stats {
+    int32_t collect_timing; /* in: nonzero => record per-level CUDA-event timings (adds event overhead) */
+    int32_t num_levels;     /* out */
+    int64_t reached;        /* out: vertices reached */
+    int64_t total_arcs;     /* out: sum of `arcs` over levels */
+    int64_t launches;       /* out: kernels launched by this call */
+    float device_ms;        /* out: device time source-in-frontier -> labels final */
+    float reserved;
+    b200_level_stat level[B200_MAX_LEVELS];
+} b200_stats;
+
+/* ---- library / context ---------------------------------------------------- */
+int b200_abi_version(void);
+const char *b200_status_string(int status);
+int b200_last_cuda_error(void);                 /* cudaError_t of the last failing call on this thread */
+int b200_device_count(int *count);
+
+/* device: CUDA ordinal.  stream: a cudaStream_t to issue on, or NULL to let the
+ * ctx create its own non-blocking stream.  Replaces `standard_context_t context;`
+ * (test_bfs.cu:22; context.hxx:103-110). */
+int b200_ctx_create(b200_ctx **out, int device, void *stream);
+int b200_ctx_destroy(b200_ctx *ctx);
+/* Pre-size the scratch arena so no operator call allocates (the reference
+ * cudaMalloc/cudaFree's 3-6 times per operator call). */
+int b200_ctx_reserve(b200_ctx *ctx, int64_t max_frontier_items);
+int b200_ctx_sync(b200_ctx *ctx);
+int b200_ctx_num_sms(b200_ctx *ctx, int *num_sms);
+/* Keep [ptr, ptr+bytes) L2-resident for kernels on the ctx stream
+ * (cudaAccessPolicyWindow, persisting hits).  bytes = 0 clears the window. */
+int b200_ctx_l2_pin(b200_ctx *ctx, const void *d_ptr, int64_t bytes);
+
+/* ---- synthetic input (the reference has only load_graph, graph.hxx:96-223) */
+/* Symmetrised RMAT(0.57,0.19,0.19,0.05): n = 2^scale, m = 2*edge_factor*2^scale arcs,
+ * duplicates and self loops kept, arcs sorted by (src,dst) -- what graph.hxx:139-172 builds.
+ * d_weights (nullable): integer weights in [1,64] per undirected pair, as exact floats. */
+int b200_rmat_build_csr(b200_ctx *ctx, int scale, int edge_factor, uint64_t seed,
+                        uint32_t *d_row_offsets /* [n+1] */, int32_t *d_col_indices /* [m] */,
+                        float *d_weights /* [m] or NULL */, uint64_t weight_seed);
+/* Same pairs as the above, un-symmetrised, for generator parity tests: d_src/d_dst [edge_factor<<scale] */
+int b200_rmat_pairs(b200_ctx *ctx, int scale, int edge_factor, uint64_t seed, int32_t *d_src, int32_t *d_dst);
+/* CSR from an arbitrary device pair list (symmetrize adds every reverse); same ordering rules. */
+int b200_build_csr_from_pairs(b200_ctx *ctx, int64_t n, int64_t npairs, const int32_t *d_src,
+                              const int32_t *d_dst, int symmetrize, uint32_t *d_row_offsets,
+                              int32_t *d_col_indices, float *d_weights, uint64_t weight_seed);
+
+/* ---- operators with the built-in functors --------------------------------- */
+enum { B200_ADV_IDEMPOTENT = 1, B200_ADV_NO_OUTPUT = 2, B200_ADV_RAW_OUTPUT = 4 };
+
+/* advance_forward_kernel<Problem,Functor,idempotence,has_output> (advance.hxx:20-67).
+ * Expands the out-arcs of d_in[0..in_len) with a merge-path load-balanced search and
+ * applies the problem's cond_advance/apply_advance (bfs_functor.hxx:26-33,
+ * sssp_functor.hxx:20-34).  Default output is the COMPACTED list of accepted
+ * neighbours (advance + the `!= -1` filter fused, written with CTA-aggregated
+ * appends); B200_ADV_RAW_OUTPUT reproduces the reference layout out[idx] = nbr | -1
+ * for idx in [0, m_F).  *out_len = items written, *arcs = m_F. */
+int b200_advance_forward(b200_ctx *ctx, const b200_graph *g, const b200_problem *p,
+                         const int32_t *d_in, int64_t in_len, int32_t *d_out, int64_t out_capacity,
+                         int iteration, int flags, int64_t *out_len, int64_t *arcs);
+
+/* filter_kernel<Problem,Functor> (filter.hxx:11-31): stable compaction of the items
+ * for which cond_filter holds (bfs_functor.hxx:9-11, sssp_functor.hxx:12-18,
+ * pr_functor.hxx:11-17; predicates run exactly once per item, side effects included). */
+int b200_filter(b200_ctx *ctx, const b200_graph *g, const b200_problem *p, const int32_t *d_in,
+                int64_t in_len, int32_t *d_out, int64_t out_capacity, int iteration, int64_t *out_len);
+
+/* uniquify_kernel<Problem,ProblemFunctor> (filter.hxx:95-119): drops -1 and every
+ * vertex already in the visited bitmap (1 bit per vertex, [ceil(n/32)] words, exact
+ * test-and-set instead of the reference's heuristic culls), marks survivors and,
+ * for BFS, labels them iteration+1 (bfs_functor.hxx:13-24).  Correct for any source. */
+int b200_uniquify(b200_ctx *ctx, const b200_graph *g, const b200_problem *p, uint32_t *d_visited_bitmap,
+                  const int32_t *d_in, int64_t in_len, int32_t *d_out, int64_t out_capacity,
+                  int iteration, int64_t *out_len);
+
+/* sparse_to_dense_kernel (advance.hxx:69-84): frontier list -> 1-bit-per-vertex bitmap
+ * (the reference uses one int per vertex, bfs_enactor.hxx:83). bitmap is cleared first. */
+int b200_sparse_to_dense(b200_ctx *ctx, int64_t n, const int32_t *d_sparse, int64_t len, uint32_t *d_bitmap);
+/* inverse; order is ascending vertex id. */
+int b200_dense_to_sparse(b200_ctx *ctx, int64_t n, const uint32_t *d_bitmap, int32_t *d_sparse,
+                         int64_t capacity, int64_t *out_len);
+/* gen_unvisited_kernel (advance.hxx:86-106) for BFS: {v : labels[v] == -1}, ascending. */
+int b200_gen_unvisited(b200_ctx *ctx, const b200_problem *p, int64_t n, int32_t *d_unvisited,
+                       int64_t capacity, int64_t *out_len);
+/* advance_backward_kernel (advance.hxx:108-160), BFS pull step over a bitmap frontier:
+ * every vertex with visited bit clear scans its in-arcs (CSC) and stops at the first
+ * in-neighbour whose bit is set in d_frontier_bitmap; it is then labelled iteration+1,
+ * set in d_next_bitmap and in the visited bitmap.  *discovered = |F_next|,
+ * *arcs_inspected = in-arcs actually read. */
+int b200_advance_backward(b200_ctx *ctx, const b200_graph *g, const b200_problem *p,
+                          const uint32_t *d_frontier_bitmap, uint32_t *d_next_bitmap, int iteration,
+                          int64_t *discovered, int64_t *arcs_inspected);
+
+/* neighborhood_kernel<Problem,Functor,Value,reduce_op,has_output,push> (neighborhood.hxx:12-70)
+ * for Value = float: d_reduced[slot] = op over the (push: out / pull: in) neighbours u of
+ * d_in[slot] of d_values[u] (non-finite values read as 0, pr_functor.hxx:27-29); identity
+ * when the neighbourhood is empty and never folded into non-empty ones
+ * (mgpu tests/test_segreduce.cu:40-58).  scatter != 0 writes d_reduced[vertex] instead
+ * (write_reduced_value, neighborhood.hxx:60-67).  fp32 sum order is unspecified:
+ * callers compare within 1e-5 * sum|terms| + 1e-6. */
+enum { B200_OP_PLUS = 0, B200_OP_MIN = 1, B200_OP_MAX = 2 };
+int b200_neighborhood_reduce_f32(b200_ctx *ctx, const b200_graph *g, const int32_t *d_in, int64_t in_len,
+                                 const float *d_values, float *d_reduced, float identity, int op,
+                                 int push, int scatter, int64_t *arcs);
+
+/* ---- whole primitives (device-resident inputs) ----------------------------- */
+enum { B200_BFS_PUSH = 0,       /* reference default: alpha = 1/n never switches (test_bfs.cu:30) */
+       B200_BFS_REF_ALPHA = 1,  /* bfs_enactor.hxx:68: one-way push->pull when unvisited < |F|*alpha */
+       B200_BFS_BEAMER = 2 };   /* direction-optimising both ways: m_F > m_unvisited/alpha -> pull; |F| < n/beta -> push */
+
+/* bfs_enactor_t::enact_pushpull (bfs_enactor.hxx:41-117) + bfs_problem_t ctor
+ * (bfs_problem.hxx:34-46: labels = -1, labels[src] = 0).  d_labels [n] is fully overwritten. */
+int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, float alpha, float beta,
+                 int32_t *d_labels, b200_stats *stats /* nullable */);
+
+/* sssp_enactor_t::enact (sssp_enactor.hxx:40-72) + sssp_problem_t ctor
+ * (sssp_problem.hxx:40-52: labels = FLT_MAX, labels[src] = 0, preds = -1).
+ * d_dist [n] overwritten; d_preds nullable. */
+int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist, int32_t *d_preds,
+                  b200_stats *stats /* nullable */);
+
+/* pr_enactor_t::enact (pr_enactor.hxx:41-79) + pr_problem_t ctor (pr_problem.hxx:34-44).
+ * scatter = 0 reproduces the reference's slot-indexed reduced[],
+ * scatter = 1 is the intended vertex-indexed form.  d_current/d_reduced [n] overwritten;
+ * h_frontier_lens (nullable, max_iter entries) gets each iteration's output length. */
+int b200_pr_run(b200_ctx *ctx, const b200_graph *g, int max_iter, int scatter, float *d_current,
+                float *d_reduced, int64_t *h_frontier_lens, int *iterations, b200_stats *stats);
+
+/* ---- host-buffer entry points (what test_bfs.cu times + extract: H2D, run, D2H) */
+typedef struct b200_host_graph b200_host_graph; /* graph_to_device result (graph.hxx:60-83) kept by the engine */
+int b200_host_graph_upload(b200_ctx *ctx, int64_t n, int64_t m, const uint32_t *h_row_offsets,
+                           const int32_t *h_col_indices, const float *h_col_values /* nullable */,
+                           b200_host_graph **out);
+int b200_host_graph_free(b200_ctx *ctx, b200_host_graph *hg);
+int b200_host_graph_view(const b200_host_graph *hg, b200_graph *out);
+/* bfs_problem_t(graph, src) [H2D of the initial labels] + enact_pushpull + extract() [D2H]:
+ * h_labels_init (nullable => engine builds labels on device) / h_labels_out are pinned or pageable host arrays. */
+int b200_bfs_host(b200_ctx *ctx, b200_host_graph *hg, int32_t src, int mode, float alpha, float beta,
+                  const int32_t *h_labels_init, int32_t *h_labels_out, b200_stats *stats);
+int b200_sssp_host(b200_ctx *ctx, b200_host_graph *hg, int32_t src, const float *h_dist_init,
+                   float *h_dist_out, int32_t *h_preds_out, b200_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_FRONTIER_H */

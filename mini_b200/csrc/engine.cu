@@ -1,0 +1,658 @@
+// engine.cu -- C-ABI operators and primitives with the built-in functors.
+// Each entry point cites the reference interface it replaces in
+// include/b200_frontier.h.  All kernels come from include/b200/*.cuh.
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include "b200/operators.cuh"
+#include "engine.cuh"
+
+using namespace b200;
+
+namespace {
+
+// ----------------------------------------------------------------- small kernels
+__global__ void bfs_init_kernel(int32_t *labels, uint32_t *visited, int32_t *frontier, int src) {
+    labels[src] = 0;
+    visited[src >> 5] |= 1u << (src & 31);
+    frontier[0] = src;
+}
+__global__ void sssp_init_kernel(float *dist, int32_t *preds, int32_t *stamp, unsigned long long n) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        dist[i] = FLT_MAX;
+        if (preds) preds[i] = -1;
+        stamp[i] = -1;
+    }
+}
+__global__ void sssp_seed_kernel(float *dist, int32_t *frontier, int src) {
+    dist[src] = 0.0f;
+    frontier[0] = src;
+}
+__global__ void pr_init_kernel(float *current, float *reduced, int32_t *frontier, unsigned long long n) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        current[i] = 0.15f;
+        reduced[i] = 0.0f;
+        frontier[i] = (int32_t)i;
+    }
+}
+// ----------------------------------------------------------------- compaction predicates
+// cond_filter of bfs_functor_t (bfs_functor.hxx:9-11)
+struct BfsFilterPred {
+    const int *in;
+    __device__ __forceinline__ bool operator()(uint32_t idx, int &item) const {
+        item = in[idx];
+        return item != -1;
+    }
+};
+// cond_filter of sssp_functor_t (sssp_functor.hxx:12-18); the stamp test-and-set is made atomic
+struct SsspFilterPred {
+    const int *in;
+    int *stamp;
+    int iteration;
+    __device__ __forceinline__ bool operator()(uint32_t idx, int &item) const {
+        item = in[idx];
+        if (item == -1) return false;
+        return atomicExch(stamp + item, iteration) != iteration;
+    }
+};
+// cond_filter of pr_functor_t (pr_functor.hxx:11-17); degrees == NULL => computed from the offsets
+struct PrFilterPred {
+    const int *in;
+    float *current;
+    const float *reduced;
+    const float *degrees;
+    const uint32_t *offsets;
+    __device__ __forceinline__ bool operator()(uint32_t idx, int &item) const {
+        item = in[idx];
+        const float old_value = current[item];
+        const float deg = degrees ? degrees[item] : (float)(offsets[item + 1] - offsets[item]);
+        float new_value = (deg > 0) ? (0.15f + 0.85f * reduced[item] / deg) : 0.15f;
+        if (!isfinite(new_value)) new_value = 0;
+        current[item] = new_value;
+        return fabsf(new_value - old_value) > (0.001f * old_value);
+    }
+};
+// uniquify (filter.hxx:95-119) with an exact bitmap test-and-set; BFS also labels (bfs_functor.hxx:13-24)
+struct UniquifyPred {
+    const int *in;
+    uint32_t *visited;
+    int *labels;   // nullable
+    int label;
+    __device__ __forceinline__ bool operator()(uint32_t idx, int &item) const {
+        item = in[idx];
+        if (item < 0) return false;
+        const uint32_t bit = 1u << (item & 31);
+        if ((visited[item >> 5] & bit) || (atomicOr(visited + (item >> 5), bit) & bit)) return false;
+        if (labels) labels[item] = label;
+        return true;
+    }
+};
+struct UnvisitedPred {   // cond_gen_unvisited (bfs_functor.hxx:39-41) over iota(n)
+    const int *labels;
+    __device__ __forceinline__ bool operator()(uint32_t idx, int &item) const {
+        item = (int)idx;
+        return labels[idx] == -1;
+    }
+};
+struct BitmapPred {
+    const uint32_t *bitmap;
+    __device__ __forceinline__ bool operator()(uint32_t idx, int &item) const {
+        item = (int)idx;
+        return (bitmap[idx >> 5] >> (idx & 31)) & 1u;
+    }
+};
+
+// get_value_to_reduce of pr_functor_t (pr_functor.hxx:27-29)
+struct FiniteValueFn {
+    const float *values;
+    __device__ __forceinline__ float operator()(int, int nbr, uint32_t) const {
+        const float x = values[nbr];
+        return isfinite(x) ? x : 0.0f;
+    }
+};
+
+int check_counts(b200_ctx *ctx, int64_t len) {
+    if (len < 0 || len >= (1ll << 32)) return B200_ERR_INVALID;
+    return b200_ctx_reserve(ctx, len);
+}
+
+int run_compact_result(b200_ctx *ctx, int64_t *out_len) {
+    B200_CUDA(read_counters(&ctx->ws));
+    if (out_len) *out_len = (int64_t)ctx->ws.h_counters[B200_CNT_OUT];
+    return ctx->ws.h_counters[B200_CNT_OVERFLOW] ? B200_ERR_OVERFLOW : B200_OK;
+}
+
+template <class Pred>
+int compact_op(b200_ctx *ctx, Pred pred, int64_t len, int32_t *d_out, int64_t cap, int64_t *out_len) {
+    if (len == 0) {
+        if (out_len) *out_len = 0;
+        return B200_OK;
+    }
+    B200_TRY(check_counts(ctx, len));
+    b200_workspace *ws = &ctx->ws;
+    B200_CUDA(cudaSetDevice(ws->device));
+    B200_CUDA(reset_counters(ws));
+    B200_CUDA(launch_compact(ws, pred, (uint32_t)len, d_out, (unsigned long long)cap, ws->d_counters + B200_CNT_OUT,
+                             ws->d_counters + B200_CNT_OVERFLOW));
+    return run_compact_result(ctx, out_len);
+}
+
+cudaEvent_t *level_events(b200_ctx *ctx) {
+    if (!ctx->ev_level) {
+        const int cnt = 3 * B200_MAX_LEVELS + 3;
+        ctx->ev_level = new cudaEvent_t[cnt];
+        for (int i = 0; i < cnt; ++i) cudaEventCreate(&ctx->ev_level[i]);
+        ctx->ev_level_count = cnt;
+    }
+    return ctx->ev_level;
+}
+
+void finish_level_timing(b200_ctx *ctx, b200_stats *stats) {
+    if (!stats || !stats->collect_timing) return;
+    cudaEvent_t *ev = ctx->ev_level;
+    const int L = stats->num_levels < B200_MAX_LEVELS ? stats->num_levels : B200_MAX_LEVELS;
+    for (int l = 0; l < L; ++l) {
+        cudaEventElapsedTime(&stats->level[l].advance_ms, ev[3 * l + 1], ev[3 * l + 2]);
+        cudaEventElapsedTime(&stats->level[l].level_ms, ev[3 * l], ev[3 * l + 3]);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// ============================================================== operators
+int b200_advance_forward(b200_ctx *ctx, const b200_graph *g, const b200_problem *p, const int32_t *d_in,
+                         int64_t in_len, int32_t *d_out, int64_t out_capacity, int iteration, int flags,
+                         int64_t *out_len, int64_t *arcs) {
+    if (!ctx || !g || !p || in_len < 0 || (in_len && !d_in)) return B200_ERR_INVALID;
+    if (out_len) *out_len = 0;
+    if (arcs) *arcs = 0;
+    if (in_len == 0) return B200_OK;
+    const bool no_out = flags & B200_ADV_NO_OUTPUT, raw = flags & B200_ADV_RAW_OUTPUT, idem = flags & B200_ADV_IDEMPOTENT;
+    if (!no_out && !d_out) return B200_ERR_INVALID;
+    B200_TRY(check_counts(ctx, in_len));
+    b200_workspace *ws = &ctx->ws;
+    B200_CUDA(cudaSetDevice(ws->device));
+    B200_CUDA(reset_counters(ws));
+    B200_CUDA(launch_frontier_scan(ws, d_in, (uint32_t)in_len, g->row_offsets));
+    const LbsArgs a = make_lbs_args(ws, d_in, (uint32_t)in_len, g->row_offsets, g->col_indices);
+    const unsigned long long cap = (unsigned long long)out_capacity;
+    cudaError_t e = cudaErrorInvalidValue;
+    if (p->kind == B200_PROBLEM_BFS) {
+        if (idem) {
+            if (!p->visited_bitmap) return B200_ERR_INVALID;
+            BfsIdempotentOp op{p->visited_bitmap};
+            e = no_out ? launch_lbs_advance<OUT_NONE, false>(ws, a, op, d_out, cap)
+                       : raw ? launch_lbs_advance<OUT_RAW, false>(ws, a, op, d_out, cap)
+                             : launch_lbs_advance<OUT_COMPACT, false>(ws, a, op, d_out, cap);
+        } else {
+            if (!p->visited_bitmap || !p->labels) return B200_ERR_INVALID;
+            BfsPushOp op{p->visited_bitmap, p->labels, iteration + 1};
+            e = no_out ? launch_lbs_advance<OUT_NONE, false>(ws, a, op, d_out, cap)
+                       : raw ? launch_lbs_advance<OUT_RAW, false>(ws, a, op, d_out, cap)
+                             : launch_lbs_advance<OUT_COMPACT, false>(ws, a, op, d_out, cap);
+        }
+    } else if (p->kind == B200_PROBLEM_SSSP) {
+        if (!p->dist || !p->weights) return B200_ERR_INVALID;
+        // idempotent => duplicates are kept in the output and b200_filter dedupes (config 3);
+        // otherwise the visited stamp is applied inside the advance.
+        SsspRelaxOp op{p->dist, p->weights, p->preds, idem ? nullptr : p->visited, iteration};
+        if (!idem && !p->visited) return B200_ERR_INVALID;
+        e = no_out ? launch_lbs_advance<OUT_NONE, false>(ws, a, op, d_out, cap)
+                   : raw ? launch_lbs_advance<OUT_RAW, false>(ws, a, op, d_out, cap)
+                         : launch_lbs_advance<OUT_COMPACT, false>(ws, a, op, d_out, cap);
+    } else {
+        return B200_ERR_UNSUPPORTED;
+    }
+    B200_CUDA(e);
+    B200_CUDA(read_counters(ws));
+    if (arcs) *arcs = (int64_t)ws->h_counters[B200_CNT_TOTAL];
+    if (out_len) *out_len = no_out ? 0 : (int64_t)ws->h_counters[B200_CNT_OUT];
+    return ws->h_counters[B200_CNT_OVERFLOW] ? B200_ERR_OVERFLOW : B200_OK;
+}
+
+int b200_filter(b200_ctx *ctx, const b200_graph *g, const b200_problem *p, const int32_t *d_in, int64_t in_len,
+                int32_t *d_out, int64_t out_capacity, int iteration, int64_t *out_len) {
+    if (!ctx || !p || in_len < 0 || (in_len && (!d_in || !d_out))) return B200_ERR_INVALID;
+    switch (p->kind) {
+        case B200_PROBLEM_BFS:
+            return compact_op(ctx, BfsFilterPred{d_in}, in_len, d_out, out_capacity, out_len);
+        case B200_PROBLEM_SSSP:
+            if (!p->visited) return B200_ERR_INVALID;
+            return compact_op(ctx, SsspFilterPred{d_in, p->visited, iteration}, in_len, d_out, out_capacity, out_len);
+        case B200_PROBLEM_PR:
+            if (!p->current_ranks || !p->reduced_ranks || (!p->degrees && !g)) return B200_ERR_INVALID;
+            return compact_op(ctx, PrFilterPred{d_in, p->current_ranks, p->reduced_ranks, p->degrees, g ? g->row_offsets : nullptr},
+                              in_len, d_out, out_capacity, out_len);
+        default:
+            return B200_ERR_UNSUPPORTED;
+    }
+}
+
+int b200_uniquify(b200_ctx *ctx, const b200_graph *, const b200_problem *p, uint32_t *d_visited_bitmap,
+                  const int32_t *d_in, int64_t in_len, int32_t *d_out, int64_t out_capacity, int iteration,
+                  int64_t *out_len) {
+    if (!ctx || !d_visited_bitmap || in_len < 0 || (in_len && (!d_in || !d_out))) return B200_ERR_INVALID;
+    int *labels = (p && p->kind == B200_PROBLEM_BFS) ? p->labels : nullptr;
+    return compact_op(ctx, UniquifyPred{d_in, d_visited_bitmap, labels, iteration + 1}, in_len, d_out, out_capacity, out_len);
+}
+
+int b200_sparse_to_dense(b200_ctx *ctx, int64_t n, const int32_t *d_sparse, int64_t len, uint32_t *d_bitmap) {
+    if (!ctx || n < 0 || len < 0 || !d_bitmap || (len && !d_sparse)) return B200_ERR_INVALID;
+    cudaStream_t st = ws_stream(&ctx->ws);
+    B200_CUDA(cudaSetDevice(ctx->ws.device));
+    B200_CUDA(cudaMemsetAsync(d_bitmap, 0, sizeof(uint32_t) * (size_t)((n + 31) / 32), st));
+    if (len) {
+        sparse_to_bitmap_kernel<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(d_sparse, (uint32_t)len, d_bitmap);
+        ctx->ws.launches++;
+        B200_CUDA(cudaGetLastError());
+    }
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+int b200_dense_to_sparse(b200_ctx *ctx, int64_t n, const uint32_t *d_bitmap, int32_t *d_sparse, int64_t capacity,
+                         int64_t *out_len) {
+    if (!ctx || !d_bitmap || !d_sparse) return B200_ERR_INVALID;
+    return compact_op(ctx, BitmapPred{d_bitmap}, n, d_sparse, capacity, out_len);
+}
+
+int b200_gen_unvisited(b200_ctx *ctx, const b200_problem *p, int64_t n, int32_t *d_unvisited, int64_t capacity,
+                       int64_t *out_len) {
+    if (!ctx || !p || p->kind != B200_PROBLEM_BFS || !p->labels || !d_unvisited) return B200_ERR_INVALID;
+    return compact_op(ctx, UnvisitedPred{p->labels}, n, d_unvisited, capacity, out_len);
+}
+
+int b200_advance_backward(b200_ctx *ctx, const b200_graph *g, const b200_problem *p, const uint32_t *d_frontier_bitmap,
+                          uint32_t *d_next_bitmap, int iteration, int64_t *discovered, int64_t *arcs_inspected) {
+    if (!ctx || !g || !p || p->kind != B200_PROBLEM_BFS || !p->labels || !p->visited_bitmap || !d_frontier_bitmap ||
+        !d_next_bitmap)
+        return B200_ERR_INVALID;
+    b200_workspace *ws = &ctx->ws;
+    B200_CUDA(cudaSetDevice(ws->device));
+    B200_CUDA(reset_counters(ws));
+    const uint32_t *off = g->col_offsets ? g->col_offsets : g->row_offsets;
+    const int32_t *idx = g->row_indices ? g->row_indices : g->col_indices;
+    bfs_pull_kernel<256><<<ws->num_sms * 8, 256, 0, ws_stream(ws)>>>((uint32_t)g->n, off, idx, d_frontier_bitmap, d_next_bitmap,
+                                                                      p->visited_bitmap, p->labels, iteration + 1, ws->d_counters);
+    ws->launches++;
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(read_counters(ws));
+    if (discovered) *discovered = (int64_t)ws->h_counters[B200_CNT_OUT];
+    if (arcs_inspected) *arcs_inspected = (int64_t)ws->h_counters[B200_CNT_ARCS];
+    return B200_OK;
+}
+
+int b200_neighborhood_reduce_f32(b200_ctx *ctx, const b200_graph *g, const int32_t *d_in, int64_t in_len,
+                                 const float *d_values, float *d_reduced, float identity, int op, int push,
+                                 int scatter, int64_t *arcs) {
+    if (!ctx || !g || in_len < 0 || (in_len && (!d_in || !d_values || !d_reduced))) return B200_ERR_INVALID;
+    if (arcs) *arcs = 0;
+    if (in_len == 0) return B200_OK;
+    B200_TRY(check_counts(ctx, in_len));
+    b200_workspace *ws = &ctx->ws;
+    B200_CUDA(cudaSetDevice(ws->device));
+    const uint32_t *off = push ? g->row_offsets : (g->col_offsets ? g->col_offsets : g->row_offsets);
+    const int32_t *idx = push ? g->col_indices : (g->row_indices ? g->row_indices : g->col_indices);
+    B200_CUDA(reset_counters(ws));
+    const float neutral = op == B200_OP_PLUS ? PlusF32::neutral() : (op == B200_OP_MIN ? MinF32::neutral() : MaxF32::neutral());
+    NeighborhoodDegree<float> deg{d_in, off, d_reduced, identity, neutral, scatter};
+    B200_CUDA(launch_scan(ws, deg, (uint32_t)in_len, ws->d_scanned, ws->d_counters + B200_CNT_TOTAL));
+    const LbsArgs a = make_lbs_args(ws, d_in, (uint32_t)in_len, off, idx);
+    FiniteValueFn vf{d_values};
+    cudaError_t e;
+    if (op == B200_OP_PLUS) e = launch_lbs_segreduce<float, PlusF32>(ws, a, vf, d_reduced, scatter);
+    else if (op == B200_OP_MIN) e = launch_lbs_segreduce<float, MinF32>(ws, a, vf, d_reduced, scatter);
+    else if (op == B200_OP_MAX) e = launch_lbs_segreduce<float, MaxF32>(ws, a, vf, d_reduced, scatter);
+    else return B200_ERR_INVALID;
+    B200_CUDA(e);
+    B200_CUDA(read_counters(ws));
+    if (arcs) *arcs = (int64_t)ws->h_counters[B200_CNT_TOTAL];
+    return B200_OK;
+}
+
+// ============================================================== primitives
+int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, float alpha, float beta,
+                 int32_t *d_labels, b200_stats *stats) {
+    if (!ctx || !g || !d_labels || g->n < 1 || src < 0 || src >= g->n || g->n > (1ll << 31)) return B200_ERR_INVALID;
+    if (mode < B200_BFS_PUSH || mode > B200_BFS_BEAMER) return B200_ERR_INVALID;
+    const int64_t n = g->n;
+    B200_CUDA(cudaSetDevice(ctx->ws.device));
+    B200_TRY(ensure_traversal_scratch(ctx, n));
+    b200_workspace *ws = &ctx->ws;
+    cudaStream_t st = ws_stream(ws);
+    const size_t words = (size_t)((n + 31) / 32);
+    const bool timing = stats && stats->collect_timing;
+    cudaEvent_t *ev = timing ? level_events(ctx) : nullptr;
+    const int64_t launches0 = ws->launches;
+    const uint32_t *pull_off = g->col_offsets ? g->col_offsets : g->row_offsets;
+    const int32_t *pull_idx = g->row_indices ? g->row_indices : g->col_indices;
+
+    B200_CUDA(cudaEventRecord(ctx->ev_run[0], st));
+    // bfs_problem_t ctor (bfs_problem.hxx:38-42) + init_frontier (bfs_enactor.hxx:34-38)
+    B200_CUDA(cudaMemsetAsync(d_labels, 0xFF, sizeof(int32_t) * (size_t)n, st));
+    B200_CUDA(cudaMemsetAsync(ctx->bm_visited, 0, sizeof(uint32_t) * words, st));
+    bfs_init_kernel<<<1, 1, 0, st>>>(d_labels, ctx->bm_visited, ctx->frontier[0], src);
+    ws->launches++;
+    B200_CUDA(cudaGetLastError());
+
+    int sel = 0, bsel = 0, level = 0;
+    int64_t flen = 1, unvisited = n - 1, reached = 1, total_arcs = 0;
+    int64_t m_unexplored = g->m;
+    bool pull = false;
+    if (alpha <= 0.f) alpha = 15.f;
+    if (beta <= 0.f) beta = 18.f;
+
+    for (;;) {
+        b200_level_stat *ls = (stats && level < B200_MAX_LEVELS) ? &stats->level[level] : nullptr;
+        const bool tl = timing && level < B200_MAX_LEVELS;
+        if (tl && level == 0) B200_CUDA(cudaEventRecord(ev[0], st));   // later levels start at the previous level's end marker
+        B200_CUDA(reset_counters(ws));
+        int64_t found, arcs, next_deg;
+        if (!pull) {
+            B200_CUDA(launch_frontier_scan(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets));
+            const LbsArgs a = make_lbs_args(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets, g->col_indices);
+            BfsPushOp op{ctx->bm_visited, d_labels, level + 1};
+            if (tl) B200_CUDA(cudaEventRecord(ev[3 * level + 1], st));
+            if (mode == B200_BFS_BEAMER)
+                B200_CUDA((launch_lbs_advance<OUT_COMPACT, true>(ws, a, op, ctx->frontier[sel ^ 1], (unsigned long long)n)));
+            else
+                B200_CUDA((launch_lbs_advance<OUT_COMPACT, false>(ws, a, op, ctx->frontier[sel ^ 1], (unsigned long long)n)));
+            if (tl) B200_CUDA(cudaEventRecord(ev[3 * level + 2], st));
+            B200_CUDA(read_counters(ws));
+            if (ws->h_counters[B200_CNT_OVERFLOW]) return B200_ERR_OVERFLOW;
+            found = (int64_t)ws->h_counters[B200_CNT_OUT];
+            arcs = (int64_t)ws->h_counters[B200_CNT_TOTAL];
+            next_deg = (int64_t)ws->h_counters[B200_CNT_AUX];
+        } else {
+            if (tl) B200_CUDA(cudaEventRecord(ev[3 * level + 1], st));
+            bfs_pull_kernel<256><<<ws->num_sms * 8, 256, 0, st>>>((uint32_t)n, pull_off, pull_idx, ctx->bm_frontier[bsel],
+                                                                  ctx->bm_frontier[bsel ^ 1], ctx->bm_visited, d_labels,
+                                                                  level + 1, ws->d_counters);
+            ws->launches++;
+            B200_CUDA(cudaGetLastError());
+            if (tl) B200_CUDA(cudaEventRecord(ev[3 * level + 2], st));
+            B200_CUDA(read_counters(ws));
+            found = (int64_t)ws->h_counters[B200_CNT_OUT];
+            arcs = (int64_t)ws->h_counters[B200_CNT_ARCS];
+            next_deg = (int64_t)ws->h_counters[B200_CNT_AUX];
+        }
+        if (ls) {
+            ls->direction = pull ? 1 : 0;
+            ls->frontier_len = pull ? unvisited : flen;
+            ls->arcs = arcs;
+            ls->discovered = found;
+        }
+        total_arcs += arcs;
+        ++level;
+        if (tl) B200_CUDA(cudaEventRecord(ev[3 * level], st));   // closes level-1; reused as next level's start marker
+        if (found == 0) break;
+        reached += found;
+        unvisited -= found;
+        const bool was_pull = pull;
+        if (!pull) {
+            m_unexplored -= arcs;
+            sel ^= 1;
+            if (mode == B200_BFS_REF_ALPHA) {
+                // bfs_enactor.hxx:68: (float)num_unvisited < (float)frontier_length * threshold
+                if ((float)unvisited < (float)found * alpha) pull = true;
+            } else if (mode == B200_BFS_BEAMER) {
+                if ((double)next_deg > (double)m_unexplored / alpha && found > flen) pull = true;
+            }
+        } else {
+            bsel ^= 1;
+            if (mode == B200_BFS_BEAMER && (double)found < (double)n / beta && found < flen) pull = false;
+        }
+        flen = found;
+        if (pull && !was_pull) {
+            // frontier list -> bitmap (sparse_to_dense_kernel, advance.hxx:69-84)
+            B200_CUDA(cudaMemsetAsync(ctx->bm_frontier[bsel], 0, sizeof(uint32_t) * words, st));
+            sparse_to_bitmap_kernel<<<(unsigned)((flen + 255) / 256), 256, 0, st>>>(ctx->frontier[sel], (uint32_t)flen,
+                                                                                   ctx->bm_frontier[bsel]);
+            ws->launches++;
+            B200_CUDA(cudaGetLastError());
+        } else if (!pull && was_pull) {
+            // bitmap -> frontier list for the push levels that finish the traversal
+            B200_CUDA(reset_counters(ws));
+            B200_CUDA(launch_compact(ws, BitmapPred{ctx->bm_frontier[bsel]}, (uint32_t)n, ctx->frontier[sel], (unsigned long long)n,
+                                     ws->d_counters + B200_CNT_OUT, ws->d_counters + B200_CNT_OVERFLOW));
+        }
+    }
+    B200_CUDA(cudaEventRecord(ctx->ev_run[1], st));
+    B200_CUDA(cudaEventSynchronize(ctx->ev_run[1]));
+    if (stats) {
+        stats->num_levels = level;
+        stats->reached = reached;
+        stats->total_arcs = total_arcs;
+        stats->launches = ws->launches - launches0;
+        B200_CUDA(cudaEventElapsedTime(&stats->device_ms, ctx->ev_run[0], ctx->ev_run[1]));
+        finish_level_timing(ctx, stats);
+    }
+    return B200_OK;
+}
+
+int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist, int32_t *d_preds, b200_stats *stats) {
+    if (!ctx || !g || !d_dist || !g->col_values || g->n < 1 || src < 0 || src >= g->n || g->n > (1ll << 31))
+        return B200_ERR_INVALID;
+    const int64_t n = g->n;
+    B200_CUDA(cudaSetDevice(ctx->ws.device));
+    B200_TRY(ensure_traversal_scratch(ctx, n));
+    b200_workspace *ws = &ctx->ws;
+    cudaStream_t st = ws_stream(ws);
+    const bool timing = stats && stats->collect_timing;
+    cudaEvent_t *ev = timing ? level_events(ctx) : nullptr;
+    const int64_t launches0 = ws->launches;
+
+    B200_CUDA(cudaEventRecord(ctx->ev_run[0], st));
+    // sssp_problem_t ctor (sssp_problem.hxx:44-49) + init_frontier (sssp_enactor.hxx:33-37)
+    sssp_init_kernel<<<ws->num_sms * 4, 256, 0, st>>>(d_dist, d_preds, ctx->stamp, (unsigned long long)n);
+    sssp_seed_kernel<<<1, 1, 0, st>>>(d_dist, ctx->frontier[0], src);
+    ws->launches += 2;
+    B200_CUDA(cudaGetLastError());
+
+    int sel = 0, it = 0;
+    int64_t flen = 1, total_arcs = 0;
+    for (;;) {
+        b200_level_stat *ls = (stats && it < B200_MAX_LEVELS) ? &stats->level[it] : nullptr;
+        const bool tl = timing && it < B200_MAX_LEVELS;
+        if (tl && it == 0) B200_CUDA(cudaEventRecord(ev[0], st));
+        B200_CUDA(reset_counters(ws));
+        B200_CUDA(launch_frontier_scan(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets));
+        const LbsArgs a = make_lbs_args(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets, g->col_indices);
+        SsspRelaxOp op{d_dist, g->col_values, d_preds, ctx->stamp, it};
+        if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 1], st));
+        B200_CUDA((launch_lbs_advance<OUT_COMPACT, false>(ws, a, op, ctx->frontier[sel ^ 1], (unsigned long long)n)));
+        if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 2], st));
+        B200_CUDA(read_counters(ws));
+        if (ws->h_counters[B200_CNT_OVERFLOW]) return B200_ERR_OVERFLOW;
+        const int64_t found = (int64_t)ws->h_counters[B200_CNT_OUT];
+        const int64_t arcs = (int64_t)ws->h_counters[B200_CNT_TOTAL];
+        if (ls) {
+            ls->direction = 0;
+            ls->frontier_len = flen;
+            ls->arcs = arcs;
+            ls->discovered = found;
+        }
+        total_arcs += arcs;
+        ++it;
+        if (tl) B200_CUDA(cudaEventRecord(ev[3 * it], st));
+        if (found == 0) break;
+        sel ^= 1;
+        flen = found;
+    }
+    B200_CUDA(cudaEventRecord(ctx->ev_run[1], st));
+    B200_CUDA(cudaEventSynchronize(ctx->ev_run[1]));
+    if (stats) {
+        stats->num_levels = it;
+        stats->reached = -1;
+        stats->total_arcs = total_arcs;
+        stats->launches = ws->launches - launches0;
+        B200_CUDA(cudaEventElapsedTime(&stats->device_ms, ctx->ev_run[0], ctx->ev_run[1]));
+        finish_level_timing(ctx, stats);
+    }
+    return B200_OK;
+}
+
+int b200_pr_run(b200_ctx *ctx, const b200_graph *g, int max_iter, int scatter, float *d_current, float *d_reduced,
+                int64_t *h_frontier_lens, int *iterations, b200_stats *stats) {
+    if (!ctx || !g || !d_current || !d_reduced || g->n < 1 || g->n > (1ll << 31)) return B200_ERR_INVALID;
+    const int64_t n = g->n;
+    B200_CUDA(cudaSetDevice(ctx->ws.device));
+    B200_TRY(ensure_traversal_scratch(ctx, n));
+    b200_workspace *ws = &ctx->ws;
+    cudaStream_t st = ws_stream(ws);
+    const bool timing = stats && stats->collect_timing;
+    cudaEvent_t *ev = timing ? level_events(ctx) : nullptr;
+    const int64_t launches0 = ws->launches;
+    const uint32_t *off = g->col_offsets ? g->col_offsets : g->row_offsets;   // push=false (pr_enactor.hxx:53)
+    const int32_t *idx = g->row_indices ? g->row_indices : g->col_indices;
+
+    B200_CUDA(cudaEventRecord(ctx->ev_run[0], st));
+    pr_init_kernel<<<ws->num_sms * 4, 256, 0, st>>>(d_current, d_reduced, ctx->frontier[0], (unsigned long long)n);
+    ws->launches++;
+    B200_CUDA(cudaGetLastError());
+    int sel = 0, it = 0;
+    int64_t flen = n, total_arcs = 0;
+    while (flen > 0 && it < max_iter) {
+        b200_level_stat *ls = (stats && it < B200_MAX_LEVELS) ? &stats->level[it] : nullptr;
+        const bool tl = timing && it < B200_MAX_LEVELS;
+        if (tl && it == 0) B200_CUDA(cudaEventRecord(ev[0], st));
+        B200_CUDA(reset_counters(ws));
+        NeighborhoodDegree<float> deg{ctx->frontier[sel], off, d_reduced, 0.0f, 0.0f, scatter};
+        B200_CUDA(launch_scan(ws, deg, (uint32_t)flen, ws->d_scanned, ws->d_counters + B200_CNT_TOTAL));
+        const LbsArgs a = make_lbs_args(ws, ctx->frontier[sel], (uint32_t)flen, off, idx);
+        if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 1], st));
+        B200_CUDA((launch_lbs_segreduce<float, PlusF32>(ws, a, FiniteValueFn{d_current}, d_reduced, scatter)));
+        if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 2], st));
+        B200_CUDA(launch_compact(ws, PrFilterPred{ctx->frontier[sel], d_current, d_reduced, nullptr, g->row_offsets},
+                                 (uint32_t)flen, ctx->frontier[sel ^ 1], (unsigned long long)n,
+                                 ws->d_counters + B200_CNT_OUT, ws->d_counters + B200_CNT_OVERFLOW));
+        B200_CUDA(read_counters(ws));
+        const int64_t out = (int64_t)ws->h_counters[B200_CNT_OUT];
+        const int64_t arcs = (int64_t)ws->h_counters[B200_CNT_TOTAL];
+        if (ls) {
+            ls->direction = 1;
+            ls->frontier_len = flen;
+            ls->arcs = arcs;
+            ls->discovered = out;
+        }
+        if (h_frontier_lens) h_frontier_lens[it] = out;
+        total_arcs += arcs;
+        ++it;
+        if (tl) B200_CUDA(cudaEventRecord(ev[3 * it], st));
+        sel ^= 1;
+        flen = out;
+    }
+    B200_CUDA(cudaEventRecord(ctx->ev_run[1], st));
+    B200_CUDA(cudaEventSynchronize(ctx->ev_run[1]));
+    if (iterations) *iterations = it;
+    if (stats) {
+        stats->num_levels = it;
+        stats->reached = n;
+        stats->total_arcs = total_arcs;
+        stats->launches = ws->launches - launches0;
+        B200_CUDA(cudaEventElapsedTime(&stats->device_ms, ctx->ev_run[0], ctx->ev_run[1]));
+        finish_level_timing(ctx, stats);
+    }
+    return B200_OK;
+}
+
+// ============================================================== host-buffer entry points
+int b200_host_graph_upload(b200_ctx *ctx, int64_t n, int64_t m, const uint32_t *h_row_offsets,
+                           const int32_t *h_col_indices, const float *h_col_values, b200_host_graph **out) {
+    if (!ctx || !out || n < 1 || m < 0 || m >= (1ll << 32) || !h_row_offsets || (m && !h_col_indices)) return B200_ERR_INVALID;
+    *out = nullptr;
+    B200_CUDA(cudaSetDevice(ctx->ws.device));
+    b200_host_graph *hg = new b200_host_graph;
+    std::memset(hg, 0, sizeof(*hg));
+    hg->n = n;
+    hg->m = m;
+    cudaStream_t st = ws_stream(&ctx->ws);
+    int s = B200_OK;
+    do {
+        if ((s = cuda_status(cudaMalloc(&hg->d_row_offsets, sizeof(uint32_t) * (size_t)(n + 1))))) break;
+        if ((s = cuda_status(cudaMalloc(&hg->d_col_indices, sizeof(int32_t) * (size_t)(m ? m : 1))))) break;
+        if (h_col_values && (s = cuda_status(cudaMalloc(&hg->d_col_values, sizeof(float) * (size_t)(m ? m : 1))))) break;
+        if ((s = cuda_status(cudaMalloc(&hg->d_labels, sizeof(int32_t) * (size_t)n)))) break;
+        if ((s = cuda_status(cudaMalloc(&hg->d_dist, sizeof(float) * (size_t)n)))) break;
+        if ((s = cuda_status(cudaMalloc(&hg->d_preds, sizeof(int32_t) * (size_t)n)))) break;
+        if ((s = cuda_status(cudaMemcpyAsync(hg->d_row_offsets, h_row_offsets, sizeof(uint32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st)))) break;
+        if (m && (s = cuda_status(cudaMemcpyAsync(hg->d_col_indices, h_col_indices, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, st)))) break;
+        if (m && h_col_values && (s = cuda_status(cudaMemcpyAsync(hg->d_col_values, h_col_values, sizeof(float) * (size_t)m, cudaMemcpyHostToDevice, st)))) break;
+        s = cuda_status(cudaStreamSynchronize(st));
+    } while (0);
+    if (s != B200_OK) {
+        b200_host_graph_free(ctx, hg);
+        return s;
+    }
+    *out = hg;
+    return B200_OK;
+}
+
+int b200_host_graph_free(b200_ctx *ctx, b200_host_graph *hg) {
+    if (!hg) return B200_OK;
+    if (ctx) cudaSetDevice(ctx->ws.device);
+    cudaFree(hg->d_row_offsets);
+    cudaFree(hg->d_col_indices);
+    cudaFree(hg->d_col_values);
+    cudaFree(hg->d_labels);
+    cudaFree(hg->d_dist);
+    cudaFree(hg->d_preds);
+    delete hg;
+    return B200_OK;
+}
+
+int b200_host_graph_view(const b200_host_graph *hg, b200_graph *out) {
+    if (!hg || !out) return B200_ERR_INVALID;
+    out->n = hg->n;
+    out->m = hg->m;
+    out->row_offsets = hg->d_row_offsets;
+    out->col_indices = hg->d_col_indices;
+    out->col_values = hg->d_col_values;
+    out->col_offsets = hg->d_row_offsets;   // symmetric graphs: CSC aliases CSR (graph.hxx:75-80)
+    out->row_indices = hg->d_col_indices;
+    out->row_values = hg->d_col_values;
+    return B200_OK;
+}
+
+int b200_bfs_host(b200_ctx *ctx, b200_host_graph *hg, int32_t src, int mode, float alpha, float beta,
+                  const int32_t *h_labels_init, int32_t *h_labels_out, b200_stats *stats) {
+    if (!ctx || !hg || !h_labels_out) return B200_ERR_INVALID;
+    b200_graph g;
+    B200_TRY(b200_host_graph_view(hg, &g));
+    cudaStream_t st = ws_stream(&ctx->ws);
+    B200_CUDA(cudaSetDevice(ctx->ws.device));
+    // bfs_problem_t ctor uploads the host-initialised labels (bfs_problem.hxx:38-43: to_mem(labels));
+    // the engine rebuilds them on the device anyway, the copy is kept so the timed region moves the
+    // same bytes the reference's constructor does.
+    if (h_labels_init)
+        B200_CUDA(cudaMemcpyAsync(hg->d_labels, h_labels_init, sizeof(int32_t) * (size_t)hg->n, cudaMemcpyHostToDevice, st));
+    B200_TRY(b200_bfs_run(ctx, &g, src, mode, alpha, beta, hg->d_labels, stats));
+    // extract() (bfs_problem.hxx:48-50)
+    B200_CUDA(cudaMemcpyAsync(h_labels_out, hg->d_labels, sizeof(int32_t) * (size_t)hg->n, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+int b200_sssp_host(b200_ctx *ctx, b200_host_graph *hg, int32_t src, const float *h_dist_init, float *h_dist_out,
+                   int32_t *h_preds_out, b200_stats *stats) {
+    if (!ctx || !hg || !h_dist_out || !hg->d_col_values) return B200_ERR_INVALID;
+    b200_graph g;
+    B200_TRY(b200_host_graph_view(hg, &g));
+    cudaStream_t st = ws_stream(&ctx->ws);
+    B200_CUDA(cudaSetDevice(ctx->ws.device));
+    if (h_dist_init)
+        B200_CUDA(cudaMemcpyAsync(hg->d_dist, h_dist_init, sizeof(float) * (size_t)hg->n, cudaMemcpyHostToDevice, st));
+    B200_TRY(b200_sssp_run(ctx, &g, src, hg->d_dist, h_preds_out ? hg->d_preds : nullptr, stats));
+    // extract() (sssp_problem.hxx:54-57)
+    B200_CUDA(cudaMemcpyAsync(h_dist_out, hg->d_dist, sizeof(float) * (size_t)hg->n, cudaMemcpyDeviceToHost, st));
+    if (h_preds_out)
+        B200_CUDA(cudaMemcpyAsync(h_preds_out, hg->d_preds, sizeof(int32_t) * (size_t)hg->n, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// engine.cuh -- private state behind the opaque b200_ctx handle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "b200/workspace.h"
+#include "b200_frontier.h"
+
+struct b200_ctx {
+    b200_workspace ws;
+    bool own_stream;
+    // traversal scratch, sized by the largest n seen (ensure_traversal_scratch)
+    int64_t scratch_n;
+    int32_t *frontier[2];      // ping-pong sparse frontiers, n ints each (fused filter => |F| <= n)
+    uint32_t *bm_visited;      // 1 bit / vertex
+    uint32_t *bm_frontier[2];  // pull-phase frontier bitmaps
+    int32_t *stamp;            // SSSP per-iteration dedupe stamps
+    // per-level timing events (created lazily when stats->collect_timing)
+    cudaEvent_t ev_run[2];
+    cudaEvent_t *ev_level;     // 3 per level: level start, advance start, advance stop
+    int ev_level_count;
+    // L2 persistence
+    bool l2_window_set;
+};
+
+struct b200_host_graph {
+    int64_t n, m;
+    uint32_t *d_row_offsets;
+    int32_t *d_col_indices;
+    float *d_col_values;
+    int32_t *d_labels;   // result staging (BFS)
+    float *d_dist;       // result staging (SSSP)
+    int32_t *d_preds;
+};
+
+namespace b200 {
+
+extern thread_local int g_last_cuda_error;
+
+inline int cuda_status(cudaError_t e) {
+    if (e == cudaSuccess) return B200_OK;
+    g_last_cuda_error = (int)e;
+    (void)cudaGetLastError();   // clear the sticky-less error
+    return e == cudaErrorMemoryAllocation ? B200_ERR_NOMEM : B200_ERR_CUDA;
+}
+
+#define B200_CUDA(call)                                   \
+    do {                                                  \
+        cudaError_t _e = (call);                          \
+        if (_e != cudaSuccess) return ::b200::cuda_status(_e); \
+    } while (0)
+
+#define B200_TRY(call)                 \
+    do {                               \
+        int _s = (call);               \
+        if (_s != B200_OK) return _s;  \
+    } while (0)
+
+int ensure_traversal_scratch(b200_ctx *ctx, int64_t n);
+
+}  // namespace b200

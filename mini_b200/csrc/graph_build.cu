@@ -1,0 +1,157 @@
+// graph_build.cu -- device-side synthetic RMAT generator and CSR builder.
+// Produces what graph.hxx:139-172 builds from a sorted tuple list (arcs ordered by
+// (src,dst), duplicates and self loops kept, empty rows get the next offset) and
+// what load_graph(_, true, _) does for symmetrisation (graph.hxx:130-137), but on
+// the GPU and with offsets that can hold 2^31 arcs.  Not on the timed hot path:
+// uses cub::DeviceRadixSort (CUDA toolkit library) for the (src,dst) sort.
+#include <cub/device/device_radix_sort.cuh>
+#include "engine.cuh"
+#include "rmat.cuh"
+
+using namespace b200;
+
+namespace {
+
+__global__ void rmat_keys_kernel(uint64_t key, int scale, unsigned long long npairs, unsigned long long *keys) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < npairs; e += stride) {
+        uint32_t u, v;
+        rmat_pair(key, e, scale, u, v);
+        keys[2 * e] = ((unsigned long long)u << 32) | v;
+        keys[2 * e + 1] = ((unsigned long long)v << 32) | u;
+    }
+}
+
+__global__ void rmat_pairs_kernel(uint64_t key, int scale, unsigned long long npairs, int32_t *src, int32_t *dst) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < npairs; e += stride) {
+        uint32_t u, v;
+        rmat_pair(key, e, scale, u, v);
+        src[e] = (int32_t)u;
+        dst[e] = (int32_t)v;
+    }
+}
+
+__global__ void pairs_to_keys_kernel(const int32_t *src, const int32_t *dst, unsigned long long npairs, int symmetrize,
+                                     unsigned long long *keys) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < npairs; e += stride) {
+        const uint32_t u = (uint32_t)src[e], v = (uint32_t)dst[e];
+        if (symmetrize) {
+            keys[2 * e] = ((unsigned long long)u << 32) | v;
+            keys[2 * e + 1] = ((unsigned long long)v << 32) | u;
+        } else {
+            keys[e] = ((unsigned long long)u << 32) | v;
+        }
+    }
+}
+
+// sorted (src<<32|dst) keys -> col_indices, row_offsets (every row r gets the index of
+// its first arc; empty rows inherit the next row's), optional pair weights.
+__global__ void keys_to_csr_kernel(const unsigned long long *keys, unsigned long long m, unsigned long long n,
+                                   uint32_t *row_offsets, int32_t *col_indices, float *weights, uint64_t wkey) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        const unsigned long long k = keys[i];
+        const uint32_t s = (uint32_t)(k >> 32), d = (uint32_t)k;
+        col_indices[i] = (int32_t)d;
+        if (weights) weights[i] = pair_weight(wkey, s, d);
+        const long long prev = i ? (long long)(keys[i - 1] >> 32) : -1ll;
+        for (long long r = prev + 1; r <= (long long)s; ++r) row_offsets[r] = (uint32_t)i;
+        if (i == m - 1)
+            for (unsigned long long r = (unsigned long long)s + 1; r <= n; ++r) row_offsets[r] = (uint32_t)m;
+    }
+}
+
+__global__ void fill_u32_kernel(uint32_t *p, unsigned long long count, uint32_t v) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) p[i] = v;
+}
+
+int sort_and_emit(b200_ctx *ctx, unsigned long long *keys_a, unsigned long long *keys_b, long long m, long long n,
+                  int key_bits, uint32_t *d_row_offsets, int32_t *d_col_indices, float *d_weights, uint64_t wseed) {
+    cudaStream_t st = (cudaStream_t)ctx->ws.stream;
+    if (m == 0) {
+        fill_u32_kernel<<<256, 256, 0, st>>>(d_row_offsets, (unsigned long long)n + 1, 0u);
+        B200_CUDA(cudaGetLastError());
+        B200_CUDA(cudaStreamSynchronize(st));
+        return B200_OK;
+    }
+    cub::DoubleBuffer<unsigned long long> buf(keys_a, keys_b);
+    size_t temp_bytes = 0;
+    B200_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, buf, (long long)m, 0, key_bits, st));
+    void *temp = nullptr;
+    B200_CUDA(cudaMalloc(&temp, temp_bytes ? temp_bytes : 16));
+    cudaError_t e = cub::DeviceRadixSort::SortKeys(temp, temp_bytes, buf, (long long)m, 0, key_bits, st);
+    if (e == cudaSuccess) {
+        keys_to_csr_kernel<<<ctx->ws.num_sms * 8, 256, 0, st>>>(buf.Current(), (unsigned long long)m, (unsigned long long)n,
+                                                               d_row_offsets, d_col_indices, d_weights, weight_key(wseed));
+        e = cudaGetLastError();
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(temp);
+    B200_CUDA(e);
+    B200_CUDA(e2);
+    return B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_rmat_pairs(b200_ctx *ctx, int scale, int edge_factor, uint64_t seed, int32_t *d_src, int32_t *d_dst) {
+    if (!ctx || scale < 1 || scale > 31 || edge_factor < 1 || !d_src || !d_dst) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->ws.device));
+    const unsigned long long npairs = (unsigned long long)edge_factor << scale;
+    rmat_pairs_kernel<<<ctx->ws.num_sms * 8, 256, 0, (cudaStream_t)ctx->ws.stream>>>(rmat_key(seed), scale, npairs, d_src, d_dst);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaStreamSynchronize((cudaStream_t)ctx->ws.stream));
+    return B200_OK;
+}
+
+int b200_rmat_build_csr(b200_ctx *ctx, int scale, int edge_factor, uint64_t seed, uint32_t *d_row_offsets,
+                        int32_t *d_col_indices, float *d_weights, uint64_t weight_seed) {
+    if (!ctx || scale < 1 || scale > 31 || edge_factor < 1 || !d_row_offsets || !d_col_indices) return B200_ERR_INVALID;
+    const unsigned long long npairs = (unsigned long long)edge_factor << scale;
+    const unsigned long long m = 2 * npairs;
+    if (m >= (1ull << 32)) return B200_ERR_UNSUPPORTED;
+    B200_CUDA(cudaSetDevice(ctx->ws.device));
+    unsigned long long *ka = nullptr, *kb = nullptr;
+    B200_CUDA(cudaMalloc(&ka, sizeof(unsigned long long) * m));
+    cudaError_t e = cudaMalloc(&kb, sizeof(unsigned long long) * m);
+    if (e != cudaSuccess) { cudaFree(ka); return cuda_status(e); }
+    rmat_keys_kernel<<<ctx->ws.num_sms * 8, 256, 0, (cudaStream_t)ctx->ws.stream>>>(rmat_key(seed), scale, npairs, ka);
+    int s = cuda_status(cudaGetLastError());
+    if (s == B200_OK)
+        s = sort_and_emit(ctx, ka, kb, (long long)m, 1ll << scale, 32 + scale, d_row_offsets, d_col_indices, d_weights, weight_seed);
+    cudaFree(ka);
+    cudaFree(kb);
+    return s;
+}
+
+int b200_build_csr_from_pairs(b200_ctx *ctx, int64_t n, int64_t npairs, const int32_t *d_src, const int32_t *d_dst,
+                              int symmetrize, uint32_t *d_row_offsets, int32_t *d_col_indices, float *d_weights,
+                              uint64_t weight_seed) {
+    if (!ctx || n < 1 || n > (1ll << 31) || npairs < 0 || !d_row_offsets || (npairs && (!d_src || !d_dst || !d_col_indices)))
+        return B200_ERR_INVALID;
+    const unsigned long long m = (unsigned long long)npairs * (symmetrize ? 2 : 1);
+    if (m >= (1ull << 32)) return B200_ERR_UNSUPPORTED;
+    B200_CUDA(cudaSetDevice(ctx->ws.device));
+    unsigned long long *ka = nullptr, *kb = nullptr;
+    B200_CUDA(cudaMalloc(&ka, sizeof(unsigned long long) * (m ? m : 1)));
+    cudaError_t e = cudaMalloc(&kb, sizeof(unsigned long long) * (m ? m : 1));
+    if (e != cudaSuccess) { cudaFree(ka); return cuda_status(e); }
+    int s = B200_OK;
+    if (npairs) {
+        pairs_to_keys_kernel<<<ctx->ws.num_sms * 8, 256, 0, (cudaStream_t)ctx->ws.stream>>>(d_src, d_dst, (unsigned long long)npairs, symmetrize, ka);
+        s = cuda_status(cudaGetLastError());
+    }
+    int bits = 1;
+    while ((1ll << bits) < n) ++bits;
+    if (s == B200_OK) s = sort_and_emit(ctx, ka, kb, (long long)m, n, 32 + bits, d_row_offsets, d_col_indices, d_weights, weight_seed);
+    cudaFree(ka);
+    cudaFree(kb);
+    return s;
+}
+
+}  // extern "C"
