@@ -2,6 +2,7 @@
 // Each entry point cites the reference interface it replaces in
 // include/b200_frontier.h.  All kernels come from include/b200/*.cuh.
 #include <cfloat>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include "b200/operators.cuh"
@@ -28,6 +29,18 @@ __global__ void sssp_init_kernel(float *dist, int32_t *preds, int32_t *stamp, un
 __global__ void sssp_seed_kernel(float *dist, int32_t *frontier, int src) {
     dist[src] = 0.0f;
     frontier[0] = src;
+}
+__global__ void iota_fill_kernel(int32_t *frontier, int32_t *preds, unsigned long long n) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        frontier[i] = (int32_t)i;
+        preds[i] = INT_MAX;
+    }
+}
+__global__ void preds_fixup_kernel(int32_t *preds, unsigned long long n, int src) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (preds[i] == INT_MAX || i == (unsigned long long)src) preds[i] = -1;
 }
 __global__ void pr_init_kernel(float *current, float *reduced, int32_t *frontier, unsigned long long n) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -101,6 +114,23 @@ struct BitmapPred {
     __device__ __forceinline__ bool operator()(uint32_t idx, int &item) const {
         item = (int)idx;
         return (bitmap[idx >> 5] >> (idx & 31)) & 1u;
+    }
+};
+
+// Deterministic predecessors once the distances are final: the smallest u with
+// dist[u] + w(u,v) == dist[v].  (The reference writes preds[dst] = src from every
+// relaxation attempt, sssp_functor.hxx:31-34, so its GPU preds are a race)
+struct SsspPredOp {
+    const float *dist;
+    const float *weights;
+    int *preds;
+    __device__ __forceinline__ bool probe(int src, int dst, uint32_t eid) const {
+        const float ds = dist[src];
+        return ds != FLT_MAX && ds + ld_stream(weights + eid) == dist[dst];
+    }
+    __device__ __forceinline__ bool commit(int src, int dst, uint32_t, uint32_t, uint32_t) const {
+        atomicMin(preds + dst, src);
+        return false;
     }
 };
 
@@ -462,7 +492,7 @@ int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist
         B200_CUDA(reset_counters(ws));
         B200_CUDA(launch_frontier_scan(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets));
         const LbsArgs a = make_lbs_args(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets, g->col_indices);
-        SsspRelaxOp op{d_dist, g->col_values, d_preds, ctx->stamp, it};
+        SsspRelaxOp op{d_dist, g->col_values, nullptr, ctx->stamp, it};   // preds: one exact pass at the end
         if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 1], st));
         B200_CUDA((launch_lbs_advance<OUT_COMPACT, false>(ws, a, op, ctx->frontier[sel ^ 1], (unsigned long long)n)));
         if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 2], st));
@@ -482,6 +512,18 @@ int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist
         if (found == 0) break;
         sel ^= 1;
         flen = found;
+    }
+    if (d_preds) {
+        iota_fill_kernel<<<ws->num_sms * 4, 256, 0, st>>>(ctx->frontier[0], d_preds, (unsigned long long)n);
+        ws->launches++;
+        B200_CUDA(cudaGetLastError());
+        B200_CUDA(reset_counters(ws));
+        B200_CUDA(launch_frontier_scan(ws, ctx->frontier[0], (uint32_t)n, g->row_offsets));
+        const LbsArgs a = make_lbs_args(ws, ctx->frontier[0], (uint32_t)n, g->row_offsets, g->col_indices);
+        B200_CUDA((launch_lbs_advance<OUT_NONE, false>(ws, a, SsspPredOp{d_dist, g->col_values, d_preds}, nullptr, 0ull)));
+        preds_fixup_kernel<<<ws->num_sms * 4, 256, 0, st>>>(d_preds, (unsigned long long)n, src);
+        ws->launches++;
+        B200_CUDA(cudaGetLastError());
     }
     B200_CUDA(cudaEventRecord(ctx->ev_run[1], st));
     B200_CUDA(cudaEventSynchronize(ctx->ev_run[1]));
