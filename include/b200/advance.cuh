@@ -3,9 +3,9 @@
 // Push replaces the transform_lbs user lambda `neighbors_expand`
 // (advance.hxx:53-61) AND the `!= -1` filter_kernel that always follows it
 // (bfs_enactor.hxx:60-65, filter.hxx:11-31): accepted neighbours are appended
-// to the output frontier through a CTA-level shared-memory stage (warp ballot ->
-// one shared atomic per warp row -> one global atomic per tile -> coalesced
-// copy), so the m_F-sized intermediate with -1 holes never exists.
+// to the output frontier through per-warp shared-memory stages (warp ballot ->
+// stage -> one global atomic per ~256 accepted vertices -> coalesced copy), so the
+// m_F-sized intermediate with -1 holes never exists.
 // OUT_RAW keeps the reference layout out[idx] = nbr | -1.
 //
 // An Op supplies the per-arc functor in two halves so the kernel can batch the
@@ -24,18 +24,41 @@ enum { OUT_NONE = 0, OUT_COMPACT = 1, OUT_RAW = 2 };
 // DEG_SUM: also accumulate sum(deg(u)) over the emitted vertices into
 // counters[B200_CNT_AUX] (one atomic per CTA) so the next level's m_F -- the input
 // of the push/pull decision -- is known without another pass.
+//
+// Output staging is per WARP (WSTAGE ints of shared memory each): a warp appends its
+// accepted neighbours with a ballot + popc, and when its stage is nearly full claims
+// a range of the output frontier with ONE global atomic and copies the stage out with
+// coalesced stores.  No CTA barrier is involved, so together with the barrier-free
+// tile walk of lbs.cuh the warps of a CTA never wait for each other inside a window.
 template <class Op, int OUT_MODE, bool DEG_SUM, int NT, int VT, int SEG_T>
 __global__ void __launch_bounds__(NT) lbs_advance_kernel(LbsArgs a, Op op, int *__restrict__ out,
                                                          unsigned long long out_capacity,
                                                          unsigned long long *counters) {
+    constexpr int NW = NT / 32;
+    constexpr int WSTAGE = 32 * VT * 2;      // a tile adds at most 32*VT per warp
     __shared__ LbsSmem<NT, VT, SEG_T> sm;
-    __shared__ int stage[OUT_MODE == OUT_COMPACT ? NT * VT : 1];
-    __shared__ uint32_t s_cnt;
-    __shared__ unsigned long long s_gbase;
-    if (threadIdx.x == 0) s_cnt = 0;   // ordered before first use by the syncs in lbs_for_each_tile
+    __shared__ int wstage[OUT_MODE == OUT_COMPACT ? NW : 1][OUT_MODE == OUT_COMPACT ? WSTAGE : 1];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    int *stage = wstage[OUT_MODE == OUT_COMPACT ? warp : 0];
+    uint32_t wcnt = 0;                       // warp-uniform fill of this warp's stage
     unsigned long long deg_sum = 0;
 
-    lbs_for_each_tile<NT, VT, SEG_T>(a, sm, [&](uint32_t first_arc, uint32_t n_arcs, int ns, uint32_t) {
+    auto flush = [&]() {
+        __syncwarp();
+        unsigned long long g = 0;
+        if (lane == 0) g = atomicAdd(&counters[B200_CNT_OUT], (unsigned long long)wcnt);
+        g = __shfl_sync(FULL_MASK, g, 0);
+        for (uint32_t k = lane; k < wcnt; k += 32) {
+            const int u = stage[k];
+            if (g + k < out_capacity) out[g + k] = u;
+            if (DEG_SUM) deg_sum += __ldg(a.offsets + u + 1) - __ldg(a.offsets + u);
+        }
+        if (lane == 0 && g + wcnt > out_capacity) counters[B200_CNT_OVERFLOW] = 1ull;
+        wcnt = 0;
+        __syncwarp();
+    };
+
+    lbs_for_each_tile<NT, VT, SEG_T>(a, sm, [&](uint32_t first_arc, uint32_t n_arcs, int j_lo, int j_hi, uint32_t) {
         int src[VT], dst[VT];
         uint32_t eid[VT], rank[VT];
         bool cand[VT];
@@ -45,7 +68,7 @@ __global__ void __launch_bounds__(NT) lbs_advance_kernel(LbsArgs a, Op op, int *
             cand[i] = k < n_arcs;
             if (cand[i]) {
                 const uint32_t arc = first_arc + k;
-                const int j = lbs_locate(sm.start, ns, arc);
+                const int j = lbs_locate(sm.start, j_lo, j_hi, arc);
                 src[i] = sm.vert[j];
                 eid[i] = sm.base[j] + arc;
                 rank[i] = arc - sm.start[j];
@@ -68,42 +91,21 @@ __global__ void __launch_bounds__(NT) lbs_advance_kernel(LbsArgs a, Op op, int *
                 if (cand[i]) emit = op.commit(src[i], dst[i], eid[i], rank[i], first_arc + k);
                 if (OUT_MODE == OUT_COMPACT) {
                     const unsigned mask = __ballot_sync(FULL_MASK, emit);
-                    if (mask) {
-                        uint32_t base = 0;
-                        const unsigned leader = __ffs(mask) - 1;
-                        if (lane_id() == leader) base = atomicAdd(&s_cnt, (uint32_t)__popc(mask));
-                        base = __shfl_sync(FULL_MASK, base, leader);
-                        if (emit) stage[base + __popc(mask & lanemask_lt())] = dst[i];
-                    }
+                    if (emit) stage[wcnt + __popc(mask & lanemask_lt())] = dst[i];
+                    wcnt += __popc(mask);
                 }
             }
         }
-        if (OUT_MODE == OUT_COMPACT) {
-            __syncthreads();
-            const uint32_t cnt = s_cnt;
-            if (cnt) {   // CTA-uniform
-                if (threadIdx.x == 0) s_gbase = atomicAdd(&counters[B200_CNT_OUT], (unsigned long long)cnt);
-                __syncthreads();
-                const unsigned long long g = s_gbase;
-                for (uint32_t k = threadIdx.x; k < cnt; k += NT) {
-                    const int u = stage[k];
-                    if (g + k < out_capacity) out[g + k] = u;
-                    if (DEG_SUM) deg_sum += __ldg(a.offsets + u + 1) - __ldg(a.offsets + u);
-                }
-                if (threadIdx.x == 0) {
-                    s_cnt = 0;
-                    if (g + cnt > out_capacity) counters[B200_CNT_OVERFLOW] = 1ull;
-                }
-            }
-        }
+        if (OUT_MODE == OUT_COMPACT && wcnt > WSTAGE - 32 * VT) flush();
     });
+    if (OUT_MODE == OUT_COMPACT && wcnt) flush();
     if (DEG_SUM) {
         __shared__ unsigned long long s_deg;
         if (threadIdx.x == 0) s_deg = 0;
         __syncthreads();
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) deg_sum += __shfl_xor_sync(FULL_MASK, deg_sum, d);
-        if (lane_id() == 0 && deg_sum) atomicAdd(&s_deg, deg_sum);
+        if (lane == 0 && deg_sum) atomicAdd(&s_deg, deg_sum);
         __syncthreads();
         if (threadIdx.x == 0 && s_deg) atomicAdd(&counters[B200_CNT_AUX], s_deg);
     }

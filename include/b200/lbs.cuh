@@ -6,9 +6,9 @@
 //     segment starts; it is cut into gridDim.x equal CONTIGUOUS chunks, so a CTA
 //     does one merge-path binary search for each end of its chunk (no separate
 //     partition kernel, no `mp` allocation) and then walks its chunk tile by tile;
-//   * per tile the segment starts, the source vertex and (row_offset - start) of
-//     up to SEG_T segments are staged in shared memory; an arc finds its segment
-//     with a binary search over that staged slice;
+//   * the segment starts, the source vertex and (row_offset - start) of up to SEG_T
+//     segments are staged in shared memory once per window; an arc finds its segment
+//     with a binary search over only the staged segments its tile touches;
 //   * arcs are assigned to threads strided by NT, so the 32 lanes of a warp read
 //     32 consecutive column indices (one 128-byte line) whenever they sit in the
 //     same segment;
@@ -35,7 +35,6 @@ struct LbsSmem {
     uint32_t base[SEG_T];    // offsets[vertex_j] - start_j  (so edge_id = base + arc)
     int vert[SEG_T];         // vertex_j
     uint32_t bounds[4];      // s0, a0, s1, a1
-    uint32_t a_end, s_next;
 };
 
 // Number of segment starts that precede diagonal d in the merged order
@@ -52,9 +51,8 @@ __device__ __forceinline__ uint32_t merge_path_segments(const uint32_t *scanned,
     return (uint32_t)lo;
 }
 
-// Largest j in [0, ns) with start[j] <= arc.  Requires start[0] <= arc.
-__device__ __forceinline__ int lbs_locate(const uint32_t *start, int ns, uint32_t arc) {
-    int lo = 0, hi = ns;
+// Largest j in [lo, hi) with start[j] <= arc.  Requires start[lo] <= arc.
+__device__ __forceinline__ int lbs_locate(const uint32_t *start, int lo, int hi, uint32_t arc) {
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if (start[mid] <= arc) lo = mid;
@@ -63,10 +61,14 @@ __device__ __forceinline__ int lbs_locate(const uint32_t *start, int ns, uint32_
     return lo;
 }
 
-// Walks this CTA's chunk.  For every tile calls
-//     body(first_arc, n_arcs (<= NT*VT), ns (staged segments), first_seg)
-// with the staged slice valid in `sm`; body is called by ALL threads and must
-// end with the CTA converged (it may __syncthreads()).
+// Walks this CTA's chunk.  Segments are staged one WINDOW (up to SEG_T segments) at a
+// time; a window is cut into tiles of up to NT*VT arcs.  For every tile calls
+//     body(first_arc, n_arcs, j_lo, j_hi, first_seg)
+// where the staged segments [j_lo, j_hi) (window-relative; slot = first_seg + j) cover
+// the tile's arcs and sm.start[j_lo] <= first_arc.  There is NO CTA barrier between the
+// tiles of a window (the staged slice is read-only, every thread derives the tile
+// bounds itself), so warps run ahead of each other freely; the only barriers are the
+// two around a window refill.  body must not use CTA-wide barriers.
 template <int NT, int VT, int SEG_T, class Body>
 __device__ __forceinline__ void lbs_for_each_tile(const LbsArgs &a, LbsSmem<NT, VT, SEG_T> &sm, Body body) {
     constexpr uint32_t ARC_T = NT * VT;
@@ -88,28 +90,33 @@ __device__ __forceinline__ void lbs_for_each_tile(const LbsArgs &a, LbsSmem<NT, 
     if (a0 >= a1) return;
     uint32_t cur_s = s0 > 0 ? s0 - 1 : 0;   // segment that contains arc a0
     uint32_t cur_a = a0;
-    while (cur_a < a1) {
+    while (cur_a < a1) {                     // one iteration per window
         const int ns = (int)min((uint32_t)SEG_T, s1 - cur_s);
         for (int j = threadIdx.x; j < ns; j += NT) {
             const uint32_t st = __ldg(a.scanned + cur_s + j);
             const int v = __ldg(a.frontier + cur_s + j);
             sm.start[j] = st;
             sm.vert[j] = v;
-            sm.base[j] = __ldg(a.offsets + v) - st;
-        }
-        if (threadIdx.x == 0) {
-            // arcs of segments that are not staged must wait for the next tile
-            uint32_t lim = (cur_s + (uint32_t)ns < s1) ? __ldg(a.scanned + cur_s + ns) : a1;
-            uint32_t e = a1 - cur_a > ARC_T ? cur_a + ARC_T : a1;
-            sm.a_end = e < lim ? e : lim;
+            sm.base[j] = (v >= 0 ? __ldg(a.offsets + v) : 0u) - st;
         }
         __syncthreads();
-        const uint32_t a_end = sm.a_end;
-        body(cur_a, a_end - cur_a, ns, cur_s);
-        if (threadIdx.x == 0) sm.s_next = cur_s + (uint32_t)lbs_locate(sm.start, ns, a_end);
-        __syncthreads();
-        cur_s = sm.s_next;   // (the next write of s_next / a_end / start[] is ordered by the sync above
-        cur_a = a_end;       //  and by the staging sync of the next iteration)
+        // arcs of segments that are not staged wait for the next window
+        uint32_t win_end = a1;
+        if (cur_s + (uint32_t)ns < s1) {
+            const uint32_t lim = __ldg(a.scanned + cur_s + ns);
+            if (lim < win_end) win_end = lim;
+        }
+        int j_lo = 0;                        // sm.start[0] <= cur_a by construction
+        while (cur_a < win_end) {
+            const uint32_t a_end = win_end - cur_a > ARC_T ? cur_a + ARC_T : win_end;
+            j_lo = lbs_locate(sm.start, j_lo, ns, cur_a);
+            const int j_hi = lbs_locate(sm.start, j_lo, ns, a_end - 1) + 1;
+            body(cur_a, a_end - cur_a, j_lo, j_hi, cur_s);
+            cur_a = a_end;
+        }
+        // the next window starts at the segment that contains arc win_end
+        cur_s += (uint32_t)lbs_locate(sm.start, j_lo, ns, win_end);
+        __syncthreads();                     // everyone is done reading this window
     }
 }
 

@@ -87,7 +87,7 @@ template <class Value, class ROp, class ValueFn, int NT, int VT, int SEG_T>
 __global__ void __launch_bounds__(NT) lbs_segreduce_kernel(LbsArgs a, ValueFn vf, Value *__restrict__ reduced,
                                                            int scatter) {
     __shared__ LbsSmem<NT, VT, SEG_T> sm;
-    lbs_for_each_tile<NT, VT, SEG_T>(a, sm, [&](uint32_t first_arc, uint32_t n_arcs, int ns, uint32_t first_seg) {
+    lbs_for_each_tile<NT, VT, SEG_T>(a, sm, [&](uint32_t first_arc, uint32_t n_arcs, int j_lo, int j_hi, uint32_t first_seg) {
         const unsigned lane = lane_id();
         int seg[VT];
         Value x[VT];
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(NT) lbs_segreduce_kernel(LbsArgs a, ValueFn vf
             x[i] = ROp::neutral();
             if (k < n_arcs) {
                 const uint32_t arc = first_arc + k;
-                const int j = lbs_locate(sm.start, ns, arc);
+                const int j = lbs_locate(sm.start, j_lo, j_hi, arc);
                 const uint32_t eid = sm.base[j] + arc;
                 seg[i] = j;
                 x[i] = vf(sm.vert[j], ld_stream(a.indices + eid), eid);
@@ -118,7 +118,6 @@ __global__ void __launch_bounds__(NT) lbs_segreduce_kernel(LbsArgs a, ValueFn vf
             if (j >= 0 && (lane == 31 || jn != j))
                 ROp::combine(reduced + (scatter ? (uint32_t)sm.vert[j] : first_seg + (uint32_t)j), v);
         }
-        __syncthreads();   // sm.vert is re-staged by the next tile
     });
 }
 
