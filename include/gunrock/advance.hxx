@@ -1,0 +1,183 @@
+// advance.hxx -- the advance operators of gunrock::oprtr::advance with the reference
+// signatures (gunrock/src/advance.hxx:20-25, 69-74, 86-91, 108-114), implemented on the
+// B200 engine kernels (include/b200/*.cuh) instead of mgpu transform_scan + transform_lbs
+// + transform_compact.  User functors are instantiated into those kernels here, in the
+// caller's translation unit.
+//
+// Output layout of advance_forward_kernel:
+//   default                      compacted: only accepted neighbours, no -1 holes (advance
+//                                + the `!= -1` filter fused); return value = items written.
+//   -DB200_ADVANCE_RAW_OUTPUT    reference layout out[idx] = nbr | -1 for every arc,
+//                                return value = m_F (advance.hxx:60,66).
+// Either way a following filter_kernel yields the same frontier, so enactors written
+// against the reference work unchanged.
+#pragma once
+#include "b200/operators.cuh"
+#include "frontier.hxx"
+#include "intrinsics.hxx"
+
+namespace gunrock {
+namespace oprtr {
+namespace advance {
+
+namespace detail {
+inline void check(cudaError_t e) { mgpu::throw_on_error(e); }
+
+// Adapts a reference-style Functor (static cond_advance/apply_advance taking the
+// problem's data_slice_t*) to the engine's probe/commit protocol.  Both halves are
+// always evaluated, exactly like advance.hxx:57-58.
+template <typename Problem, typename Functor, bool idempotence>
+struct RefFunctorOp {
+    typename Problem::data_slice_t *data;
+    int iteration;
+    __device__ __forceinline__ bool probe(int, int, uint32_t) const { return true; }
+    __device__ __forceinline__ bool commit(int src, int dst, uint32_t eid, uint32_t rank, uint32_t out_idx) const {
+        const bool cond = Functor::cond_advance(src, dst, (int)eid, (int)rank, (int)out_idx, data, iteration);
+        const bool applied = Functor::apply_advance(src, dst, (int)eid, (int)rank, (int)out_idx, data, iteration);
+        return idempotence ? true : (cond && applied);
+    }
+};
+
+// degree scan of `input` over `offsets`; also mirrors the scan into the graph's
+// d_scanned_row_offsets like the reference does (advance.hxx:40).
+inline void scan_frontier(b200_workspace *ws, const int *frontier, size_t len, const int *offsets, int *mirror,
+                          size_t mirror_capacity) {
+    check(b200::reset_counters(ws));
+    check(b200::launch_frontier_scan(ws, frontier, (uint32_t)len, reinterpret_cast<const uint32_t *>(offsets)));
+    if (mirror && len <= mirror_capacity)
+        check(cudaMemcpyAsync(mirror, ws->d_scanned, sizeof(int) * len, cudaMemcpyDeviceToDevice, b200::ws_stream(ws)));
+}
+}  // namespace detail
+
+template <typename Problem, typename Functor, bool idempotence, bool has_output>
+int advance_forward_kernel(std::shared_ptr<Problem> problem, std::shared_ptr<frontier_t<int>> &input,
+                           std::shared_ptr<frontier_t<int>> &output, int iteration, standard_context_t &context) {
+    const size_t len = input->size();
+    if (!len) {
+        if (has_output) output->resize(0);
+        return 0;
+    }
+    graph_device_t &g = *problem->gslice;
+    if (b200_ctx_reserve(context.engine(), (int64_t)len) != B200_OK) throw cuda_exception_t(cudaErrorMemoryAllocation);
+    b200_workspace *ws = context.workspace();
+    const int *in = input->data()->data();
+    detail::scan_frontier(ws, in, len, g.d_row_offsets.data(), g.d_scanned_row_offsets.data(), g.d_scanned_row_offsets.size());
+    const b200::LbsArgs a = b200::make_lbs_args(ws, in, (uint32_t)len, reinterpret_cast<const uint32_t *>(g.d_row_offsets.data()),
+                                                g.d_col_indices.data());
+    detail::RefFunctorOp<Problem, Functor, idempotence> op{problem->d_data_slice.data(), iteration};
+    int *out = has_output ? output->data()->data() : nullptr;
+    const unsigned long long cap = has_output ? output->capacity() : 0;
+    if (!has_output) {
+        detail::check(b200::launch_lbs_advance<b200::OUT_NONE, false>(ws, a, op, out, cap));
+    } else {
+#ifdef B200_ADVANCE_RAW_OUTPUT
+        detail::check(b200::launch_lbs_advance<b200::OUT_RAW, false>(ws, a, op, out, cap));
+#else
+        detail::check(b200::launch_lbs_advance<b200::OUT_COMPACT, false>(ws, a, op, out, cap));
+#endif
+    }
+    detail::check(b200::read_counters(ws));
+    if (!has_output) return 0;
+    const size_t produced = (size_t)ws->h_counters[B200_CNT_OUT];
+    output->resize(produced);   // prints the reference's overflow message and exits if it does not fit
+    return (int)produced;
+}
+
+// dense[v] = cond_sparse_to_dense(v) ? 1 : 0 for every v in `sparse` (advance.hxx:69-84).
+template <typename Problem, typename Functor>
+void sparse_to_dense_kernel(std::shared_ptr<Problem> problem, std::shared_ptr<frontier_t<int>> &sparse,
+                            std::shared_ptr<frontier_t<int>> &dense, int iteration, standard_context_t &context) {
+    const int *items = sparse->data()->data();
+    int *flags = dense->data()->data();
+    typename Problem::data_slice_t *data = problem->d_data_slice.data();
+    transform([=] __device__(int idx) {
+        const int v = items[idx];
+        flags[v] = Functor::cond_sparse_to_dense(v, data, iteration) ? 1 : 0;
+    }, sparse->size(), context);
+}
+
+namespace detail {
+template <typename Problem, typename Functor>
+struct GenUnvisitedPred {
+    const int *items;
+    typename Problem::data_slice_t *data;
+    int iteration;
+    __device__ __forceinline__ bool operator()(uint32_t idx, int &item) const {
+        item = items[idx];
+        return Functor::cond_gen_unvisited(item, data, iteration);
+    }
+};
+
+// One thread per unvisited vertex; stops at the first in-neighbour that is in the
+// frontier flags and wins apply_advance.  (The reference expands every in-arc of every
+// unvisited vertex through LBS, advance.hxx:140-155; results are identical because
+// apply_advance can succeed only once per vertex.)
+template <typename Problem, typename Functor>
+__global__ void pull_list_kernel(int *unvisited, uint32_t count, const int *__restrict__ col_offsets,
+                                 const int *__restrict__ row_indices, const int *__restrict__ flags_in, int *flags_out,
+                                 typename Problem::data_slice_t *data, int iteration, unsigned long long *arcs) {
+    unsigned long long seen = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const int v = unvisited[i];
+        if (v < 0) continue;
+        const int b = col_offsets[v], e = col_offsets[v + 1];
+        for (int k = b; k < e; ++k) {
+            const int nbr = row_indices[k];
+            ++seen;
+            if (flags_in[nbr] && Functor::apply_advance(nbr, v, k, k - b, k, data, iteration)) {
+                flags_out[v] = 1;
+                unvisited[i] = -1;
+                break;
+            }
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) seen += __shfl_xor_sync(0xffffffffu, seen, d);
+    if ((threadIdx.x & 31) == 0 && seen) atomicAdd(arcs, seen);
+}
+}  // namespace detail
+
+// compact {item in indices : cond_gen_unvisited(item)} (advance.hxx:86-106); order preserved.
+template <typename Problem, typename Functor>
+int gen_unvisited_kernel(std::shared_ptr<Problem> problem, std::shared_ptr<frontier_t<int>> &indices,
+                         std::shared_ptr<frontier_t<int>> &unvisited, int iteration, standard_context_t &context) {
+    const size_t len = indices->size();
+    if (!len) {
+        unvisited->resize(0);
+        return 0;
+    }
+    if (b200_ctx_reserve(context.engine(), (int64_t)len) != B200_OK) throw cuda_exception_t(cudaErrorMemoryAllocation);
+    b200_workspace *ws = context.workspace();
+    detail::check(b200::reset_counters(ws));
+    detail::GenUnvisitedPred<Problem, Functor> pred{indices->data()->data(), problem->d_data_slice.data(), iteration};
+    detail::check(b200::launch_compact(ws, pred, (uint32_t)len, unvisited->data()->data(), unvisited->capacity(),
+                                       ws->d_counters + B200_CNT_OUT, ws->d_counters + B200_CNT_OVERFLOW));
+    detail::check(b200::read_counters(ws));
+    unvisited->resize((size_t)ws->h_counters[B200_CNT_OUT]);
+    return (int)unvisited->size();
+}
+
+// Pull step (advance.hxx:108-160): for every v in `unvisited` whose in-neighbourhood
+// meets the frontier flags `bitmap`, apply_advance(nbr, v) runs, bitmap_out[v] = 1 and
+// the list entry becomes -1.  Returns the number of in-arcs inspected.
+template <typename Problem, typename Functor>
+int advance_backward_kernel(std::shared_ptr<Problem> problem, std::shared_ptr<frontier_t<int>> &unvisited,
+                            std::shared_ptr<frontier_t<int>> &bitmap, std::shared_ptr<frontier_t<int>> &bitmap_out,
+                            int iteration, standard_context_t &context) {
+    const size_t len = unvisited->size();
+    if (!len) return 0;
+    graph_device_t &g = *problem->gslice;
+    b200_workspace *ws = context.workspace();
+    detail::check(b200::reset_counters(ws));
+    const unsigned grid = (unsigned)std::min<size_t>((len + 255) / 256, (size_t)ws->num_sms * 16);
+    detail::pull_list_kernel<Problem, Functor><<<grid, 256, 0, context.stream()>>>(
+        unvisited->data()->data(), (uint32_t)len, g.d_col_offsets.data(), g.d_row_indices.data(), bitmap->data()->data(),
+        bitmap_out->data()->data(), problem->d_data_slice.data(), iteration, ws->d_counters + B200_CNT_ARCS);
+    ws->launches++;
+    detail::check(cudaGetLastError());
+    detail::check(b200::read_counters(ws));
+    return (int)ws->h_counters[B200_CNT_ARCS];
+}
+
+}  // namespace advance
+}  // namespace oprtr
+}  // namespace gunrock

@@ -1,0 +1,50 @@
+// bfs_functor.hxx -- the BFS functor set (names and argument lists of
+// gunrock/src/bfs/bfs_functor.hxx:7-53).
+#pragma once
+#include "bfs/bfs_problem.hxx"
+
+namespace gunrock {
+namespace bfs {
+
+struct bfs_functor_t {
+    typedef bfs_problem_t::data_slice_t slice_t;
+
+    // filter: drop the -1 holes an un-compacted advance leaves
+    static __device__ __forceinline__ bool cond_filter(int idx, slice_t *data, int iteration) { return idx != -1; }
+
+    // uniquify: label a vertex the first time it is seen.  Valid for every source and for
+    // vertex 0 (the reference's version only accepts idx > 0 and labels > 0);
+    // exactness comes from the visited-bit test-and-set that precedes this call.
+    static __device__ __forceinline__ bool cond_uniq(int idx, slice_t *data, int iteration) {
+        if (idx < 0) return false;
+        const int seen = data->d_labels[idx];
+        if (seen >= 0 && seen <= iteration) return false;
+        data->d_labels[idx] = iteration + 1;
+        return true;
+    }
+
+    // advance: visit dst if nobody has yet; the compare-and-swap decides the winner
+    static __device__ __forceinline__ bool cond_advance(int src, int dst, int edge_id, int rank, int output_idx,
+                                                        slice_t *data, int iteration) {
+        return data->d_labels[dst] == -1;
+    }
+    static __device__ __forceinline__ bool apply_advance(int src, int dst, int edge_id, int rank, int output_idx,
+                                                         slice_t *data, int iteration) {
+        return atomicCAS(data->d_labels + dst, -1, iteration + 1) == -1;
+    }
+
+    // push -> pull hand-over
+    static __device__ __forceinline__ bool cond_sparse_to_dense(int idx, slice_t *data, int iteration) {
+        return data->d_labels[idx] == iteration;
+    }
+    static __device__ __forceinline__ bool cond_gen_unvisited(int idx, slice_t *data, int iteration) {
+        return data->d_labels[idx] == -1;
+    }
+
+    // neighborhood-reduce hooks (unused by BFS itself)
+    static __device__ __forceinline__ int get_value_to_reduce(int idx, slice_t *data, int iteration) { return iteration; }
+    static __device__ __forceinline__ void write_reduced_value(int item, int val, slice_t *data, int iteration) {}
+};
+
+}  // namespace bfs
+}  // namespace gunrock
