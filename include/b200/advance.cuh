@@ -19,7 +19,19 @@
 
 namespace b200 {
 
-enum { OUT_NONE = 0, OUT_COMPACT = 1, OUT_RAW = 2 };
+enum { OUT_NONE = 0, OUT_COMPACT = 1, OUT_RAW = 2, OUT_ROUTED = 3 };
+
+// OUT_ROUTED (multi-GPU push): every accepted vertex goes to the box of its owner
+// (op.route(u) in [0, num_dest)); box[me] is this rank's next frontier, the others are
+// the per-peer send buffers of the alltoallv that follows.  Bucketing happens inside the
+// advance kernel's flush, so no separate partition pass runs before the exchange.
+constexpr int MAX_DEST = 8;
+struct RoutedOut {
+    int *box[MAX_DEST];
+    unsigned long long capacity[MAX_DEST];
+    unsigned long long *count;   // [MAX_DEST] device counters
+    int num_dest;
+};
 
 // DEG_SUM: also accumulate sum(deg(u)) over the emitted vertices into
 // counters[B200_CNT_AUX] (one atomic per CTA) so the next level's m_F -- the input
@@ -33,25 +45,77 @@ enum { OUT_NONE = 0, OUT_COMPACT = 1, OUT_RAW = 2 };
 template <class Op, int OUT_MODE, bool DEG_SUM, int NT, int VT, int SEG_T>
 __global__ void __launch_bounds__(NT) lbs_advance_kernel(LbsArgs a, Op op, int *__restrict__ out,
                                                          unsigned long long out_capacity,
-                                                         unsigned long long *counters) {
+                                                         unsigned long long *counters, RoutedOut routed) {
     constexpr int NW = NT / 32;
+    constexpr bool STAGED = OUT_MODE == OUT_COMPACT || OUT_MODE == OUT_ROUTED;
     constexpr int WSTAGE = 32 * VT * 2;      // a tile adds at most 32*VT per warp
     __shared__ LbsSmem<NT, VT, SEG_T> sm;
-    __shared__ int wstage[OUT_MODE == OUT_COMPACT ? NW : 1][OUT_MODE == OUT_COMPACT ? WSTAGE : 1];
+    __shared__ int wstage[STAGED ? NW : 1][STAGED ? WSTAGE : 1];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    int *stage = wstage[OUT_MODE == OUT_COMPACT ? warp : 0];
+    int *stage = wstage[STAGED ? warp : 0];
     uint32_t wcnt = 0;                       // warp-uniform fill of this warp's stage
     unsigned long long deg_sum = 0;
 
     auto flush = [&]() {
         __syncwarp();
+        if constexpr (OUT_MODE == OUT_ROUTED) {
+            // pass 1: how many staged vertices go to each destination (warp totals)
+            uint32_t cnt[MAX_DEST];
+#pragma unroll
+            for (int p = 0; p < MAX_DEST; ++p) cnt[p] = 0;
+            for (uint32_t k = lane; k < wcnt; k += 32) {
+                const int d = op.route(stage[k]);
+#pragma unroll
+                for (int p = 0; p < MAX_DEST; ++p) cnt[p] += (d == p);
+            }
+            unsigned long long base[MAX_DEST];
+#pragma unroll
+            for (int p = 0; p < MAX_DEST; ++p) {
+                base[p] = 0;
+                if (p < routed.num_dest) {
+                    const uint32_t c = warp_sum(cnt[p]);
+                    if (c) {
+                        if (lane == 0) base[p] = atomicAdd(&routed.count[p], (unsigned long long)c);
+                        base[p] = __shfl_sync(FULL_MASK, base[p], 0);
+                        if (lane == 0 && base[p] + c > routed.capacity[p]) counters[B200_CNT_OVERFLOW] = 1ull;
+                    }
+                }
+            }
+            // pass 2: scatter, 32 staged vertices at a time, keeping each destination's run contiguous
+            for (uint32_t k0 = 0; k0 < wcnt; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                const int u = k < wcnt ? stage[k] : -1;
+                const int d = k < wcnt ? op.route(u) : -1;
+#pragma unroll
+                for (int p = 0; p < MAX_DEST; ++p) {
+                    if (p < routed.num_dest) {
+                        const unsigned mask = __ballot_sync(FULL_MASK, d == p);
+                        if (d == p) {
+                            const unsigned long long pos = base[p] + __popc(mask & lanemask_lt());
+                            if (pos < routed.capacity[p]) routed.box[p][pos] = u;
+                        }
+                        base[p] += __popc(mask);
+                    }
+                }
+                if (DEG_SUM && u >= 0 && op.route_is_local(d)) {
+                    const uint32_t r = (uint32_t)u >> a.row_shift;
+                    deg_sum += __ldg(a.offsets + r + 1) - __ldg(a.offsets + r);
+                }
+            }
+            wcnt = 0;
+            __syncwarp();
+            return;
+        }
         unsigned long long g = 0;
         if (lane == 0) g = atomicAdd(&counters[B200_CNT_OUT], (unsigned long long)wcnt);
         g = __shfl_sync(FULL_MASK, g, 0);
         for (uint32_t k = lane; k < wcnt; k += 32) {
             const int u = stage[k];
             if (g + k < out_capacity) out[g + k] = u;
-            if (DEG_SUM) deg_sum += __ldg(a.offsets + u + 1) - __ldg(a.offsets + u);
+            if (DEG_SUM) {
+                const uint32_t r = (uint32_t)u >> a.row_shift;
+                deg_sum += __ldg(a.offsets + r + 1) - __ldg(a.offsets + r);
+            }
         }
         if (lane == 0 && g + wcnt > out_capacity) counters[B200_CNT_OVERFLOW] = 1ull;
         wcnt = 0;
@@ -89,16 +153,16 @@ __global__ void __launch_bounds__(NT) lbs_advance_kernel(LbsArgs a, Op op, int *
                 }
             } else {
                 if (cand[i]) emit = op.commit(src[i], dst[i], eid[i], rank[i], first_arc + k);
-                if (OUT_MODE == OUT_COMPACT) {
+                if (STAGED) {
                     const unsigned mask = __ballot_sync(FULL_MASK, emit);
                     if (emit) stage[wcnt + __popc(mask & lanemask_lt())] = dst[i];
                     wcnt += __popc(mask);
                 }
             }
         }
-        if (OUT_MODE == OUT_COMPACT && wcnt > WSTAGE - 32 * VT) flush();
+        if (STAGED && wcnt > WSTAGE - 32 * VT) flush();
     });
-    if (OUT_MODE == OUT_COMPACT && wcnt) flush();
+    if (STAGED && wcnt) flush();
     if (DEG_SUM) {
         __shared__ unsigned long long s_deg;
         if (threadIdx.x == 0) s_deg = 0;
@@ -180,6 +244,89 @@ struct SsspRelaxOp {
 };
 
 // ---------------------------------------------------------------------------
+// Cyclic 1D vertex partition (multi-GPU): P = 2^log_p ranks, vertex v is owned by rank
+// v & (P-1) and is row v >> log_p of that rank's CSR (global column ids).  Every bitmap
+// is indexed "rank-major": bit(v) = owner(v) * n_local + (v >> log_p), so a rank's own
+// slice is the contiguous word range [me * n_local/32, (me+1) * n_local/32) and
+// ncclAllGather of the slices yields the whole bitmap in place.  P = 1 is the identity.
+// ---------------------------------------------------------------------------
+struct Partition {
+    uint32_t log_p;      // log2(P)
+    uint32_t me;         // this rank
+    uint32_t n_local;    // vertices per rank (multiple of 32)
+    __host__ __device__ __forceinline__ uint32_t owner(uint32_t v) const { return v & ((1u << log_p) - 1u); }
+    __host__ __device__ __forceinline__ uint32_t row(uint32_t v) const { return v >> log_p; }
+    __host__ __device__ __forceinline__ uint32_t bit(uint32_t v) const { return owner(v) * n_local + row(v); }
+};
+
+// BFS push on one rank's slice.  `known` is an n-bit map: exact "visited" for owned
+// vertices, "already sent to its owner / known visited" for the others, so every remote
+// vertex crosses NVLink at most once per sending rank over the whole traversal.
+struct BfsPushPartOp {
+    uint32_t *known;
+    int *labels;         // local: labels[row(v)]
+    int next_label;
+    Partition part;
+    __device__ __forceinline__ bool probe(int, int dst, uint32_t) const {
+        const uint32_t b = part.bit((uint32_t)dst);
+        return !((known[b >> 5] >> (b & 31)) & 1u);
+    }
+    __device__ __forceinline__ bool commit(int, int dst, uint32_t, uint32_t, uint32_t) const {
+        const uint32_t b = part.bit((uint32_t)dst);
+        const uint32_t bit = 1u << (b & 31);
+        if (atomicOr(known + (b >> 5), bit) & bit) return false;
+        if (part.owner((uint32_t)dst) == part.me) labels[part.row((uint32_t)dst)] = next_label;
+        return true;
+    }
+    __device__ __forceinline__ int route(int u) const { return (int)part.owner((uint32_t)u); }
+    __device__ __forceinline__ bool route_is_local(int d) const { return d == (int)part.me; }
+};
+
+// Receiver side of the push exchange: vertices owned by this rank that peers discovered.
+// Test-and-set the visited bit; survivors get their label and join the next frontier
+// (appended after the local discoveries: same counter).  This is the uniquify filter of
+// the multi-GPU path.
+static __global__ void bfs_absorb_kernel(const int *__restrict__ inbox, uint32_t count, uint32_t *known, int *labels,
+                                         int next_label, Partition part, int *next_frontier,
+                                         unsigned long long capacity, unsigned long long *next_count,
+                                         unsigned long long *counters, const uint32_t *__restrict__ offsets) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool fresh = false;
+    int u = -1;
+    if (i < count) {
+        u = inbox[i];
+        const uint32_t b = part.bit((uint32_t)u);
+        const uint32_t bit = 1u << (b & 31);
+        fresh = !(known[b >> 5] & bit) && !(atomicOr(known + (b >> 5), bit) & bit);
+        if (fresh) labels[part.row((uint32_t)u)] = next_label;
+    }
+    const unsigned mask = __ballot_sync(FULL_MASK, fresh);
+    if (mask) {
+        unsigned long long base = 0;
+        const unsigned leader = __ffs(mask) - 1;
+        if (lane_id() == leader) base = atomicAdd(next_count, (unsigned long long)__popc(mask));
+        base = __shfl_sync(FULL_MASK, base, leader);
+        unsigned long long deg = 0;
+        if (fresh) {
+            const unsigned long long pos = base + __popc(mask & lanemask_lt());
+            if (pos < capacity) next_frontier[pos] = u;
+            else counters[B200_CNT_OVERFLOW] = 1ull;
+            const uint32_t r = part.row((uint32_t)u);
+            deg = __ldg(offsets + r + 1) - __ldg(offsets + r);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) deg += __shfl_xor_sync(FULL_MASK, deg, d);
+        if (lane_id() == leader && deg) atomicAdd(&counters[B200_CNT_AUX], deg);
+    }
+}
+
+// dst[i] |= src[i]  (fold the all-gathered frontier bitmap into `known` after a pull level)
+static __global__ void bitmap_or_kernel(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, size_t words) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) dst[i] |= src[i];
+}
+
+// ---------------------------------------------------------------------------
 // Pull (bottom-up) BFS step over bitmaps: replaces gen_unvisited_kernel +
 // sparse_to_dense_kernel + advance_backward_kernel + filter_kernel
 // (advance.hxx:69-160, bfs_enactor.hxx:74-113).  One lane per vertex, one warp
@@ -188,13 +335,16 @@ struct SsspRelaxOp {
 // each iteration).  The warp owns its word of next/visited, so
 // those are plain stores.
 // ---------------------------------------------------------------------------
+// Partitioned form: the warp walks this rank's LOCAL rows (word w of its slice), `frontier_bm`
+// is the whole (all-gathered) frontier bitmap, `next_bm` / `visited_bm` point at this rank's
+// slice of the next-frontier / known bitmaps, labels are local.
 template <int NT>
 __global__ void __launch_bounds__(NT) bfs_pull_kernel(uint32_t n, const uint32_t *__restrict__ offsets,
                                                       const int *__restrict__ indices,
                                                       const uint32_t *__restrict__ frontier_bm,
                                                       uint32_t *__restrict__ next_bm, uint32_t *__restrict__ visited_bm,
                                                       int *__restrict__ labels, int next_label,
-                                                      unsigned long long *counters) {
+                                                      unsigned long long *counters, Partition part) {
     const uint32_t num_words = (n + 31) >> 5;
     const uint32_t warps_total = (gridDim.x * NT) >> 5;
     const unsigned lane = lane_id();
@@ -206,9 +356,9 @@ __global__ void __launch_bounds__(NT) bfs_pull_kernel(uint32_t n, const uint32_t
         if (v < n && !((vis >> lane) & 1u)) {
             const uint32_t b = __ldg(offsets + v), e = __ldg(offsets + v + 1);
             for (uint32_t k = b; k < e; ++k) {
-                const int u = __ldg(indices + k);
+                const uint32_t ub = part.bit((uint32_t)__ldg(indices + k));
                 ++inspected;
-                if ((__ldg(frontier_bm + (u >> 5)) >> (u & 31)) & 1u) { found = true; break; }
+                if ((__ldg(frontier_bm + (ub >> 5)) >> (ub & 31)) & 1u) { found = true; break; }
             }
             if (found) {
                 labels[v] = next_label;

@@ -27,6 +27,7 @@ struct LbsArgs {
     const uint32_t *offsets;           // row (push) or column (pull) offsets [n+1]
     const int *indices;                // col (push) or row (pull) indices [m]
     uint32_t min_chunk;                // lower bound on the work items per CTA
+    uint32_t row_shift;                // row of vertex v in `offsets` is v >> row_shift (cyclic 1D partition: log2 P)
 };
 
 template <int NT, int VT, int SEG_T>
@@ -97,7 +98,7 @@ __device__ __forceinline__ void lbs_for_each_tile(const LbsArgs &a, LbsSmem<NT, 
             const int v = __ldg(a.frontier + cur_s + j);
             sm.start[j] = st;
             sm.vert[j] = v;
-            sm.base[j] = (v >= 0 ? __ldg(a.offsets + v) : 0u) - st;
+            sm.base[j] = (v >= 0 ? __ldg(a.offsets + (v >> a.row_shift)) : 0u) - st;
         }
         __syncthreads();
         // arcs of segments that are not staged wait for the next window

@@ -6,6 +6,7 @@
 // ctx-owned b200_workspace, so no launcher allocates.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstring>
 #include "advance.cuh"
 #include "segreduce.cuh"
 #include "tile_scan.cuh"
@@ -86,14 +87,17 @@ template <class Value, class ROp, class ValueFn> struct SegTag {};
 struct FrontierDegree {
     const int *frontier;
     const uint32_t *offsets;
+    uint32_t row_shift;
     __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
         const int v = frontier[i];
-        return v >= 0 ? __ldg(offsets + v + 1) - __ldg(offsets + v) : 0u;
+        if (v < 0) return 0u;
+        const uint32_t r = (uint32_t)v >> row_shift;
+        return __ldg(offsets + r + 1) - __ldg(offsets + r);
     }
 };
 
 inline LbsArgs make_lbs_args(const b200_workspace *ws, const int *d_frontier, uint32_t len,
-                             const uint32_t *offsets, const int *indices) {
+                             const uint32_t *offsets, const int *indices, uint32_t row_shift = 0) {
     LbsArgs a;
     a.frontier = d_frontier;
     a.num_segments = len;
@@ -102,22 +106,28 @@ inline LbsArgs make_lbs_args(const b200_workspace *ws, const int *d_frontier, ui
     a.offsets = offsets;
     a.indices = indices;
     a.min_chunk = LBS_MIN_CHUNK;
+    a.row_shift = row_shift;
     return a;
 }
 
 // degree scan of the frontier into ws->d_scanned, m_F into counters[TOTAL].
-inline cudaError_t launch_frontier_scan(b200_workspace *ws, const int *d_frontier, uint32_t len, const uint32_t *offsets) {
+inline cudaError_t launch_frontier_scan(b200_workspace *ws, const int *d_frontier, uint32_t len, const uint32_t *offsets,
+                                        uint32_t row_shift = 0) {
     if ((int64_t)len > ws->scanned_capacity) return cudaErrorInvalidValue;
-    FrontierDegree fn{d_frontier, offsets};
+    FrontierDegree fn{d_frontier, offsets, row_shift};
     return launch_scan(ws, fn, len, ws->d_scanned, ws->d_counters + B200_CNT_TOTAL);
 }
 
 // LBS advance over a frontier whose degree scan is already in the workspace.
 template <int OUT_MODE, bool DEG_SUM, class Op>
-cudaError_t launch_lbs_advance(b200_workspace *ws, const LbsArgs &a, Op op, int *d_out, unsigned long long capacity) {
+cudaError_t launch_lbs_advance(b200_workspace *ws, const LbsArgs &a, Op op, int *d_out, unsigned long long capacity,
+                               const RoutedOut *routed = nullptr) {
     auto k = lbs_advance_kernel<Op, OUT_MODE, DEG_SUM, LBS_NT, LBS_VT, LBS_SEG_T>;
     const int grid = persistent_grid<AdvTag<Op, OUT_MODE, DEG_SUM>>(k, LBS_NT, ws);
-    k<<<grid, LBS_NT, 0, ws_stream(ws)>>>(a, op, d_out, capacity, ws->d_counters);
+    RoutedOut r;
+    if (routed) r = *routed;
+    else memset(&r, 0, sizeof r);
+    k<<<grid, LBS_NT, 0, ws_stream(ws)>>>(a, op, d_out, capacity, ws->d_counters, r);
     ws->launches++;
     return cudaGetLastError();
 }

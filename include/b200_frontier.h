@@ -222,6 +222,52 @@ int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist
 int b200_pr_run(b200_ctx *ctx, const b200_graph *g, int max_iter, int scatter, float *d_current,
                 float *d_reduced, int64_t *h_frontier_lens, int *iterations, b200_stats *stats);
 
+/* ---- multi-GPU BFS: per-rank steps (new; the reference is single-GPU by design, README.md:4) -------
+ * Cyclic 1D vertex partition over P = 2^k <= 8 ranks: vertex v is owned by rank v mod P and is row
+ * v / P of that rank's CSR (column ids stay global).  Bitmaps are indexed rank-major:
+ * bit(v) = (v mod P) * n_local + v / P, so a rank's slice is contiguous and ncclAllGather of the
+ * slices rebuilds the whole bitmap.  One process drives one GPU; between the calls below the host
+ * layer issues the NCCL collectives (alltoall of counts + alltoallv of vertex ids after a push
+ * level, allgather of frontier-bitmap slices before a pull level). */
+typedef struct b200_mg_bfs_state {
+    int32_t rank, num_ranks;
+    int64_t n_global, n_local;        /* n_local = n_global / P, a multiple of 32 */
+    int32_t *labels;                  /* [n_local] local depths */
+    uint32_t *known;                  /* [n_global/32] visited (owned vertices) / already-sent (others) */
+    uint32_t *frontier_bitmap;        /* [n_global/32] all-gathered frontier of the current pull level */
+    uint32_t *next_slice;             /* [n_local/32] this rank's slice of the next frontier bitmap */
+    unsigned long long *box_counts;   /* [8] device counters of the per-destination boxes */
+} b200_mg_bfs_state;
+
+int b200_rmat_part_count(b200_ctx *ctx, int scale, int edge_factor, uint64_t seed, int rank, int num_ranks,
+                         int64_t *m_local);
+/* Local CSR of `rank`: n_local rows, global column ids, same ordering rules as b200_rmat_build_csr. */
+int b200_rmat_build_csr_part(b200_ctx *ctx, int scale, int edge_factor, uint64_t seed, int rank, int num_ranks,
+                             int64_t m_local, uint32_t *d_row_offsets /* [n_local+1] */,
+                             int32_t *d_col_indices /* [m_local] */);
+int b200_mg_bfs_init(b200_ctx *ctx, const b200_mg_bfs_state *s, int32_t src, int32_t *d_frontier,
+                     int64_t *frontier_len);
+/* One push level over the local frontier (global ids, all owned).  Local discoveries are labelled and
+ * appended to d_next_frontier, remote ones to d_send_boxes[owner] (bucketed inside the advance
+ * kernel).  h_counts[p] = items in box p (h_counts[rank] = local discoveries). */
+int b200_mg_bfs_push(b200_ctx *ctx, const b200_graph *g_local, const b200_mg_bfs_state *s, int level,
+                     const int32_t *d_frontier, int64_t frontier_len, int32_t *d_next_frontier,
+                     int32_t *const *d_send_boxes /* host array [P] of device pointers */, int64_t box_capacity,
+                     int64_t *h_counts /* [P] */, int64_t *arcs, int64_t *next_degree);
+/* Receiver side: label-if-unvisited over the vertices peers sent; survivors join d_next_frontier.
+ * *next_len = total length of the next frontier so far. */
+int b200_mg_bfs_absorb(b200_ctx *ctx, const b200_graph *g_local, const b200_mg_bfs_state *s, int level,
+                       const int32_t *d_inbox, int64_t count, int32_t *d_next_frontier, int64_t *next_len,
+                       int64_t *next_degree);
+/* One pull level over the local rows against s->frontier_bitmap; writes s->next_slice. */
+int b200_mg_bfs_pull(b200_ctx *ctx, const b200_graph *g_local, const b200_mg_bfs_state *s, int level,
+                     int64_t *found, int64_t *arcs_inspected, int64_t *found_degree);
+int b200_mg_bitmap_or(b200_ctx *ctx, uint32_t *d_dst, const uint32_t *d_src, int64_t words);
+int b200_mg_list_to_slice(b200_ctx *ctx, const b200_mg_bfs_state *s, const int32_t *d_list, int64_t len,
+                          uint32_t *d_slice);
+int b200_mg_slice_to_list(b200_ctx *ctx, const b200_mg_bfs_state *s, const uint32_t *d_slice, int32_t *d_list,
+                          int64_t *len);
+
 /* ---- host-buffer entry points (what test_bfs.cu times + extract: H2D, run, D2H) */
 typedef struct b200_host_graph b200_host_graph; /* graph_to_device result (graph.hxx:60-83) kept by the engine */
 int b200_host_graph_upload(b200_ctx *ctx, int64_t n, int64_t m, const uint32_t *h_row_offsets,

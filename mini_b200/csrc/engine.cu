@@ -307,7 +307,7 @@ int b200_advance_backward(b200_ctx *ctx, const b200_graph *g, const b200_problem
     const uint32_t *off = g->col_offsets ? g->col_offsets : g->row_offsets;
     const int32_t *idx = g->row_indices ? g->row_indices : g->col_indices;
     bfs_pull_kernel<256><<<ws->num_sms * 8, 256, 0, ws_stream(ws)>>>((uint32_t)g->n, off, idx, d_frontier_bitmap, d_next_bitmap,
-                                                                      p->visited_bitmap, p->labels, iteration + 1, ws->d_counters);
+                                                                      p->visited_bitmap, p->labels, iteration + 1, ws->d_counters, Partition{0, 0, (uint32_t)g->n});
     ws->launches++;
     B200_CUDA(cudaGetLastError());
     B200_CUDA(read_counters(ws));
@@ -401,7 +401,7 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
             if (tl) B200_CUDA(cudaEventRecord(ev[3 * level + 1], st));
             bfs_pull_kernel<256><<<ws->num_sms * 8, 256, 0, st>>>((uint32_t)n, pull_off, pull_idx, ctx->bm_frontier[bsel],
                                                                   ctx->bm_frontier[bsel ^ 1], ctx->bm_visited, d_labels,
-                                                                  level + 1, ws->d_counters);
+                                                                  level + 1, ws->d_counters, Partition{0, 0, (uint32_t)n});
             ws->launches++;
             B200_CUDA(cudaGetLastError());
             if (tl) B200_CUDA(cudaEventRecord(ev[3 * level + 2], st));

@@ -63,6 +63,44 @@ __global__ void keys_to_csr_kernel(const unsigned long long *keys, unsigned long
     }
 }
 
+// Cyclic 1D partition: keep the arcs whose tail is owned by `rank` (owner(v) = v & (P-1));
+// key = (local row << 32) | global column.  count_only => just count them.
+__global__ void rmat_part_keys_kernel(uint64_t key, int scale, unsigned long long npairs, uint32_t pmask, uint32_t log_p,
+                                      uint32_t rank, unsigned long long *keys, unsigned long long *counter, int count_only) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long rounds = (npairs + stride - 1) / stride;
+    unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long local = 0;
+    for (unsigned long long r = 0; r < rounds; ++r, e += stride) {
+        uint32_t u = 0, v = 0;
+        bool fu = false, fv = false;
+        if (e < npairs) {
+            rmat_pair(key, e, scale, u, v);
+            fu = (u & pmask) == rank;   // arc u -> v lives here
+            fv = (v & pmask) == rank;   // arc v -> u lives here
+        }
+        if (count_only) {
+            local += (fu ? 1 : 0) + (fv ? 1 : 0);
+            continue;
+        }
+        const unsigned mu = __ballot_sync(0xffffffffu, fu), mv = __ballot_sync(0xffffffffu, fv);
+        const unsigned total = __popc(mu) + __popc(mv);
+        if (total) {
+            unsigned long long base = 0;
+            const unsigned lane = threadIdx.x & 31;
+            if (lane == 0) base = atomicAdd(counter, (unsigned long long)total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned lt = (1u << lane) - 1u;
+            if (fu) keys[base + __popc(mu & lt)] = ((unsigned long long)(u >> log_p) << 32) | v;
+            if (fv) keys[base + __popc(mu) + __popc(mv & lt)] = ((unsigned long long)(v >> log_p) << 32) | u;
+        }
+    }
+    if (count_only) {
+        for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+        if ((threadIdx.x & 31) == 0 && local) atomicAdd(counter, local);
+    }
+}
+
 __global__ void fill_u32_kernel(uint32_t *p, unsigned long long count, uint32_t v) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) p[i] = v;
@@ -124,6 +162,63 @@ int b200_rmat_build_csr(b200_ctx *ctx, int scale, int edge_factor, uint64_t seed
     int s = cuda_status(cudaGetLastError());
     if (s == B200_OK)
         s = sort_and_emit(ctx, ka, kb, (long long)m, 1ll << scale, 32 + scale, d_row_offsets, d_col_indices, d_weights, weight_seed);
+    cudaFree(ka);
+    cudaFree(kb);
+    return s;
+}
+
+static int part_args_ok(int scale, int edge_factor, int rank, int num_ranks) {
+    if (scale < 1 || scale > 31 || edge_factor < 1) return 0;
+    if (num_ranks < 1 || num_ranks > 8 || (num_ranks & (num_ranks - 1))) return 0;
+    if (rank < 0 || rank >= num_ranks) return 0;
+    return ((1ll << scale) / num_ranks) % 32 == 0;
+}
+
+int b200_rmat_part_count(b200_ctx *ctx, int scale, int edge_factor, uint64_t seed, int rank, int num_ranks, int64_t *m_local) {
+    if (!ctx || !m_local || !part_args_ok(scale, edge_factor, rank, num_ranks)) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->ws.device));
+    cudaStream_t st = (cudaStream_t)ctx->ws.stream;
+    uint32_t log_p = 0;
+    while ((1 << log_p) < num_ranks) ++log_p;
+    unsigned long long *cnt = ctx->ws.d_counters + B200_CNT_AUX2;
+    B200_CUDA(cudaMemsetAsync(cnt, 0, sizeof(*cnt), st));
+    rmat_part_keys_kernel<<<ctx->ws.num_sms * 8, 256, 0, st>>>(rmat_key(seed), scale, (unsigned long long)edge_factor << scale,
+                                                               (uint32_t)num_ranks - 1, log_p, (uint32_t)rank, nullptr, cnt, 1);
+    B200_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    B200_CUDA(cudaMemcpyAsync(&h, cnt, sizeof h, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    *m_local = (int64_t)h;
+    return B200_OK;
+}
+
+int b200_rmat_build_csr_part(b200_ctx *ctx, int scale, int edge_factor, uint64_t seed, int rank, int num_ranks,
+                             int64_t m_local, uint32_t *d_row_offsets, int32_t *d_col_indices) {
+    if (!ctx || !d_row_offsets || !d_col_indices || m_local < 0 || m_local >= (1ll << 32) ||
+        !part_args_ok(scale, edge_factor, rank, num_ranks))
+        return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->ws.device));
+    cudaStream_t st = (cudaStream_t)ctx->ws.stream;
+    uint32_t log_p = 0;
+    while ((1 << log_p) < num_ranks) ++log_p;
+    const unsigned long long m = (unsigned long long)m_local;
+    unsigned long long *ka = nullptr, *kb = nullptr;
+    B200_CUDA(cudaMalloc(&ka, sizeof(unsigned long long) * (m ? m : 1)));
+    cudaError_t e = cudaMalloc(&kb, sizeof(unsigned long long) * (m ? m : 1));
+    if (e != cudaSuccess) { cudaFree(ka); return cuda_status(e); }
+    unsigned long long *cnt = ctx->ws.d_counters + B200_CNT_AUX2;
+    int s = cuda_status(cudaMemsetAsync(cnt, 0, sizeof(*cnt), st));
+    if (s == B200_OK) {
+        rmat_part_keys_kernel<<<ctx->ws.num_sms * 8, 256, 0, st>>>(rmat_key(seed), scale, (unsigned long long)edge_factor << scale,
+                                                                   (uint32_t)num_ranks - 1, log_p, (uint32_t)rank, ka, cnt, 0);
+        s = cuda_status(cudaGetLastError());
+    }
+    unsigned long long h = 0;
+    if (s == B200_OK) s = cuda_status(cudaMemcpyAsync(&h, cnt, sizeof h, cudaMemcpyDeviceToHost, st));
+    if (s == B200_OK) s = cuda_status(cudaStreamSynchronize(st));
+    if (s == B200_OK && h != m) s = B200_ERR_INVALID;   // m_local must come from b200_rmat_part_count
+    if (s == B200_OK)
+        s = sort_and_emit(ctx, ka, kb, (long long)m, (1ll << scale) / num_ranks, 32 + scale, d_row_offsets, d_col_indices, nullptr, 0);
     cudaFree(ka);
     cudaFree(kb);
     return s;

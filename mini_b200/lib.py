@@ -98,6 +98,15 @@ def load_library():
         "b200_bfs_run": ([vp, pg, i32, i32, f32, f32, vp, ps], i32),
         "b200_sssp_run": ([vp, pg, i32, vp, vp, ps], i32),
         "b200_pr_run": ([vp, pg, i32, i32, vp, vp, pi64, pi32, ps], i32),
+        "b200_rmat_part_count": ([vp, i32, i32, u64, i32, i32, pi64], i32),
+        "b200_rmat_build_csr_part": ([vp, i32, i32, u64, i32, i32, i64, vp, vp], i32),
+        "b200_mg_bfs_init": ([vp, vp, i32, vp, pi64], i32),
+        "b200_mg_bfs_push": ([vp, pg, vp, i32, vp, i64, vp, vp, i64, pi64, pi64, pi64], i32),
+        "b200_mg_bfs_absorb": ([vp, pg, vp, i32, vp, i64, vp, pi64, pi64], i32),
+        "b200_mg_bfs_pull": ([vp, pg, vp, i32, pi64, pi64, pi64], i32),
+        "b200_mg_bitmap_or": ([vp, vp, vp, i64], i32),
+        "b200_mg_list_to_slice": ([vp, vp, vp, i64, vp], i32),
+        "b200_mg_slice_to_list": ([vp, vp, vp, vp, pi64], i32),
         "b200_host_graph_upload": ([vp, i64, i64, vp, vp, vp, C.POINTER(vp)], i32),
         "b200_host_graph_free": ([vp, vp], i32),
         "b200_host_graph_view": ([vp, pg], i32),

@@ -1,0 +1,96 @@
+"""Partitioned (multi-GPU) BFS.
+ * On ONE GPU: P virtual ranks run as threads over ThreadComm, exercising the partition-aware kernels
+   (cyclic owner mapping, rank-major bitmaps, in-kernel routing, absorb, partitioned pull) bit-exactly
+   against the CPU oracle.
+ * With >= 2 GPUs (gpurun --gpus N): the same driver over NCCL (tests/run_dist_bfs.py under torchrun)."""
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+import oracle
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _virtual_ranks(scale, ef, seed, world, src, mode):
+    import mini_b200 as mb
+    from mini_b200 import dist as D
+    shared = D.ThreadComm.Shared(world)
+    out, errs = [None] * world, []
+
+    def work(rank):
+        try:
+            ctx = mb.Context(0)
+            g = D.build_rank_graph(ctx, scale, ef, seed, rank, world)
+            n = 1 << scale
+            rk = D.GpuRank(ctx, rank, world, n, g)
+            bfs = D.DistBFS(rk, D.ThreadComm(shared, rank), n, (2 * ef) << scale, mode=mode)
+            levels = bfs.run(src)
+            torch.cuda.synchronize()
+            out[rank] = (rk.labels.cpu().numpy(), g.offsets_host(), g.col_indices.cpu().numpy(), levels, bfs.levels)
+            ctx.close()
+        except BaseException as e:   # noqa: BLE001
+            errs.append(e)
+            shared.barrier.abort()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(600) for t in ts]
+    if errs:
+        raise errs[0]
+    return out
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+@pytest.mark.parametrize("mode", ["push", "beamer"])
+def test_partitioned_bfs_virtual_ranks(world, mode):
+    scale, ef, seed, src = 14, 16, 1, 0
+    o = oracle.rmat_csr(scale, ef, seed)
+    ref = oracle.bfs(o, src)
+    res = _virtual_ranks(scale, ef, seed, world, src, mode)
+    n = 1 << scale
+    labels = np.empty(n, np.int32)
+    for r, (lab, off, idx, levels, stats) in enumerate(res):
+        labels[r::world] = lab                       # vertex v = row * P + rank
+        rows = np.arange(r, n, world)
+        # the rank's CSR is exactly its rows of the global CSR
+        assert np.array_equal(np.diff(off), (o.offsets[rows + 1] - o.offsets[rows]))
+        k = min(len(rows), 50)
+        for i in range(k):
+            assert np.array_equal(idx[off[i]:off[i + 1]], o.indices[o.offsets[rows[i]]:o.offsets[rows[i] + 1]])
+    assert np.array_equal(labels, ref)
+    stats = res[0][4]
+    assert sum(l["discovered"] for l in stats) + 1 == int((ref >= 0).sum())
+    if mode == "beamer":
+        assert any(l["direction"] == "pull" for l in stats)
+    if world > 1 and mode == "push":
+        # each remote vertex is sent at most once per sender
+        assert sum(l["sent"] for l in stats) <= (world - 1) * n
+
+
+@pytest.mark.parametrize("src", [1, 77, 12345])
+def test_partitioned_bfs_other_sources(src):
+    scale, ef, seed, world = 14, 8, 3, 4
+    ref = oracle.bfs(oracle.rmat_csr(scale, ef, seed), src)
+    res = _virtual_ranks(scale, ef, seed, world, src, "beamer")
+    labels = np.empty(1 << scale, np.int32)
+    for r in range(world):
+        labels[r::world] = res[r][0]
+    assert np.array_equal(labels, ref)
+
+
+def test_nccl_ranks_if_multiple_gpus():
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    world = 2 if ngpu < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", os.path.join(ROOT, "tests", "run_dist_bfs.py"), "--scale", "16", "--backend", "nccl"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST_BFS_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
