@@ -278,5 +278,27 @@ def main():
     return run_single_gpu(args)
 
 
+def _main_with_clean_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torchrun notices) also
+    write to fd 1, so everything but our final line is diverted to stderr."""
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import io
+    buf = io.StringIO()
+    old, sys.stdout = sys.stdout, buf
+    try:
+        rc = main()
+    finally:
+        sys.stdout = old
+        lines = [l for l in buf.getvalue().splitlines() if l.startswith("{")]
+        other = [l for l in buf.getvalue().splitlines() if not l.startswith("{")]
+        for l in other:
+            print(l, file=sys.stderr)
+        if lines:
+            os.write(real_stdout, (lines[-1] + "\n").encode())
+        os.close(real_stdout)
+    return rc
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    sys.exit(_main_with_clean_stdout())

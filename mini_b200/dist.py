@@ -309,3 +309,44 @@ class DistBFS:
                     direction = PUSH
                 flen = found
         return level
+
+
+def verify_bfs_properties(rank_backend, comm, src: int):
+    """Size-independent BFS checks at full scale (no oracle needed), on the device with torch:
+    labels[src] == 0; the reached set is closed under arcs; an arc spans at most one level; every
+    reached vertex but the source has a neighbour one level up.  Returns (ok, level histogram)."""
+    import torch
+    r = rank_backend
+    world, me = r.world, r.rank
+    full = torch.empty(r.n_global, dtype=torch.int32, device=r.labels.device)
+    comm.all_gather_into(full, r.labels)                     # rank-major: full[p * n_local + row]
+    off = r.g.row_offsets.to(torch.int64) & 0xFFFFFFFF
+    deg = off[1:] - off[:-1]
+    ok = True
+    if src % world == me:
+        ok &= int(r.labels[src // world].item()) == 0
+    has_parent = torch.zeros(r.n_local, dtype=torch.bool, device=full.device)
+    step = 1 << 22                                           # rows per chunk: bounds the temporaries
+    for lo in range(0, r.n_local, step):
+        hi = min(lo + step, r.n_local)
+        a, b = int(off[lo].item()), int(off[hi].item())
+        if a == b:
+            continue
+        rows = torch.repeat_interleave(torch.arange(lo, hi, device=full.device), deg[lo:hi])
+        cols = r.g.col_indices[a:b].long()
+        lv = r.labels[rows]
+        lu = full[(cols % world) * r.n_local + cols // world]
+        ok &= bool(((lv >= 0) == (lu >= 0)).all())
+        reached = lv >= 0
+        if bool(reached.any()):
+            ok &= int((lv[reached] - lu[reached]).abs().max().item()) <= 1
+        has_parent[rows[reached & (lu == lv - 1)]] = True
+    mine = r.labels
+    need = mine > 0
+    ok &= bool((has_parent | ~need).all())
+    hist = torch.bincount((mine[mine >= 0]).long(), minlength=64)[:64]
+    tot = comm.all_reduce_sum([int(ok)] + hist.tolist())
+    hist_g = tot[1:]
+    while hist_g and hist_g[-1] == 0:
+        hist_g.pop()
+    return tot[0] == world, hist_g

@@ -18,6 +18,7 @@ def run(args) -> int:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl.%h.%p.log")   # keep NCCL's banner off stdout (one JSON line)
     dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
     scale = args.scale or 26
     ef = 16
@@ -95,6 +96,7 @@ def run(args) -> int:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
 
+    props_ok, level_hist = D.verify_bfs_properties(rk, comm, 0)
     all_launches = comm.all_reduce_sum([launches])[0]
     sent = sum(l["sent"] for l in levels)
     if rank == 0:
@@ -121,9 +123,10 @@ def run(args) -> int:
                          "note": "per-kernel roofline is reported by the N=1 line; exchange volume: "
                                  f"{sent * 4} bytes of vertex ids per BFS over NVLink"},
             "cpu_baseline": None,
+            "parity": {"bfs_properties_hold_at_full_scale": props_ok, "vertices_per_level": level_hist},
         }
         print(json.dumps(line))
     dist.barrier()
     ctx.close()
     dist.destroy_process_group()
-    return 0
+    return 0 if props_ok else 1

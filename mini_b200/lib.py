@@ -182,7 +182,10 @@ class Context:
             raise RuntimeError("mini_b200 needs a CUDA device (no CPU fallback)")
         torch.cuda.set_device(device)
         if stream == "torch":
-            stream = torch.cuda.current_stream(device).cuda_stream
+            # torch's default stream is the legacy default stream, whose handle is 0; pass the explicit
+            # cudaStreamLegacy handle (0x1) so the ctx really shares it (NULL would make the ctx create a
+            # private non-blocking stream that is NOT ordered with torch / NCCL work).
+            stream = torch.cuda.current_stream(device).cuda_stream or 1
         h = C.c_void_p()
         _check(self._L.b200_ctx_create(C.byref(h), device, C.c_void_p(stream) if stream else None), "b200_ctx_create")
         self._h = h
