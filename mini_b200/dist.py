@@ -312,7 +312,7 @@ class DistBFS:
 
 
 def verify_bfs_properties(rank_backend, comm, src: int):
-    """Size-independent BFS checks at full scale (no oracle needed), on the device with torch:
+    """Size-independent BFS checks at full scale, on the device with torch:
     labels[src] == 0; the reached set is closed under arcs; an arc spans at most one level; every
     reached vertex but the source has a neighbour one level up.  Returns (ok, level histogram)."""
     import torch
