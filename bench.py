@@ -150,6 +150,7 @@ def run_single_gpu(args):
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
     ctx = mb.Context(dev)
+    ctx.set_advance_impl(mb.ADVANCE_LBS if args.advance == "lbs" else mb.ADVANCE_QUAD)
     g = ctx.rmat_graph(scale, 16, 1)
     mode = {"push": mb.BFS_PUSH, "beamer": mb.BFS_BEAMER}[args.mode]
     sampler = ClockSampler(dev)
@@ -194,7 +195,7 @@ def run_single_gpu(args):
         except Exception:
             traffic = None
     roofline = {
-        "bound": "hbm", "kernel": "lbs_advance_kernel<BfsPushOp,COMPACT> (heaviest BFS level)",
+        "bound": "hbm", "kernel": ("quad_advance_kernel<BfsPushQ,COMPACT>" if args.advance == "quad" else "lbs_advance_kernel<BfsPushOp,COMPACT>") + " (heaviest BFS level)",
         "achieved": top_gbs, "peak": peak, "unit": "GB/s", "frac": top_gbs / peak, "traffic": traffic,
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": push_level_bytes(lv[top]), "launch_ms": lv_ms[top],
@@ -266,6 +267,8 @@ def main():
     ap.add_argument("--scale", type=int, default=0)
     ap.add_argument("--mode", default="push", choices=["push", "beamer"])
     ap.add_argument("--cpu-runs", type=int, default=3)
+    ap.add_argument("--advance", default="quad", choices=["quad", "lbs"],
+                    help="push-advance kernel: quad_advance.cuh (default) or the first-generation advance.cuh")
     ap.add_argument("--mg-mode", dest="mg_mode", default="beamer", choices=["push", "beamer"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

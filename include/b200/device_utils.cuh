@@ -36,6 +36,12 @@ __device__ __forceinline__ int4 ld_stream_v4(const int4 *p) {
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+__device__ __forceinline__ float4 ld_stream_v4(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -43,6 +49,19 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 }
 __device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Shared memory through explicit 32-bit shared-window addresses.  A generic pointer that has
+// travelled through a struct makes the compiler rebuild the window base (S2R SR_CgaCtaId + LEA)
+// in front of every access; these keep it a plain LDS/STS.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <cstring>
 #include "advance.cuh"
+#include "quad_advance.cuh"
 #include "segreduce.cuh"
 #include "tile_scan.cuh"
 #include "workspace.h"
@@ -127,7 +128,79 @@ cudaError_t launch_lbs_advance(b200_workspace *ws, const LbsArgs &a, Op op, int 
     RoutedOut r;
     if (routed) r = *routed;
     else memset(&r, 0, sizeof r);
+#ifdef B200_LBS_PAD_KB   // tuning builds: cap the resident CTAs per SM with unused dynamic shared memory
+    k<<<ws->num_sms * (224 / B200_LBS_PAD_KB), LBS_NT, B200_LBS_PAD_KB * 1024 - 24 * 1024, ws_stream(ws)>>>(a, op, d_out, capacity, ws->d_counters, r);
+#else
     k<<<grid, LBS_NT, 0, ws_stream(ws)>>>(a, op, d_out, capacity, ws->d_counters, r);
+#endif
+    ws->launches++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// quad advance (quad_advance.cuh): one CTA of QUAD_NT threads per SM; the per-warp windows,
+// candidate buffers and output stages live in opt-in dynamic shared memory, the rest of the
+// SM's SRAM stays L1 for the visited bitmap.
+// (the B200_QUAD_* macros exist for tuning builds: python -m mini_b200.build --define ... --out ...)
+// ---------------------------------------------------------------------------
+#ifndef B200_QUAD_NT
+#define B200_QUAD_NT 1024
+#endif
+#ifndef B200_QUAD_VT
+#define B200_QUAD_VT 2
+#endif
+#ifndef B200_QUAD_WSEG
+#define B200_QUAD_WSEG 32
+#endif
+constexpr int QUAD_NT = B200_QUAD_NT, QUAD_WSEG = B200_QUAD_WSEG, QUAD_WSTAGE = 64 * QUAD_R;
+constexpr uint32_t QUAD_MIN_CHUNK = 256;           // work items per warp, lower bound
+
+inline bool quad_aligned(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline QuadArgs make_quad_args(const b200_workspace *ws, const int *d_frontier, uint32_t len, const uint32_t *offsets,
+                               const int *indices, const float *weights, uint32_t row_shift = 0) {
+    QuadArgs a;
+    a.frontier = d_frontier;
+    a.num_segments = len;
+    a.scanned = ws->d_scanned;
+    a.rows = reinterpret_cast<const uint2 *>(ws->d_rows);
+    a.total = ws->d_counters + B200_CNT_TOTAL;
+    a.offsets = offsets;
+    a.indices4 = reinterpret_cast<const int4 *>(indices);
+    a.weights4 = reinterpret_cast<const float4 *>(weights);
+    a.min_chunk = QUAD_MIN_CHUNK;
+    a.row_shift = row_shift;
+    return a;
+}
+
+// quad scan of the frontier into ws->d_scanned (+ row bounds into ws->d_rows), Q into counters[TOTAL].
+inline cudaError_t launch_quad_scan(b200_workspace *ws, const int *d_frontier, uint32_t len, const uint32_t *offsets,
+                                    uint32_t row_shift = 0) {
+    if ((int64_t)len > ws->scanned_capacity) return cudaErrorInvalidValue;
+    FrontierQuads fn{d_frontier, offsets, reinterpret_cast<uint2 *>(ws->d_rows), row_shift};
+    return launch_scan(ws, fn, len, ws->d_scanned, ws->d_counters + B200_CNT_TOTAL);
+}
+
+// Quad advance over a frontier whose quad scan is already in the workspace.  m_F is left in
+// counters[B200_CNT_ARCS], the emitted count in counters[B200_CNT_OUT] (or routed.count[]).
+template <int OUT_MODE, bool DEG_SUM, class Op>
+cudaError_t launch_quad_advance(b200_workspace *ws, const QuadArgs &a, Op op, int *d_out, unsigned long long capacity,
+                                const RoutedOut *routed = nullptr) {
+    constexpr int VT = Op::WEIGHTED ? 2 : B200_QUAD_VT;
+    constexpr bool STAGED = OUT_MODE == OUT_COMPACT || OUT_MODE == OUT_ROUTED;
+    auto k = quad_advance_kernel<Op, OUT_MODE, DEG_SUM, QUAD_NT, VT, QUAD_WSEG>;
+    constexpr size_t smem = sizeof(uint32_t) * (QUAD_NT / 32) * quad_warp_words<Op, STAGED, VT, QUAD_WSEG, QUAD_WSTAGE>();
+    static_assert(smem <= 232448 - 64, "per-warp areas exceed the 227 KB opt-in shared memory of sm_100");
+    static unsigned long long opted_in = 0;   // per <Op, OUT_MODE, DEG_SUM> instantiation, one bit per device
+    if (!(opted_in >> (ws->device & 63) & 1ull)) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        opted_in |= 1ull << (ws->device & 63);
+    }
+    RoutedOut r;
+    if (routed) r = *routed;
+    else memset(&r, 0, sizeof r);
+    k<<<ws->num_sms * B200_QUAD_MINB, QUAD_NT, smem, ws_stream(ws)>>>(a, op, d_out, capacity, ws->d_counters, r);
     ws->launches++;
     return cudaGetLastError();
 }

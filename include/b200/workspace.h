@@ -34,6 +34,8 @@ typedef struct b200_workspace {
                                            graph_device_t::d_scanned_row_offsets (graph.hxx:52) */
     int64_t scanned_capacity;           /* in items */
     int64_t launches;                   /* kernels launched through this workspace (bench `gpu_launches`) */
+    void *d_rows;                       /* uint2[scanned_capacity]: (row begin, row end) of every frontier
+                                           vertex, written by the quad scan beside d_scanned */
 } b200_workspace;
 
 #ifdef __cplusplus

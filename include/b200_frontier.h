@@ -126,6 +126,14 @@ int b200_ctx_num_sms(b200_ctx *ctx, int *num_sms);
 /* Keep [ptr, ptr+bytes) L2-resident for kernels on the ctx stream
  * (cudaAccessPolicyWindow, persisting hits).  bytes = 0 clears the window. */
 int b200_ctx_l2_pin(b200_ctx *ctx, const void *d_ptr, int64_t bytes);
+/* Which kernel implements the push advance (transform_scan + transform_lbs, advance.hxx:20-67)
+ * behind the operators and primitives below.  Both give identical results.
+ *   B200_ADVANCE_QUAD (default): LBS over aligned 16-byte quads of col_indices, warp-private
+ *     chunks, probe / compact / dense-commit stages, L1-resident bitmap (include/b200/quad_advance.cuh);
+ *   B200_ADVANCE_LBS: LBS over arcs, CTA-cooperative windows (include/b200/advance.cuh); also
+ *     taken automatically for B200_ADV_RAW_OUTPUT and for arrays that are not 16-byte aligned. */
+enum { B200_ADVANCE_QUAD = 0, B200_ADVANCE_LBS = 1 };
+int b200_ctx_set_advance_impl(b200_ctx *ctx, int impl);
 
 /* ---- synthetic input (the reference has only load_graph, graph.hxx:96-223) */
 /* Symmetrised RMAT(0.57,0.19,0.19,0.05): n = 2^scale, m = 2*edge_factor*2^scale arcs,

@@ -35,14 +35,21 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = "") -> str:
+    """defines/out: tuning builds (e.g. defines=["B200_QUAD_NT=512"], out="libvariant.so"); the
+    default library is what the package loads unless B200_FRONTIER_LIB points elsewhere."""
     nvcc = os.environ.get("NVCC", "nvcc")
-    os.makedirs(OBJ, exist_ok=True)
+    global OBJ, LIB
+    obj_dir, lib = OBJ, LIB
+    if out:
+        lib = os.path.join(HERE, out)
+        obj_dir = os.path.join(HERE, "build", os.path.splitext(out)[0])
+    os.makedirs(obj_dir, exist_ok=True)
     deps = _deps()
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines]
 
     def compile_one(src):
-        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         if force or _stale(obj, deps):
             cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
             r = subprocess.run(cmd, capture_output=True, text=True)
@@ -54,14 +61,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    if force or _stale(lib, objs):
+        cmd = [nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("-v", dest="verbose", action="store_true")
+    ap.add_argument("--define", action="append", default=[])
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    print(build(force=a.force, verbose=a.verbose, defines=a.define, out=a.out))

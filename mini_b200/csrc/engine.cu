@@ -207,10 +207,41 @@ int b200_advance_forward(b200_ctx *ctx, const b200_graph *g, const b200_problem 
     b200_workspace *ws = &ctx->ws;
     B200_CUDA(cudaSetDevice(ws->device));
     B200_CUDA(reset_counters(ws));
+    const unsigned long long cap = (unsigned long long)out_capacity;
+    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && !raw && quad_aligned(g->col_indices) &&
+                      (p->kind != B200_PROBLEM_SSSP || quad_aligned(p->weights));
+    cudaError_t e = cudaErrorInvalidValue;
+    if (quad) {
+        B200_CUDA(launch_quad_scan(ws, d_in, (uint32_t)in_len, g->row_offsets));
+        if (p->kind == B200_PROBLEM_BFS) {
+            const QuadArgs a = make_quad_args(ws, d_in, (uint32_t)in_len, g->row_offsets, g->col_indices, nullptr);
+            if (!p->visited_bitmap || (!idem && !p->labels)) return B200_ERR_INVALID;
+            if (idem) {
+                BfsIdempotentQ op{p->visited_bitmap};
+                e = no_out ? launch_quad_advance<OUT_NONE, false>(ws, a, op, d_out, cap)
+                           : launch_quad_advance<OUT_COMPACT, false>(ws, a, op, d_out, cap);
+            } else {
+                BfsPushQ op{p->visited_bitmap, p->labels, iteration + 1};
+                e = no_out ? launch_quad_advance<OUT_NONE, false>(ws, a, op, d_out, cap)
+                           : launch_quad_advance<OUT_COMPACT, false>(ws, a, op, d_out, cap);
+            }
+        } else if (p->kind == B200_PROBLEM_SSSP) {
+            if (!p->dist || !p->weights || (!idem && !p->visited)) return B200_ERR_INVALID;
+            const QuadArgs a = make_quad_args(ws, d_in, (uint32_t)in_len, g->row_offsets, g->col_indices, p->weights);
+            SsspRelaxQ op{p->dist, p->preds, idem ? nullptr : p->visited, iteration};
+            e = no_out ? launch_quad_advance<OUT_NONE, false>(ws, a, op, d_out, cap)
+                       : launch_quad_advance<OUT_COMPACT, false>(ws, a, op, d_out, cap);
+        } else {
+            return B200_ERR_UNSUPPORTED;
+        }
+        B200_CUDA(e);
+        B200_CUDA(read_counters(ws));
+        if (arcs) *arcs = (int64_t)ws->h_counters[B200_CNT_ARCS];
+        if (out_len) *out_len = no_out ? 0 : (int64_t)ws->h_counters[B200_CNT_OUT];
+        return ws->h_counters[B200_CNT_OVERFLOW] ? B200_ERR_OVERFLOW : B200_OK;
+    }
     B200_CUDA(launch_frontier_scan(ws, d_in, (uint32_t)in_len, g->row_offsets));
     const LbsArgs a = make_lbs_args(ws, d_in, (uint32_t)in_len, g->row_offsets, g->col_indices);
-    const unsigned long long cap = (unsigned long long)out_capacity;
-    cudaError_t e = cudaErrorInvalidValue;
     if (p->kind == B200_PROBLEM_BFS) {
         if (idem) {
             if (!p->visited_bitmap) return B200_ERR_INVALID;
@@ -370,6 +401,7 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
     B200_CUDA(cudaGetLastError());
 
     int sel = 0, bsel = 0, level = 0;
+    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(g->col_indices);
     int64_t flen = 1, unvisited = n - 1, reached = 1, total_arcs = 0;
     int64_t m_unexplored = g->m;
     bool pull = false;
@@ -383,19 +415,28 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
         B200_CUDA(reset_counters(ws));
         int64_t found, arcs, next_deg;
         if (!pull) {
-            B200_CUDA(launch_frontier_scan(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets));
-            const LbsArgs a = make_lbs_args(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets, g->col_indices);
-            BfsPushOp op{ctx->bm_visited, d_labels, level + 1};
-            if (tl) B200_CUDA(cudaEventRecord(ev[3 * level + 1], st));
-            if (mode == B200_BFS_BEAMER)
-                B200_CUDA((launch_lbs_advance<OUT_COMPACT, true>(ws, a, op, ctx->frontier[sel ^ 1], (unsigned long long)n)));
-            else
-                B200_CUDA((launch_lbs_advance<OUT_COMPACT, false>(ws, a, op, ctx->frontier[sel ^ 1], (unsigned long long)n)));
+            const bool deg = mode == B200_BFS_BEAMER;
+            int32_t *next = ctx->frontier[sel ^ 1];
+            if (quad) {
+                B200_CUDA(launch_quad_scan(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets));
+                const QuadArgs a = make_quad_args(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets, g->col_indices, nullptr);
+                BfsPushQ op{ctx->bm_visited, d_labels, level + 1};
+                if (tl) B200_CUDA(cudaEventRecord(ev[3 * level + 1], st));
+                if (deg) B200_CUDA((launch_quad_advance<OUT_COMPACT, true>(ws, a, op, next, (unsigned long long)n)));
+                else B200_CUDA((launch_quad_advance<OUT_COMPACT, false>(ws, a, op, next, (unsigned long long)n)));
+            } else {
+                B200_CUDA(launch_frontier_scan(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets));
+                const LbsArgs a = make_lbs_args(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets, g->col_indices);
+                BfsPushOp op{ctx->bm_visited, d_labels, level + 1};
+                if (tl) B200_CUDA(cudaEventRecord(ev[3 * level + 1], st));
+                if (deg) B200_CUDA((launch_lbs_advance<OUT_COMPACT, true>(ws, a, op, next, (unsigned long long)n)));
+                else B200_CUDA((launch_lbs_advance<OUT_COMPACT, false>(ws, a, op, next, (unsigned long long)n)));
+            }
             if (tl) B200_CUDA(cudaEventRecord(ev[3 * level + 2], st));
             B200_CUDA(read_counters(ws));
             if (ws->h_counters[B200_CNT_OVERFLOW]) return B200_ERR_OVERFLOW;
             found = (int64_t)ws->h_counters[B200_CNT_OUT];
-            arcs = (int64_t)ws->h_counters[B200_CNT_TOTAL];
+            arcs = (int64_t)ws->h_counters[quad ? B200_CNT_ARCS : B200_CNT_TOTAL];
             next_deg = (int64_t)ws->h_counters[B200_CNT_AUX];
         } else {
             if (tl) B200_CUDA(cudaEventRecord(ev[3 * level + 1], st));
@@ -485,21 +526,30 @@ int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist
 
     int sel = 0, it = 0;
     int64_t flen = 1, total_arcs = 0;
+    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(g->col_indices) && quad_aligned(g->col_values);
     for (;;) {
         b200_level_stat *ls = (stats && it < B200_MAX_LEVELS) ? &stats->level[it] : nullptr;
         const bool tl = timing && it < B200_MAX_LEVELS;
         if (tl && it == 0) B200_CUDA(cudaEventRecord(ev[0], st));
         B200_CUDA(reset_counters(ws));
-        B200_CUDA(launch_frontier_scan(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets));
-        const LbsArgs a = make_lbs_args(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets, g->col_indices);
-        SsspRelaxOp op{d_dist, g->col_values, nullptr, ctx->stamp, it};   // preds: one exact pass at the end
-        if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 1], st));
-        B200_CUDA((launch_lbs_advance<OUT_COMPACT, false>(ws, a, op, ctx->frontier[sel ^ 1], (unsigned long long)n)));
+        if (quad) {
+            B200_CUDA(launch_quad_scan(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets));
+            const QuadArgs a = make_quad_args(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets, g->col_indices, g->col_values);
+            SsspRelaxQ op{d_dist, nullptr, ctx->stamp, it};   // preds: one exact pass at the end
+            if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 1], st));
+            B200_CUDA((launch_quad_advance<OUT_COMPACT, false>(ws, a, op, ctx->frontier[sel ^ 1], (unsigned long long)n)));
+        } else {
+            B200_CUDA(launch_frontier_scan(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets));
+            const LbsArgs a = make_lbs_args(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets, g->col_indices);
+            SsspRelaxOp op{d_dist, g->col_values, nullptr, ctx->stamp, it};   // preds: one exact pass at the end
+            if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 1], st));
+            B200_CUDA((launch_lbs_advance<OUT_COMPACT, false>(ws, a, op, ctx->frontier[sel ^ 1], (unsigned long long)n)));
+        }
         if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 2], st));
         B200_CUDA(read_counters(ws));
         if (ws->h_counters[B200_CNT_OVERFLOW]) return B200_ERR_OVERFLOW;
         const int64_t found = (int64_t)ws->h_counters[B200_CNT_OUT];
-        const int64_t arcs = (int64_t)ws->h_counters[B200_CNT_TOTAL];
+        const int64_t arcs = (int64_t)ws->h_counters[quad ? B200_CNT_ARCS : B200_CNT_TOTAL];
         if (ls) {
             ls->direction = 0;
             ls->frontier_len = flen;
@@ -518,9 +568,15 @@ int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist
         ws->launches++;
         B200_CUDA(cudaGetLastError());
         B200_CUDA(reset_counters(ws));
-        B200_CUDA(launch_frontier_scan(ws, ctx->frontier[0], (uint32_t)n, g->row_offsets));
-        const LbsArgs a = make_lbs_args(ws, ctx->frontier[0], (uint32_t)n, g->row_offsets, g->col_indices);
-        B200_CUDA((launch_lbs_advance<OUT_NONE, false>(ws, a, SsspPredOp{d_dist, g->col_values, d_preds}, nullptr, 0ull)));
+        if (quad) {
+            B200_CUDA(launch_quad_scan(ws, ctx->frontier[0], (uint32_t)n, g->row_offsets));
+            const QuadArgs a = make_quad_args(ws, ctx->frontier[0], (uint32_t)n, g->row_offsets, g->col_indices, g->col_values);
+            B200_CUDA((launch_quad_advance<OUT_NONE, false>(ws, a, SsspPredQ{d_dist, d_preds}, nullptr, 0ull)));
+        } else {
+            B200_CUDA(launch_frontier_scan(ws, ctx->frontier[0], (uint32_t)n, g->row_offsets));
+            const LbsArgs a = make_lbs_args(ws, ctx->frontier[0], (uint32_t)n, g->row_offsets, g->col_indices);
+            B200_CUDA((launch_lbs_advance<OUT_NONE, false>(ws, a, SsspPredOp{d_dist, g->col_values, d_preds}, nullptr, 0ull)));
+        }
         preds_fixup_kernel<<<ws->num_sms * 4, 256, 0, st>>>(d_preds, (unsigned long long)n, src);
         ws->launches++;
         B200_CUDA(cudaGetLastError());

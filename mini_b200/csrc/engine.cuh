@@ -20,6 +20,7 @@ struct b200_ctx {
     int ev_level_count;
     // L2 persistence
     bool l2_window_set;
+    int adv_impl;              // B200_ADVANCE_QUAD | B200_ADVANCE_LBS
 };
 
 struct b200_host_graph {

@@ -84,10 +84,9 @@ int b200_mg_bfs_push(b200_ctx *ctx, const b200_graph *g, const b200_mg_bfs_state
     const Partition part = part_of(s);
     B200_CUDA(reset_counters(ws));
     B200_CUDA(cudaMemsetAsync(s->box_counts, 0, sizeof(unsigned long long) * MAX_DEST, st));
+    bool quad = false;
     if (frontier_len) {
         B200_TRY(b200_ctx_reserve(ctx, frontier_len));
-        B200_CUDA(launch_frontier_scan(ws, d_frontier, (uint32_t)frontier_len, g->row_offsets, part.log_p));
-        const LbsArgs a = make_lbs_args(ws, d_frontier, (uint32_t)frontier_len, g->row_offsets, g->col_indices, part.log_p);
         RoutedOut r;
         memset(&r, 0, sizeof r);
         r.num_dest = s->num_ranks;
@@ -96,14 +95,24 @@ int b200_mg_bfs_push(b200_ctx *ctx, const b200_graph *g, const b200_mg_bfs_state
             r.box[p] = p == s->rank ? d_next_frontier : d_send_boxes[p];
             r.capacity[p] = p == s->rank ? (unsigned long long)s->n_local : (unsigned long long)box_capacity;
         }
-        BfsPushPartOp op{s->known, s->labels, level + 1, part};
-        B200_CUDA((launch_lbs_advance<OUT_ROUTED, true>(ws, a, op, nullptr, 0ull, &r)));
+        quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(g->col_indices);
+        if (quad) {
+            B200_CUDA(launch_quad_scan(ws, d_frontier, (uint32_t)frontier_len, g->row_offsets, part.log_p));
+            const QuadArgs a = make_quad_args(ws, d_frontier, (uint32_t)frontier_len, g->row_offsets, g->col_indices, nullptr, part.log_p);
+            BfsPushPartQ op{s->known, s->labels, level + 1, part};
+            B200_CUDA((launch_quad_advance<OUT_ROUTED, true>(ws, a, op, nullptr, 0ull, &r)));
+        } else {
+            B200_CUDA(launch_frontier_scan(ws, d_frontier, (uint32_t)frontier_len, g->row_offsets, part.log_p));
+            const LbsArgs a = make_lbs_args(ws, d_frontier, (uint32_t)frontier_len, g->row_offsets, g->col_indices, part.log_p);
+            BfsPushPartOp op{s->known, s->labels, level + 1, part};
+            B200_CUDA((launch_lbs_advance<OUT_ROUTED, true>(ws, a, op, nullptr, 0ull, &r)));
+        }
     }
     unsigned long long h_box[MAX_DEST];
     B200_CUDA(cudaMemcpyAsync(h_box, s->box_counts, sizeof h_box, cudaMemcpyDeviceToHost, st));
     B200_CUDA(read_counters(ws));
     for (int p = 0; p < s->num_ranks; ++p) h_counts[p] = (int64_t)h_box[p];
-    if (arcs) *arcs = (int64_t)ws->h_counters[B200_CNT_TOTAL];
+    if (arcs) *arcs = (int64_t)ws->h_counters[quad ? B200_CNT_ARCS : B200_CNT_TOTAL];
     if (next_degree) *next_degree = (int64_t)ws->h_counters[B200_CNT_AUX];
     return ws->h_counters[B200_CNT_OVERFLOW] ? B200_ERR_OVERFLOW : B200_OK;
 }

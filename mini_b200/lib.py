@@ -6,13 +6,14 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libb200_frontier.so")
+_LIB_PATH = os.environ.get("B200_FRONTIER_LIB") or os.path.join(_HERE, "libb200_frontier.so")   # env: tuning builds
 
 BFS_PUSH, BFS_REF_ALPHA, BFS_BEAMER = 0, 1, 2
 ADV_IDEMPOTENT, ADV_NO_OUTPUT, ADV_RAW_OUTPUT = 1, 2, 4
 OP_PLUS, OP_MIN, OP_MAX = 0, 1, 2
 PROBLEM_BFS, PROBLEM_SSSP, PROBLEM_PR = 1, 2, 3
 MAX_LEVELS = 512
+ADVANCE_QUAD, ADVANCE_LBS = 0, 1
 
 
 class B200Error(RuntimeError):
@@ -83,6 +84,7 @@ def load_library():
         "b200_ctx_sync": ([vp], i32),
         "b200_ctx_num_sms": ([vp, pi32], i32),
         "b200_ctx_l2_pin": ([vp, vp, i64], i32),
+        "b200_ctx_set_advance_impl": ([vp, i32], i32),
         "b200_ctx_workspace": ([vp], vp),
         "b200_rmat_build_csr": ([vp, i32, i32, u64, vp, vp, vp, u64], i32),
         "b200_rmat_pairs": ([vp, i32, i32, u64, vp, vp], i32),
@@ -210,6 +212,10 @@ class Context:
 
     def sync(self):
         _check(self._L.b200_ctx_sync(self._h), "b200_ctx_sync")
+
+    def set_advance_impl(self, impl: int):
+        """ADVANCE_QUAD (default) or ADVANCE_LBS: which kernel runs the push advance (same results)."""
+        _check(self._L.b200_ctx_set_advance_impl(self._h, impl), "b200_ctx_set_advance_impl")
 
     def l2_pin(self, tensor):
         if tensor is None:

@@ -17,10 +17,12 @@ FIXTURES = ["ref_fixture_bfs.json", "ref_fixture_sssp_directed.json",
 FLT_MAX = np.finfo(np.float32).max
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["quad", "lbs"])
+def ctx(request):
+    """Every parity test runs against both push-advance kernels (quad_advance.cuh / advance.cuh)."""
     import mini_b200
     c = mini_b200.Context(0)
+    c.set_advance_impl(mini_b200.ADVANCE_QUAD if request.param == "quad" else mini_b200.ADVANCE_LBS)
     yield c
     c.close()
 
