@@ -20,9 +20,11 @@
 //    the index/weight stream and the frontier arrays bypass L1 (ld.global.nc.L1::no_allocate),
 //    and shared memory is kept small so the unified 256 KB SRAM is mostly cache.  A stale L1
 //    word only costs a failed atomicOr; the global atomic decides who wins a vertex.
-//    (Tried and rejected, numbers in profiles/README.md: a software "hub" copy of the low-id
-//    part of the bitmap in shared memory with L2-only probes for the rest -- it takes the SRAM
-//    away from L1 and was 2x slower: 0.56 ms vs 0.26 ms on the heaviest scale-22 level.)
+//    (Tried and rejected, numbers in profiles/README.md: (a) a software "hub" copy of the low-id
+//    part of the bitmap in shared memory, updated or as a read-only pre-filter -- it takes the
+//    SRAM away from L1 and was 1.7-2.4x slower on the heaviest scale-22 level; (b) re-dealing the
+//    tile through shared memory so one probe instruction covers 32 consecutive neighbours -- 12 %
+//    slower, most rows are too short for neighbouring arcs to share a bitmap line.)
 //
 // Stage 1 runs for every arc, unrolled so all loads of a thread are in flight together:
 //   SrcVal   load_src(src)                          once per quad (e.g. dist[src])
@@ -318,8 +320,10 @@ quad_advance_kernel(QuadArgs a, Op op, int *__restrict__ out, unsigned long long
             int j_lo = 0;
             while (cur_q < win_end) {
                 const uint32_t q_end = win_end - cur_q > 32u * VT ? cur_q + 32u * VT : win_end;
-                j_lo = lbs_locate(start, j_lo, ns, cur_q);
-                const int j_hi = lbs_locate(start, j_lo, ns, q_end - 1) + 1;
+                // (tiles of a long row: the next staged segment starts beyond the tile, nothing to search)
+                if (j_lo + 1 < ns && start[j_lo + 1] <= cur_q) j_lo = lbs_locate(start, j_lo + 1, ns, cur_q);
+                int j_hi = j_lo + 1;
+                if (j_hi < ns && start[j_hi] <= q_end - 1) j_hi = lbs_locate(start, j_hi, ns, q_end - 1) + 1;
                 tile(cur_q, q_end - cur_q, j_lo, j_hi);
                 cur_q = q_end;
             }
