@@ -153,7 +153,7 @@ cudaError_t launch_lbs_advance(b200_workspace *ws, const LbsArgs &a, Op op, int 
 #define B200_QUAD_WSEG 32
 #endif
 constexpr int QUAD_NT = B200_QUAD_NT, QUAD_WSEG = B200_QUAD_WSEG, QUAD_WSTAGE = 64 * QUAD_R;
-constexpr uint32_t QUAD_MIN_CHUNK = 256;           // work items per warp, lower bound
+constexpr uint32_t QUAD_MIN_CHUNK = 64;            // work items per warp, lower bound
 
 inline bool quad_aligned(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

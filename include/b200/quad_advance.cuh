@@ -72,6 +72,9 @@ struct FrontierQuads {
     }
 };
 
+#ifndef B200_QUAD_SPLIT
+#define B200_QUAD_SPLIT 8
+#endif
 #ifndef B200_QUAD_R
 #define B200_QUAD_R 2
 #endif
@@ -215,20 +218,24 @@ quad_advance_kernel(QuadArgs a, Op op, int *__restrict__ out, unsigned long long
         __syncwarp();
     };
 
-    // ---- stage 1, one tile: up to 32*VT quads, lane-strided so a warp reads 512 contiguous bytes
-    auto tile = [&](uint32_t first_q, uint32_t nq, int j_lo, int j_hi) {
+    // ---- stage 1 is software-pipelined over tiles: fetch(t+1) -- segment search and the 128-bit
+    // index / weight loads -- is issued BEFORE probe(t), so the DRAM latency of the index stream
+    // overlaps the L1/L2 latency of the previous tile's probes.  A tile's state lives in registers.
+    struct TileRegs {
         int dst[NA];
         float wgt[Op::WEIGHTED ? NA : 1];
         uint32_t e0[VT];
         int src[VT];
-        typename Op::SrcVal sv[VT];
-        uint32_t valid = 0u;                 // bit 4i+t: arc t of quad i lies inside its row
-        // segment search + 128-bit index (and weight) loads
+        uint32_t valid;                      // bit 4i+t: arc t of quad i lies inside its row
+    };
+    // one tile = up to 32*VT quads, lane-strided so a warp reads 512 contiguous bytes per instruction
+    auto fetch = [&](TileRegs &t, uint32_t first_q, uint32_t nq, int j_lo, int j_hi) {
+        t.valid = 0u;
 #pragma unroll
         for (int i = 0; i < VT; ++i) {
             const uint32_t k = lane + 32u * i;
-            e0[i] = 0u;
-            src[i] = 0;
+            t.e0[i] = 0u;
+            t.src[i] = 0;
             int4 d = make_int4(0, 0, 0, 0);
             float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
             if (k < nq) {
@@ -238,28 +245,31 @@ quad_advance_kernel(QuadArgs a, Op op, int *__restrict__ out, unsigned long long
                 const uint32_t q = (b >> 2) + (qa - start[j]);
                 d = ld_stream_v4(a.indices4 + q);
                 if constexpr (Op::WEIGHTED) w = ld_stream_v4(a.weights4 + q);
-                e0[i] = q << 2;
-                const uint32_t lo = b > e0[i] ? b - e0[i] : 0u;
-                const uint32_t hi = e - e0[i] < 4u ? e - e0[i] : 4u;
-                valid |= (((1u << hi) - 1u) & ~((1u << lo) - 1u)) << (4 * i);
-                src[i] = vert[j];
+                t.e0[i] = q << 2;
+                const uint32_t lo = b > t.e0[i] ? b - t.e0[i] : 0u;
+                const uint32_t hi = e - t.e0[i] < 4u ? e - t.e0[i] : 4u;
+                t.valid |= (((1u << hi) - 1u) & ~((1u << lo) - 1u)) << (4 * i);
+                t.src[i] = vert[j];
             }
-            dst[4 * i] = d.x; dst[4 * i + 1] = d.y; dst[4 * i + 2] = d.z; dst[4 * i + 3] = d.w;
-            if constexpr (Op::WEIGHTED) { wgt[4 * i] = w.x; wgt[4 * i + 1] = w.y; wgt[4 * i + 2] = w.z; wgt[4 * i + 3] = w.w; }
+            t.dst[4 * i] = d.x; t.dst[4 * i + 1] = d.y; t.dst[4 * i + 2] = d.z; t.dst[4 * i + 3] = d.w;
+            if constexpr (Op::WEIGHTED) { t.wgt[4 * i] = w.x; t.wgt[4 * i + 1] = w.y; t.wgt[4 * i + 2] = w.z; t.wgt[4 * i + 3] = w.w; }
         }
-        arc_cnt += __popc(valid);
+        arc_cnt += __popc(t.valid);
+    };
+    auto probe = [&](const TileRegs &t) {
+        typename Op::SrcVal sv[VT];
 #pragma unroll
-        for (int i = 0; i < VT; ++i) sv[i] = ((valid >> (4 * i)) & 15u) ? op.load_src(src[i]) : typename Op::SrcVal();
+        for (int i = 0; i < VT; ++i) sv[i] = ((t.valid >> (4 * i)) & 15u) ? op.load_src(t.src[i]) : typename Op::SrcVal();
         // probe every arc: issue all loads (one L1-cached load each), then judge
         uint32_t cm = 0u;                    // candidate mask
         {
             typename Op::Evidence ev[NA];
 #pragma unroll
             for (int k = 0; k < NA; ++k)
-                ev[k] = op.probe_load((valid >> k) & 1u, sv[k >> 2], src[k >> 2], dst[k], e0[k >> 2] + (k & 3));
+                ev[k] = op.probe_load((t.valid >> k) & 1u, sv[k >> 2], t.src[k >> 2], t.dst[k], t.e0[k >> 2] + (k & 3));
 #pragma unroll
             for (int k = 0; k < NA; ++k)
-                if (((valid >> k) & 1u) && op.probe_eval(ev[k], sv[k >> 2], dst[k], Op::WEIGHTED ? wgt[Op::WEIGHTED ? k : 0] : 0.f))
+                if (((t.valid >> k) & 1u) && op.probe_eval(ev[k], sv[k >> 2], t.dst[k], Op::WEIGHTED ? t.wgt[Op::WEIGHTED ? k : 0] : 0.f))
                     cm |= 1u << k;
         }
         // compact the survivors into the warp's candidate buffer
@@ -268,14 +278,14 @@ quad_advance_kernel(QuadArgs a, Op op, int *__restrict__ out, unsigned long long
             uint32_t incl = c;
 #pragma unroll
             for (int s = 1; s < 32; s <<= 1) {
-                const uint32_t t = __shfl_up_sync(FULL_MASK, incl, s);
-                if (lane >= (unsigned)s) incl += t;
+                const uint32_t u = __shfl_up_sync(FULL_MASK, incl, s);
+                if (lane >= (unsigned)s) incl += u;
             }
             const uint32_t pos0 = ccnt + incl - c;
 #pragma unroll
             for (int k = 0; k < NA; ++k) {
                 if ((cm >> k) & 1u) {
-                    const Cand cd = op.make_cand(sv[k >> 2], src[k >> 2], dst[k], e0[k >> 2] + (k & 3), Op::WEIGHTED ? wgt[Op::WEIGHTED ? k : 0] : 0.f);
+                    const Cand cd = op.make_cand(sv[k >> 2], t.src[k >> 2], t.dst[k], t.e0[k >> 2] + (k & 3), Op::WEIGHTED ? t.wgt[Op::WEIGHTED ? k : 0] : 0.f);
                     const uint32_t pos = pos0 + __popc(cm & ((1u << k) - 1u));
 #pragma unroll
                     for (int w = 0; w < Cand::WORDS; ++w) cbuf[w * CCAP + pos] = cd.w[w];
@@ -285,28 +295,48 @@ quad_advance_kernel(QuadArgs a, Op op, int *__restrict__ out, unsigned long long
             if (ccnt >= 32u * R) drain(32u * R - 1u);
         }
     };
+    TileRegs pend;                           // the tile whose loads are in flight
+    bool have_pend = false;
+    auto tile = [&](uint32_t first_q, uint32_t nq, int j_lo, int j_hi) {
+        TileRegs next;
+        fetch(next, first_q, nq, j_lo, j_hi);
+        if (have_pend) probe(pend);
+        pend = next;
+        have_pend = true;
+    };
 
     // ---- this warp's chunk of the merged (quads U segment starts) list.  Consecutive chunks go
     // to different SMs, so a level too small for the whole grid still spreads over the chip.
     const unsigned long long work = Q + a.num_segments;
+    // Each warp takes SPLIT pieces, total_warps apart, so rows of very different cost (a hub row
+    // whose sorted neighbours share bitmap lines vs. many short rows) average out over the warps.
+    // The 2*SPLIT merge-path searches run in parallel lanes: one search latency in total.
+    constexpr int SPLIT = B200_QUAD_SPLIT;
+    static_assert(SPLIT >= 1 && SPLIT <= 16, "one lane per chunk boundary");
     const uint32_t total_warps = gridDim.x * NW, gw = warp * gridDim.x + blockIdx.x;
-    unsigned long long chunk = ceil_div<unsigned long long>(work, total_warps);
+    unsigned long long chunk = ceil_div<unsigned long long>(work, (unsigned long long)total_warps * SPLIT);
     if (chunk < a.min_chunk) chunk = a.min_chunk;
-    const unsigned long long d0 = (unsigned long long)gw * chunk;
-    if (Q != 0 && d0 < work) {
+    uint32_t sb = 0;
+    {
+        const unsigned long long piece = (unsigned long long)(lane >> 1) * total_warps + gw;
+        unsigned long long d = (piece + (lane & 1u)) * chunk;
+        if (d > work) d = work;
+        if (Q != 0 && lane < 2u * SPLIT) sb = merge_path_segments(a.scanned, a.num_segments, Q, d);
+    }
+    for (int c = 0; c < SPLIT; ++c) {
+        const unsigned long long d0 = ((unsigned long long)c * total_warps + gw) * chunk;
+        const uint32_t s0 = __shfl_sync(FULL_MASK, sb, 2 * c), s1 = __shfl_sync(FULL_MASK, sb, 2 * c + 1);
+        if (Q == 0 || d0 >= work) break;
         const unsigned long long d1 = d0 + chunk < work ? d0 + chunk : work;
-        uint32_t sb = 0;
-        if (lane < 2) sb = merge_path_segments(a.scanned, a.num_segments, Q, lane ? d1 : d0);
-        const uint32_t s0 = __shfl_sync(FULL_MASK, sb, 0), s1 = __shfl_sync(FULL_MASK, sb, 1);
         const uint32_t q0 = (uint32_t)(d0 - s0), q1 = (uint32_t)(d1 - s1);
         uint32_t cur_s = s0 > 0 ? s0 - 1 : 0;   // segment that contains quad q0 (or an empty one just before it)
         uint32_t cur_q = q0;
         while (cur_q < q1) {                     // one iteration per window of <= WSEG segments
             const int ns = (int)min((uint32_t)WSEG, s1 - cur_s);
             for (int j = lane; j < ns; j += 32) {
-                const uint2 row = __ldg(a.rows + cur_s + j);
-                start[j] = __ldg(a.scanned + cur_s + j);
-                vert[j] = __ldg(a.frontier + cur_s + j);
+                const uint2 row = ld_stream_v2(a.rows + cur_s + j);
+                start[j] = ld_stream(a.scanned + cur_s + j);
+                vert[j] = ld_stream(a.frontier + cur_s + j);
                 rb[j] = row.x;
                 re[j] = row.y;
             }
@@ -314,7 +344,7 @@ quad_advance_kernel(QuadArgs a, Op op, int *__restrict__ out, unsigned long long
             uint32_t win_end = q1;
             bool more = false;
             if (cur_s + (uint32_t)ns < s1) {
-                const uint32_t lim = __ldg(a.scanned + cur_s + ns);
+                const uint32_t lim = ld_stream(a.scanned + cur_s + ns);
                 if (lim < win_end) { win_end = lim; more = true; }
             }
             int j_lo = 0;
@@ -327,13 +357,15 @@ quad_advance_kernel(QuadArgs a, Op op, int *__restrict__ out, unsigned long long
                 tile(cur_q, q_end - cur_q, j_lo, j_hi);
                 cur_q = q_end;
             }
-            if (!more) break;                    // win_end == q1: chunk done
+            if (!more) break;                    // win_end == q1: piece done
             cur_s += (uint32_t)ns;               // scanned[cur_s + ns] == win_end == cur_q
             __syncwarp();
         }
-        if (ccnt) drain(0u);
-        if (STAGED && wcnt) flush();
+        __syncwarp();
     }
+    if (have_pend) probe(pend);
+    if (ccnt) drain(0u);
+    if (STAGED && wcnt) flush();
 
     // ---- CTA totals: arcs walked (m_F) and, optionally, the degree sum of the emitted vertices
 #pragma unroll
