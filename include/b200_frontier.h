@@ -44,7 +44,8 @@ enum {
     B200_ERR_INVALID = 2,   /* bad argument */
     B200_ERR_OVERFLOW = 3,  /* an output frontier exceeded the capacity the caller gave */
     B200_ERR_NOMEM = 4,
-    B200_ERR_UNSUPPORTED = 5
+    B200_ERR_UNSUPPORTED = 5,
+    B200_ERR_TIMEOUT = 6    /* a cross-GPU barrier of the peer-memory path waited too long for a peer */
 };
 
 typedef struct b200_ctx b200_ctx; /* replaces mgpu::standard_context_t (context.hxx:103-219) + per-call mem_t scratch */
@@ -275,6 +276,33 @@ int b200_mg_list_to_slice(b200_ctx *ctx, const b200_mg_bfs_state *s, const int32
                           uint32_t *d_slice);
 int b200_mg_slice_to_list(b200_ctx *ctx, const b200_mg_bfs_state *s, const uint32_t *d_slice, int32_t *d_list,
                           int64_t *len);
+
+/* ---- multi-GPU BFS over NVLink PEER MEMORY: the exchange fused into the kernels (new) ----
+ * Same partition and algorithm as the b200_mg_* steps, but no collective library on the data path:
+ * every rank owns a symmetric heap (control block, two frontier-bitmap slices, one inbox segment per
+ * sender) that its peers map (CUDA IPC between processes, plain pointers inside one process);
+ *   push level : the advance kernel's flush stores remote discoveries straight into the owner's inbox
+ *                (the alltoallv), a flag barrier publishes the counts, one absorb kernel labels them;
+ *   pull level : one kernel reads all peers' bitmap slices through NVLink and folds them into `known`
+ *                (the allgather), then the early-exit pull runs over the local rows;
+ *   every level: the {|F_next|, arcs, deg, sent} rows are written into every peer's heap, summed
+ *                after the barrier (the allreduce) and read by the host from mapped pinned memory.
+ * All ranks must call b200_p2p_bfs_run with the same (src, mode, alpha, beta); it returns after the
+ * whole traversal.  B200_ERR_TIMEOUT if a peer never arrives at a barrier (20 s). */
+#define B200_IPC_HANDLE_BYTES 64
+typedef struct b200_p2p_bfs b200_p2p_bfs;
+int b200_p2p_bfs_heap_bytes(int num_ranks, int64_t n_global, int64_t *bytes);
+/* n_global / num_ranks must be a multiple of 128.  ipc_handle_out (nullable) receives the
+ * cudaIpcMemHandle_t of the heap (B200_IPC_HANDLE_BYTES); heap_base_out (nullable) its address. */
+int b200_p2p_bfs_create(b200_ctx *ctx, int rank, int num_ranks, int64_t n_global, b200_p2p_bfs **out,
+                        void *ipc_handle_out, void **heap_base_out);
+/* Map the peers' heaps: ipc_handles = num_ranks consecutive handles gathered from all ranks (other
+ * processes), or peer_bases = heap addresses valid in this process (ranks as threads / streams). */
+int b200_p2p_bfs_connect(b200_p2p_bfs *s, const void *ipc_handles, void *const *peer_bases);
+int b200_p2p_bfs_run(b200_p2p_bfs *s, const b200_graph *g_local, int64_t m_global, int32_t src, int mode,
+                     float alpha, float beta, int32_t *d_labels_local, b200_stats *stats /* nullable */,
+                     int64_t *sent_per_level /* nullable, [B200_MAX_LEVELS] vertices all ranks sent */);
+int b200_p2p_bfs_destroy(b200_p2p_bfs *s);
 
 /* ---- host-buffer entry points (what test_bfs.cu times + extract: H2D, run, D2H) */
 typedef struct b200_host_graph b200_host_graph; /* graph_to_device result (graph.hxx:60-83) kept by the engine */

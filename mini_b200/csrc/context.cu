@@ -53,6 +53,7 @@ const char *b200_status_string(int status) {
         case B200_ERR_OVERFLOW: return "output frontier capacity exceeded";
         case B200_ERR_NOMEM: return "out of device memory";
         case B200_ERR_UNSUPPORTED: return "unsupported";
+        case B200_ERR_TIMEOUT: return "a peer GPU did not reach a barrier in time";
         default: return "unknown status";
     }
 }

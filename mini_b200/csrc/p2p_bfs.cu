@@ -1,0 +1,574 @@
+// p2p_bfs.cu -- multi-GPU BFS whose frontier exchange is FUSED INTO THE KERNELS over NVLink peer
+// memory (no NCCL call on the data path).  New (the reference is single-GPU, README.md:4); the
+// NCCL form of the same algorithm is multi_gpu.cu + mini_b200/dist.py and stays as the baseline.
+//
+// One process drives one GPU.  Every rank allocates one "symmetric heap" (same layout on every
+// rank), exports it with cudaIpcGetMemHandle and maps the heaps of its peers, so a kernel can
+// store straight into a peer's HBM through NVLink / NVSwitch:
+//
+//   push level : quad_advance_kernel<OUT_ROUTED> buckets accepted vertices by owner in its flush
+//                and writes them DIRECTLY into the owner's inbox segment (box[p] is a peer
+//                pointer) -- this is the alltoallv; a 1-warp kernel then publishes the per-peer
+//                counts and runs a flag barrier across the GPUs; p2p_absorb_kernel applies
+//                label-if-unvisited to what arrived (the uniquify filter of the exchange);
+//   pull level : p2p_gather_or_kernel reads every peer's frontier-bitmap slice through NVLink into
+//                the local full bitmap and folds it into `known` in the same pass -- this is the
+//                allgather; the early-exit pull then runs over the local rows;
+//   every level: p2p_stats_kernel writes this rank's {|F_next|, arcs, deg(F_next), sent} row into
+//                every peer's heap, barriers, sums the rows (the allreduce) and leaves the result in
+//                mapped pinned memory: ONE host synchronisation per level, zero collectives.
+//
+// Heap hazards are excluded by construction: slices are double-buffered (a level reads
+// slice[sb] and writes slice[sb^1]); stats rows are double-buffered by barrier parity; inbox
+// segments and counts are rewritten only after the level-closing barrier, which every rank
+// reaches after its own absorb.  Barrier waits carry a wall-clock timeout (B200_ERR_TIMEOUT)
+// so a lost peer cannot hang the GPU.
+#include <climits>
+#include <cstring>
+#include <new>
+#include "b200/operators.cuh"
+#include "engine.cuh"
+
+using namespace b200;
+
+namespace {
+
+constexpr int P2P_MAX = MAX_DEST;
+constexpr size_t P2P_CTRL_BYTES = 4096;
+constexpr unsigned long long P2P_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+constexpr int P2P_TIMED_LEVELS = 64;
+
+struct Ctrl {                                  // heap offset 0 on every rank
+    unsigned long long flags[P2P_MAX];         // flags[p]: last barrier epoch rank p signalled to me
+    unsigned long long counts[P2P_MAX];        // counts[p]: vertices rank p left in my inbox segment p
+    unsigned long long stats[2][P2P_MAX][8];   // stats[parity][p]: rank p's row of the level summary
+};
+static_assert(sizeof(Ctrl) <= P2P_CTRL_BYTES, "control block");
+
+struct Peers {
+    unsigned char *base[P2P_MAX];
+};
+
+enum { RES_SUM = 0, RES_OWN = 8, RES_TIMEOUT = 16, RES_WORDS = 32 };
+enum { ROW_NEXT = 0, ROW_ARCS = 1, ROW_DEG = 2, ROW_SENT = 3, ROW_OVERFLOW = 4 };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// One warp: lane p signals rank p (release: everything this rank wrote before -- in this kernel
+// or in earlier kernels of the stream -- is visible to whoever acquires the flag) and waits for
+// rank p's signal.  Returns false on every lane if any wait timed out.
+__device__ __forceinline__ bool p2p_signal_wait(const Peers &peers, int me, int P, unsigned long long epoch) {
+    const int p = (int)lane_id();
+    bool ok = true;
+    __threadfence_system();
+    if (p < P && p != me) {
+        st_release_sys(&reinterpret_cast<Ctrl *>(peers.base[p])->flags[me], epoch);
+        const unsigned long long *mine = &reinterpret_cast<const Ctrl *>(peers.base[me])->flags[p];
+        const unsigned long long t0 = globaltimer_ns();
+        while (ld_acquire_sys(mine) < epoch) {
+            if (globaltimer_ns() - t0 > P2P_TIMEOUT_NS) {
+                ok = false;
+                break;
+            }
+        }
+    }
+    ok = __all_sync(FULL_MASK, ok);
+    __syncwarp();
+    __threadfence_system();
+    return ok;
+}
+
+__global__ void p2p_init_kernel(int32_t *labels, uint32_t *known, int32_t *frontier, int src, Partition part) {
+    const uint32_t b = part.bit((uint32_t)src);
+    known[b >> 5] |= 1u << (b & 31);              // every rank knows the source is visited
+    if (part.owner((uint32_t)src) == part.me) {
+        labels[part.row((uint32_t)src)] = 0;
+        frontier[0] = src;
+    }
+}
+
+// After a push advance: tell every peer how many vertices this rank left in its inbox, then barrier.
+__global__ void __launch_bounds__(32) p2p_publish_counts_kernel(Peers peers, int me, int P, unsigned long long epoch,
+                                                                const unsigned long long *box_counts,
+                                                                unsigned long long *res) {
+    const int p = (int)lane_id();
+    if (p < P && p != me) st_relaxed_sys(&reinterpret_cast<Ctrl *>(peers.base[p])->counts[me], box_counts[p]);
+    const bool ok = p2p_signal_wait(peers, me, P, epoch);
+    if (p == 0 && !ok) res[RES_TIMEOUT] = 1ull;
+}
+
+// Level summary: this rank's row goes into every peer's heap, barrier, sum of the rows -> mapped
+// pinned memory (what an allreduce + a D2H copy would have delivered).
+__global__ void __launch_bounds__(32) p2p_stats_kernel(Peers peers, int me, int P, unsigned long long epoch, int parity,
+                                                       const unsigned long long *counters,
+                                                       const unsigned long long *box_counts, int push, int arcs_slot,
+                                                       unsigned long long *res) {
+    const int p = (int)lane_id();
+    unsigned long long row[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) row[k] = 0;
+    if (push) {
+        row[ROW_NEXT] = box_counts[me];
+        for (int q = 0; q < P; ++q)
+            if (q != me) row[ROW_SENT] += box_counts[q];
+    } else {
+        row[ROW_NEXT] = counters[B200_CNT_OUT];
+    }
+    row[ROW_ARCS] = counters[arcs_slot];
+    row[ROW_DEG] = counters[B200_CNT_AUX];
+    row[ROW_OVERFLOW] = counters[B200_CNT_OVERFLOW];
+    if (p < P) {
+        unsigned long long *dst = reinterpret_cast<Ctrl *>(peers.base[p])->stats[parity][me];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) st_relaxed_sys(dst + k, row[k]);
+    }
+    const bool ok = p2p_signal_wait(peers, me, P, epoch);
+    if (p < 8) {
+        const Ctrl *mine = reinterpret_cast<const Ctrl *>(peers.base[me]);
+        unsigned long long s = 0;
+        for (int q = 0; q < P; ++q) s += ld_relaxed_sys(&mine->stats[parity][q][p]);
+        res[RES_SUM + p] = s;
+        res[RES_OWN + p] = row[p];
+    }
+    if (p == 0 && !ok) res[RES_TIMEOUT] = 1ull;
+    __threadfence_system();
+}
+
+// Receiver side of the push exchange over ALL inbox segments in one launch (counts live on the
+// device): label-if-unvisited, survivors join the next frontier after the local discoveries.
+__global__ void __launch_bounds__(256) p2p_absorb_kernel(const int *__restrict__ inbox, size_t seg_stride,
+                                                         const unsigned long long *counts, int me, int P,
+                                                         uint32_t *known, int *labels, int next_label, Partition part,
+                                                         int *next_frontier, unsigned long long capacity,
+                                                         unsigned long long *next_count, unsigned long long *counters,
+                                                         const uint32_t *__restrict__ offsets) {
+    const unsigned lane = lane_id();
+    const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long deg_sum = 0;
+    for (int q = 0; q < P; ++q) {
+        if (q == me) continue;
+        const unsigned long long cnt = ld_relaxed_sys(counts + q);
+        const int *seg = inbox + (size_t)q * seg_stride;
+        for (unsigned long long base = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < cnt;
+             base += nthreads) {
+            const unsigned long long i = base + lane;
+            bool fresh = false;
+            int u = -1;
+            if (i < cnt) {
+                u = __ldcg(seg + i);
+                const uint32_t b = part.bit((uint32_t)u);
+                const uint32_t bit = 1u << (b & 31);
+                fresh = !(known[b >> 5] & bit) && !(atomicOr(known + (b >> 5), bit) & bit);
+                if (fresh) labels[part.row((uint32_t)u)] = next_label;
+            }
+            const unsigned mask = __ballot_sync(FULL_MASK, fresh);
+            if (mask) {
+                unsigned long long pos0 = 0;
+                const unsigned leader = __ffs(mask) - 1;
+                if (lane == leader) pos0 = atomicAdd(next_count, (unsigned long long)__popc(mask));
+                pos0 = __shfl_sync(FULL_MASK, pos0, leader);
+                if (fresh) {
+                    const unsigned long long pos = pos0 + __popc(mask & lanemask_lt());
+                    if (pos < capacity) next_frontier[pos] = u;
+                    else counters[B200_CNT_OVERFLOW] = 1ull;
+                    const uint32_t r = part.row((uint32_t)u);
+                    deg_sum += __ldg(offsets + r + 1) - __ldg(offsets + r);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) deg_sum += __shfl_xor_sync(FULL_MASK, deg_sum, d);
+    if (lane == 0 && deg_sum) atomicAdd(&counters[B200_CNT_AUX], deg_sum);
+}
+
+// next frontier list (length on the device) -> this rank's bitmap slice (pre-cleared)
+__global__ void p2p_list_to_slice_kernel(const int *__restrict__ list, const unsigned long long *len_ptr, uint32_t *slice,
+                                         Partition part) {
+    const unsigned long long len = *len_ptr;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const uint32_t r = part.row((uint32_t)list[i]);
+        atomicOr(slice + (r >> 5), 1u << (r & 31));
+    }
+}
+
+// The allgather of a pull level, fused with the fold into `known`: read every rank's frontier
+// slice through NVLink (own slice locally), write the full rank-major bitmap, OR into known.
+__global__ void __launch_bounds__(256) p2p_gather_or_kernel(Peers peers, size_t slice_off, uint32_t quads_per_slice, int P,
+                                                            uint4 *__restrict__ full, uint4 *__restrict__ known) {
+    const size_t total = (size_t)quads_per_slice * (size_t)P;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint32_t p = (uint32_t)(i / quads_per_slice);
+        const uint32_t j = (uint32_t)(i - (size_t)p * quads_per_slice);
+        const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(peers.base[p] + slice_off) + j);
+        full[i] = v;
+        if (v.x | v.y | v.z | v.w) {
+            uint4 k = known[i];
+            k.x |= v.x; k.y |= v.y; k.z |= v.z; k.w |= v.w;
+            known[i] = k;
+        }
+    }
+}
+
+struct SliceListPred {   // bit r of the slice set -> emit global id r * P + me
+    const uint32_t *slice;
+    Partition part;
+    __device__ __forceinline__ bool operator()(uint32_t idx, int &item) const {
+        item = (int)((idx << part.log_p) | part.me);
+        return (slice[idx >> 5] >> (idx & 31)) & 1u;
+    }
+};
+
+// CUDA loads kernels lazily, and a load may have to wait for every kernel running in the context.
+// A rank that spins in a flag barrier while a peer rank OF THE SAME PROCESS (ranks as threads) is
+// about to launch a kernel for the first time would therefore deadlock: load everything up front.
+template <class K>
+cudaError_t preload(K k) {
+    cudaFuncAttributes a;
+    return cudaFuncGetAttributes(&a, k);
+}
+cudaError_t preload_kernels() {
+    cudaError_t e;
+    constexpr int VT = B200_QUAD_VT;
+    if ((e = preload(p2p_init_kernel)) != cudaSuccess) return e;
+    if ((e = preload(p2p_publish_counts_kernel)) != cudaSuccess) return e;
+    if ((e = preload(p2p_stats_kernel)) != cudaSuccess) return e;
+    if ((e = preload(p2p_absorb_kernel)) != cudaSuccess) return e;
+    if ((e = preload(p2p_list_to_slice_kernel)) != cudaSuccess) return e;
+    if ((e = preload(p2p_gather_or_kernel)) != cudaSuccess) return e;
+    if ((e = preload(bfs_pull_kernel<256>)) != cudaSuccess) return e;
+    if ((e = preload(scan_sizes_kernel<SCAN_NT, SCAN_VT, FrontierQuads>)) != cudaSuccess) return e;
+    if ((e = preload(scan_sizes_kernel<SCAN_NT, SCAN_VT, FrontierDegree>)) != cudaSuccess) return e;
+    if ((e = preload(compact_kernel<COMPACT_NT, COMPACT_VT, SliceListPred>)) != cudaSuccess) return e;
+    if ((e = preload(quad_advance_kernel<BfsPushPartQ, OUT_ROUTED, true, QUAD_NT, VT, QUAD_WSEG>)) != cudaSuccess) return e;
+    if ((e = preload(lbs_advance_kernel<BfsPushPartOp, OUT_ROUTED, true, LBS_NT, LBS_VT, LBS_SEG_T>)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+}  // namespace
+
+struct b200_p2p_bfs {
+    b200_ctx *ctx;
+    int rank, P;
+    uint32_t log_p;
+    int64_t n_global, n_local;
+    uint32_t wl;                       // words per bitmap slice
+    unsigned char *heap;
+    size_t heap_bytes, off_slice[2], off_inbox;
+    bool connected;
+    Peers peers;
+    void *opened[P2P_MAX];             // cudaIpcOpenMemHandle results (closed in destroy)
+    uint32_t *known, *full;            // [n_global/32] each, local
+    unsigned long long *box_counts;    // [P2P_MAX] device counters of the routed boxes
+    unsigned long long *h_res, *d_res; // mapped pinned result block
+    unsigned long long epoch;
+    unsigned stats_seq;
+    cudaEvent_t ev_run[2];
+    cudaEvent_t ev_level[P2P_TIMED_LEVELS + 1];
+    bool have_level_events;
+};
+
+extern "C" {
+
+int b200_p2p_bfs_heap_bytes(int num_ranks, int64_t n_global, int64_t *bytes) {
+    if (!bytes || num_ranks < 1 || num_ranks > P2P_MAX || (num_ranks & (num_ranks - 1)) || n_global < 1) return B200_ERR_INVALID;
+    const int64_t n_local = n_global / num_ranks;
+    if (n_local * num_ranks != n_global || n_local % 128) return B200_ERR_INVALID;
+    const size_t slice = ((size_t)(n_local / 32) * 4 + 255) & ~(size_t)255;
+    *bytes = (int64_t)(P2P_CTRL_BYTES + 2 * slice + (size_t)n_global * 4);
+    return B200_OK;
+}
+
+int b200_p2p_bfs_create(b200_ctx *ctx, int rank, int num_ranks, int64_t n_global, b200_p2p_bfs **out,
+                        void *ipc_handle_out, void **heap_base_out) {
+    if (!ctx || !out || rank < 0 || rank >= num_ranks || n_global > (1ll << 31)) return B200_ERR_INVALID;
+    *out = nullptr;
+    int64_t bytes = 0;
+    B200_TRY(b200_p2p_bfs_heap_bytes(num_ranks, n_global, &bytes));
+    B200_CUDA(cudaSetDevice(ctx->ws.device));
+    b200_p2p_bfs *s = new (std::nothrow) b200_p2p_bfs;
+    if (!s) return B200_ERR_NOMEM;
+    std::memset(s, 0, sizeof(*s));
+    s->ctx = ctx;
+    s->rank = rank;
+    s->P = num_ranks;
+    while ((1 << s->log_p) < num_ranks) ++s->log_p;
+    s->n_global = n_global;
+    s->n_local = n_global / num_ranks;
+    s->wl = (uint32_t)(s->n_local / 32);
+    const size_t slice = ((size_t)s->wl * 4 + 255) & ~(size_t)255;
+    s->off_slice[0] = P2P_CTRL_BYTES;
+    s->off_slice[1] = P2P_CTRL_BYTES + slice;
+    s->off_inbox = P2P_CTRL_BYTES + 2 * slice;
+    s->heap_bytes = (size_t)bytes;
+    int st = B200_OK;
+    do {
+        if ((st = cuda_status(cudaMalloc(&s->heap, s->heap_bytes)))) break;
+        if ((st = cuda_status(cudaMemset(s->heap, 0, P2P_CTRL_BYTES + 2 * slice)))) break;
+        if ((st = cuda_status(cudaMalloc(&s->known, (size_t)(n_global / 8))))) break;
+        if ((st = cuda_status(cudaMalloc(&s->full, (size_t)(n_global / 8))))) break;
+        if ((st = cuda_status(cudaMalloc(&s->box_counts, sizeof(unsigned long long) * P2P_MAX)))) break;
+        if ((st = cuda_status(cudaHostAlloc(&s->h_res, sizeof(unsigned long long) * RES_WORDS, cudaHostAllocMapped)))) break;
+        std::memset(s->h_res, 0, sizeof(unsigned long long) * RES_WORDS);
+        if ((st = cuda_status(cudaHostGetDevicePointer(&s->d_res, s->h_res, 0)))) break;
+        if ((st = cuda_status(cudaEventCreate(&s->ev_run[0])))) break;
+        if ((st = cuda_status(cudaEventCreate(&s->ev_run[1])))) break;
+        if ((st = ensure_traversal_scratch(ctx, s->n_local))) break;
+        if ((st = cuda_status(preload_kernels()))) break;
+        if (ipc_handle_out) {
+            cudaIpcMemHandle_t h;
+            if ((st = cuda_status(cudaIpcGetMemHandle(&h, s->heap)))) break;
+            static_assert(sizeof(h) == B200_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+            std::memcpy(ipc_handle_out, &h, sizeof(h));
+        }
+        if ((st = cuda_status(cudaDeviceSynchronize()))) break;
+    } while (0);
+    if (st != B200_OK) {
+        b200_p2p_bfs_destroy(s);
+        return st;
+    }
+    for (int p = 0; p < P2P_MAX; ++p) s->peers.base[p] = s->heap;   // until connected
+    if (heap_base_out) *heap_base_out = s->heap;
+    *out = s;
+    return B200_OK;
+}
+
+int b200_p2p_bfs_connect(b200_p2p_bfs *s, const void *ipc_handles, void *const *peer_bases) {
+    if (!s || (s->P > 1 && !ipc_handles && !peer_bases)) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(s->ctx->ws.device));
+    for (int p = 0; p < s->P; ++p) {
+        if (p == s->rank) {
+            s->peers.base[p] = s->heap;
+        } else if (peer_bases) {
+            if (!peer_bases[p]) return B200_ERR_INVALID;
+            // same process: heaps on other devices need peer access enabled once
+            cudaPointerAttributes attr;
+            B200_CUDA(cudaPointerGetAttributes(&attr, peer_bases[p]));
+            if (attr.device != s->ctx->ws.device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(attr.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_status(e);
+                (void)cudaGetLastError();
+            }
+            s->peers.base[p] = static_cast<unsigned char *>(peer_bases[p]);
+        } else {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, static_cast<const unsigned char *>(ipc_handles) + (size_t)p * B200_IPC_HANDLE_BYTES, sizeof(h));
+            void *ptr = nullptr;
+            B200_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            s->opened[p] = ptr;
+            s->peers.base[p] = static_cast<unsigned char *>(ptr);
+        }
+    }
+    s->connected = true;
+    return B200_OK;
+}
+
+int b200_p2p_bfs_destroy(b200_p2p_bfs *s) {
+    if (!s) return B200_OK;
+    cudaSetDevice(s->ctx->ws.device);
+    cudaStreamSynchronize((cudaStream_t)s->ctx->ws.stream);
+    for (int p = 0; p < P2P_MAX; ++p)
+        if (s->opened[p]) cudaIpcCloseMemHandle(s->opened[p]);
+    if (s->heap) cudaFree(s->heap);
+    if (s->known) cudaFree(s->known);
+    if (s->full) cudaFree(s->full);
+    if (s->box_counts) cudaFree(s->box_counts);
+    if (s->h_res) cudaFreeHost(s->h_res);
+    if (s->ev_run[0]) cudaEventDestroy(s->ev_run[0]);
+    if (s->ev_run[1]) cudaEventDestroy(s->ev_run[1]);
+    if (s->have_level_events)
+        for (int i = 0; i <= P2P_TIMED_LEVELS; ++i) cudaEventDestroy(s->ev_level[i]);
+    delete s;
+    return B200_OK;
+}
+
+int b200_p2p_bfs_run(b200_p2p_bfs *s, const b200_graph *g, int64_t m_global, int32_t src, int mode, float alpha, float beta,
+                     int32_t *d_labels, b200_stats *stats, int64_t *sent_per_level) {
+    if (!s || !g || !d_labels || src < 0 || src >= s->n_global || g->n != s->n_local || m_global < g->m) return B200_ERR_INVALID;
+    if (mode != B200_BFS_PUSH && mode != B200_BFS_BEAMER) return B200_ERR_INVALID;
+    if (s->P > 1 && !s->connected) return B200_ERR_INVALID;
+    b200_ctx *ctx = s->ctx;
+    b200_workspace *ws = &ctx->ws;
+    B200_CUDA(cudaSetDevice(ws->device));
+    cudaStream_t st = ws_stream(ws);
+    const int me = s->rank, P = s->P;
+    const Partition part{s->log_p, (uint32_t)me, (uint32_t)s->n_local};
+    const int64_t n = s->n_global;
+    const bool timing = stats && stats->collect_timing;
+    if (timing && !s->have_level_events) {
+        for (int i = 0; i <= P2P_TIMED_LEVELS; ++i) B200_CUDA(cudaEventCreate(&s->ev_level[i]));
+        s->have_level_events = true;
+    }
+    const int64_t launches0 = ws->launches;
+    const uint32_t *pull_off = g->col_offsets ? g->col_offsets : g->row_offsets;
+    const int32_t *pull_idx = g->row_indices ? g->row_indices : g->col_indices;
+    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(g->col_indices);
+    Ctrl *my_ctrl = reinterpret_cast<Ctrl *>(s->heap);
+    int *my_inbox = reinterpret_cast<int *>(s->heap + s->off_inbox);
+    if (alpha <= 0.f) alpha = 15.f;
+    if (beta <= 0.f) beta = 18.f;
+
+    B200_CUDA(cudaEventRecord(s->ev_run[0], st));
+    B200_CUDA(cudaMemsetAsync(d_labels, 0xFF, sizeof(int32_t) * (size_t)s->n_local, st));
+    B200_CUDA(cudaMemsetAsync(s->known, 0, (size_t)(n / 8), st));
+    p2p_init_kernel<<<1, 1, 0, st>>>(d_labels, s->known, ctx->frontier[0], src, part);
+    ws->launches++;
+    B200_CUDA(cudaGetLastError());
+
+    int sel = 0, sb = 0, level = 0;
+    bool pull = false;
+    int64_t flen_local = part.owner((uint32_t)src) == part.me ? 1 : 0, flen = 1, reached = 1, total_arcs = 0;
+    int64_t m_unexplored = m_global;
+    int status = B200_OK;
+
+    for (;;) {
+        const bool tl = timing && level < P2P_TIMED_LEVELS;
+        if (tl && level == 0) B200_CUDA(cudaEventRecord(s->ev_level[0], st));
+        B200_CUDA(reset_counters(ws));
+        uint32_t *slice_w = reinterpret_cast<uint32_t *>(s->heap + s->off_slice[sb ^ 1]);
+        if (!pull) {
+            B200_CUDA(cudaMemsetAsync(s->box_counts, 0, sizeof(unsigned long long) * P2P_MAX, st));
+            int32_t *next = ctx->frontier[sel ^ 1];
+            if (flen_local) {
+                RoutedOut r;
+                std::memset(&r, 0, sizeof r);
+                r.num_dest = P;
+                r.count = s->box_counts;
+                for (int p = 0; p < P; ++p) {
+                    // box[p]: segment `me` of rank p's inbox -- a peer pointer: the flush stores over NVLink
+                    r.box[p] = p == me ? next : reinterpret_cast<int *>(s->peers.base[p] + s->off_inbox) + (size_t)me * (size_t)s->n_local;
+                    r.capacity[p] = (unsigned long long)s->n_local;
+                }
+                if (quad) {
+                    B200_CUDA(launch_quad_scan(ws, ctx->frontier[sel], (uint32_t)flen_local, g->row_offsets, part.log_p));
+                    const QuadArgs a = make_quad_args(ws, ctx->frontier[sel], (uint32_t)flen_local, g->row_offsets, g->col_indices, nullptr, part.log_p);
+                    BfsPushPartQ op{s->known, d_labels, level + 1, part};
+                    B200_CUDA((launch_quad_advance<OUT_ROUTED, true>(ws, a, op, nullptr, 0ull, &r)));
+                } else {
+                    B200_CUDA(launch_frontier_scan(ws, ctx->frontier[sel], (uint32_t)flen_local, g->row_offsets, part.log_p));
+                    const LbsArgs a = make_lbs_args(ws, ctx->frontier[sel], (uint32_t)flen_local, g->row_offsets, g->col_indices, part.log_p);
+                    BfsPushPartOp op{s->known, d_labels, level + 1, part};
+                    B200_CUDA((launch_lbs_advance<OUT_ROUTED, true>(ws, a, op, nullptr, 0ull, &r)));
+                }
+            }
+            if (P > 1) {
+                p2p_publish_counts_kernel<<<1, 32, 0, st>>>(s->peers, me, P, ++s->epoch, s->box_counts, s->d_res);
+                p2p_absorb_kernel<<<ws->num_sms * 2, 256, 0, st>>>(my_inbox, (size_t)s->n_local, my_ctrl->counts, me, P, s->known,
+                                                                   d_labels, level + 1, part, next, (unsigned long long)s->n_local,
+                                                                   s->box_counts + me, ws->d_counters, g->row_offsets);
+                ws->launches += 2;
+                B200_CUDA(cudaGetLastError());
+            }
+            if (mode == B200_BFS_BEAMER) {
+                B200_CUDA(cudaMemsetAsync(slice_w, 0, sizeof(uint32_t) * (size_t)s->wl, st));
+                p2p_list_to_slice_kernel<<<ws->num_sms, 256, 0, st>>>(next, s->box_counts + me, slice_w, part);
+                ws->launches++;
+                B200_CUDA(cudaGetLastError());
+            }
+        } else {
+            p2p_gather_or_kernel<<<ws->num_sms * 4, 256, 0, st>>>(s->peers, s->off_slice[sb], s->wl / 4, P,
+                                                                  reinterpret_cast<uint4 *>(s->full), reinterpret_cast<uint4 *>(s->known));
+            bfs_pull_kernel<256><<<ws->num_sms * 8, 256, 0, st>>>((uint32_t)s->n_local, pull_off, pull_idx, s->full, slice_w,
+                                                                  s->known + (size_t)me * s->wl, d_labels, level + 1, ws->d_counters, part);
+            ws->launches += 2;
+            B200_CUDA(cudaGetLastError());
+        }
+        p2p_stats_kernel<<<1, 32, 0, st>>>(s->peers, me, P, ++s->epoch, (int)(s->stats_seq++ & 1u), ws->d_counters, s->box_counts,
+                                           pull ? 0 : 1, (pull || quad) ? B200_CNT_ARCS : B200_CNT_TOTAL, s->d_res);
+        ws->launches++;
+        B200_CUDA(cudaGetLastError());
+        if (tl) B200_CUDA(cudaEventRecord(s->ev_level[level + 1], st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        if (s->h_res[RES_TIMEOUT]) {
+            s->h_res[RES_TIMEOUT] = 0;
+            status = B200_ERR_TIMEOUT;
+            break;
+        }
+        if (s->h_res[RES_SUM + ROW_OVERFLOW]) {
+            status = B200_ERR_OVERFLOW;
+            break;
+        }
+        const int64_t found = (int64_t)s->h_res[RES_SUM + ROW_NEXT], arcs = (int64_t)s->h_res[RES_SUM + ROW_ARCS];
+        const int64_t next_deg = (int64_t)s->h_res[RES_SUM + ROW_DEG], sent = (int64_t)s->h_res[RES_SUM + ROW_SENT];
+        const int64_t next_local = (int64_t)s->h_res[RES_OWN + ROW_NEXT];
+        if (stats && level < B200_MAX_LEVELS) {
+            b200_level_stat *ls = &stats->level[level];
+            ls->direction = pull ? 1 : 0;
+            ls->frontier_len = flen;
+            ls->arcs = arcs;
+            ls->discovered = found;
+        }
+        if (sent_per_level && level < B200_MAX_LEVELS) sent_per_level[level] = sent;
+        total_arcs += arcs;
+        ++level;
+        if (found == 0) break;
+        reached += found;
+        if (!pull) {
+            m_unexplored -= arcs;
+            sel ^= 1;
+            flen_local = next_local;
+            if (mode == B200_BFS_BEAMER && (double)next_deg > (double)m_unexplored / alpha && found > flen) {
+                pull = true;
+                sb ^= 1;   // the slice written this level is the frontier of the first pull level
+            }
+        } else {
+            sb ^= 1;
+            if ((double)found < (double)n / beta && found < flen) {
+                // hand the (small) frontier back to push: peers' last pull discoveries become "known",
+                // this rank's slice becomes its frontier list
+                p2p_gather_or_kernel<<<ws->num_sms * 4, 256, 0, st>>>(s->peers, s->off_slice[sb], s->wl / 4, P,
+                                                                      reinterpret_cast<uint4 *>(s->full), reinterpret_cast<uint4 *>(s->known));
+                ws->launches++;
+                B200_CUDA(cudaGetLastError());
+                B200_CUDA(reset_counters(ws));
+                B200_CUDA(launch_compact(ws, SliceListPred{reinterpret_cast<const uint32_t *>(s->heap + s->off_slice[sb]), part},
+                                         (uint32_t)s->n_local, ctx->frontier[sel], (unsigned long long)s->n_local,
+                                         ws->d_counters + B200_CNT_OUT, ws->d_counters + B200_CNT_OVERFLOW));
+                flen_local = next_local;
+                pull = false;
+            }
+        }
+        flen = found;
+    }
+    B200_CUDA(cudaEventRecord(s->ev_run[1], st));
+    B200_CUDA(cudaEventSynchronize(s->ev_run[1]));
+    if (stats) {
+        stats->num_levels = level;
+        stats->reached = reached;
+        stats->total_arcs = total_arcs;
+        stats->launches = ws->launches - launches0;
+        B200_CUDA(cudaEventElapsedTime(&stats->device_ms, s->ev_run[0], s->ev_run[1]));
+        if (timing) {
+            const int L = level < P2P_TIMED_LEVELS ? level : P2P_TIMED_LEVELS;
+            for (int l = 0; l < L; ++l) {
+                B200_CUDA(cudaEventElapsedTime(&stats->level[l].level_ms, s->ev_level[l], s->ev_level[l + 1]));
+                stats->level[l].advance_ms = 0.f;
+            }
+        }
+    }
+    return status;
+}
+
+}  // extern "C"

@@ -109,6 +109,11 @@ def load_library():
         "b200_mg_bitmap_or": ([vp, vp, vp, i64], i32),
         "b200_mg_list_to_slice": ([vp, vp, vp, i64, vp], i32),
         "b200_mg_slice_to_list": ([vp, vp, vp, vp, pi64], i32),
+        "b200_p2p_bfs_heap_bytes": ([i32, i64, pi64], i32),
+        "b200_p2p_bfs_create": ([vp, i32, i32, i64, C.POINTER(vp), vp, C.POINTER(vp)], i32),
+        "b200_p2p_bfs_connect": ([vp, vp, vp], i32),
+        "b200_p2p_bfs_run": ([vp, pg, i64, i32, i32, f32, f32, vp, ps, pi64], i32),
+        "b200_p2p_bfs_destroy": ([vp], i32),
         "b200_host_graph_upload": ([vp, i64, i64, vp, vp, vp, C.POINTER(vp)], i32),
         "b200_host_graph_free": ([vp, vp], i32),
         "b200_host_graph_view": ([vp, pg], i32),

@@ -1,0 +1,87 @@
+"""Peer-memory multi-GPU BFS (include/b200_frontier.h, b200_p2p_bfs_*): one rank per GPU, the frontier
+exchange fused into the kernels over NVLink.  This module only sets the ranks up -- it allocates the
+rank's symmetric heap, trades the CUDA IPC handles through torch.distributed (or plain addresses when
+the ranks are threads of one process) and calls the C entry point that runs the whole traversal."""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import lib as L
+
+IPC_HANDLE_BYTES = 64
+
+
+class P2PBfs:
+    def __init__(self, ctx, rank: int, world: int, n_global: int, m_global: int, graph_local):
+        import torch
+        self._L = L.load_library()
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.n_global, self.m_global, self.n_local = n_global, m_global, n_global // world
+        self.g = graph_local
+        self.cg = graph_local.cview()
+        self._h = C.c_void_p()
+        self._handle = (C.c_ubyte * IPC_HANDLE_BYTES)()
+        base = C.c_void_p()
+        L._check(self._L.b200_p2p_bfs_create(ctx._h, rank, world, n_global, C.byref(self._h), self._handle, C.byref(base)),
+                 "b200_p2p_bfs_create")
+        self.heap_base = base.value
+        self.labels = torch.empty(self.n_local, dtype=torch.int32, device=ctx.torch_device)
+        self.levels = []
+        self.device_ms = 0.0
+        self.launches = 0
+        if world == 1:
+            self.connect_local([self.heap_base])
+
+    # -- wiring ------------------------------------------------------------------------------
+    def ipc_handle(self) -> bytes:
+        return bytes(self._handle)
+
+    def connect_ipc(self, handles: bytes):
+        """handles: world * 64 bytes, rank-major (every rank's ipc_handle())."""
+        assert len(handles) == self.world * IPC_HANDLE_BYTES
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        L._check(self._L.b200_p2p_bfs_connect(self._h, buf, None), "b200_p2p_bfs_connect")
+
+    def connect_local(self, bases):
+        arr = (C.c_void_p * self.world)(*bases)
+        L._check(self._L.b200_p2p_bfs_connect(self._h, None, arr), "b200_p2p_bfs_connect")
+
+    def connect_torch_distributed(self):
+        """All-gather the IPC handles over the default process group (NCCL or gloo) and map the peers."""
+        import torch
+        import torch.distributed as dist
+        dev = self.ctx.torch_device if dist.get_backend() == "nccl" else torch.device("cpu")
+        mine = torch.frombuffer(bytearray(self.ipc_handle()), dtype=torch.uint8).to(dev)
+        rows = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(rows, mine)
+        self.connect_ipc(b"".join(bytes(r.cpu().numpy().tobytes()) for r in rows))
+        dist.barrier()
+
+    # -- the traversal -----------------------------------------------------------------------
+    def run(self, src: int = 0, mode: str = "beamer", alpha: float = 15.0, beta: float = 18.0, timing: bool = False):
+        cs = L.CStats()
+        cs.collect_timing = int(timing)
+        sent = (C.c_int64 * L.MAX_LEVELS)()
+        m = L.BFS_BEAMER if mode == "beamer" else L.BFS_PUSH
+        L._check(self._L.b200_p2p_bfs_run(self._h, C.byref(self.cg), self.m_global, src, m, alpha, beta,
+                                          self.labels.data_ptr(), C.byref(cs), sent), "b200_p2p_bfs_run")
+        st = L.Stats(cs)
+        self.levels = [dict(direction=l["direction"], frontier=l["frontier_len"], arcs=l["arcs"], discovered=l["discovered"],
+                            sent=int(sent[i]), level_ms=l["level_ms"]) for i, l in enumerate(st.levels)]
+        self.device_ms, self.launches = st.device_ms, st.launches
+        return st.num_levels
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b200_p2p_bfs_destroy(self._h)
+            self._h = None
+
+    # -- helpers shared with dist.GpuRank (verification, TEPS numerator) ------------------------
+    def reached_degree_sum(self) -> int:
+        import torch
+        off = self.g.row_offsets.to(torch.int64) & 0xFFFFFFFF
+        deg = off[1:] - off[:-1]
+        return int(deg[self.labels >= 0].sum().item())
+
+    def reached_count(self) -> int:
+        return int((self.labels >= 0).sum().item())

@@ -85,6 +85,90 @@ def test_partitioned_bfs_other_sources(src):
     assert np.array_equal(labels, ref)
 
 
+def _virtual_ranks_p2p(scale, ef, seed, world, src, mode, repeat=2):
+    """P ranks as threads of this process, each with its OWN stream on GPU 0 (the cross-rank flag
+    barriers spin inside kernels, so the ranks' kernels must be able to run concurrently); heaps are
+    wired by address (b200_p2p_bfs_connect with peer_bases)."""
+    import mini_b200 as mb
+    from mini_b200 import dist as D
+    from mini_b200.p2p import P2PBfs
+    bar = threading.Barrier(world)
+    bases, out, errs = [None] * world, [None] * world, []
+    n = 1 << scale
+
+    def work(rank):
+        try:
+            ctx = mb.Context(0, stream=None)
+            g = D.build_rank_graph(ctx, scale, ef, seed, rank, world)
+            bfs = P2PBfs(ctx, rank, world, n, (2 * ef) << scale, g)
+            bases[rank] = bfs.heap_base
+            bar.wait()
+            if world > 1:
+                bfs.connect_local(bases)
+            bar.wait()
+            for _ in range(repeat):
+                levels = bfs.run(src, mode)
+            ctx.sync()
+            out[rank] = (bfs.labels.cpu().numpy(), levels, list(bfs.levels))
+            bar.wait()
+            bfs.close()
+            ctx.close()
+        except BaseException as e:   # noqa: BLE001
+            errs.append(e)
+            bar.abort()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(600) for t in ts]
+    if errs:
+        raise errs[0]
+    return out
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+@pytest.mark.parametrize("mode", ["push", "beamer"])
+def test_p2p_bfs_virtual_ranks(world, mode):
+    scale, ef, seed, src = 14, 16, 1, 0
+    ref = oracle.bfs(oracle.rmat_csr(scale, ef, seed), src)
+    res = _virtual_ranks_p2p(scale, ef, seed, world, src, mode)
+    labels = np.empty(1 << scale, np.int32)
+    for r in range(world):
+        labels[r::world] = res[r][0]
+    assert np.array_equal(labels, ref)
+    stats = res[0][2]
+    assert all(res[r][2] == stats or [dict(l, level_ms=0) for l in res[r][2]] == [dict(l, level_ms=0) for l in stats]
+               for r in range(world))                    # every rank saw the same global level summary
+    assert sum(l["discovered"] for l in stats) + 1 == int((ref >= 0).sum())
+    if mode == "beamer":
+        assert any(l["direction"] == "pull" for l in stats)
+    if world > 1 and mode == "push":
+        assert 0 < sum(l["sent"] for l in stats) <= (world - 1) * (1 << scale)
+
+
+@pytest.mark.parametrize("src", [1, 77, 12345])
+def test_p2p_bfs_other_sources(src):
+    scale, ef, seed, world = 14, 8, 3, 4
+    ref = oracle.bfs(oracle.rmat_csr(scale, ef, seed), src)
+    res = _virtual_ranks_p2p(scale, ef, seed, world, src, "beamer")
+    labels = np.empty(1 << scale, np.int32)
+    for r in range(world):
+        labels[r::world] = res[r][0]
+    assert np.array_equal(labels, ref)
+
+
+def test_p2p_ranks_if_multiple_gpus():
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    world = 2 if ngpu < 4 else (4 if ngpu < 8 else 8)
+    for mode in ("beamer", "push"):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+               "127.0.0.1", "--master-port", "29621", os.path.join(ROOT, "tests", "run_p2p_bfs.py"), "--scale", "18",
+               "--mode", mode]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "P2P_BFS_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 def test_nccl_ranks_if_multiple_gpus():
     ngpu = torch.cuda.device_count()
     if ngpu < 2:
