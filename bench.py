@@ -6,8 +6,9 @@ kernel's HBM roofline and the reference's CPU BFS timed beside it.
 
 A "step" is one BFS from vertex 0 over the whole graph (source in frontier -> labels final).
 N = 1: BASELINE.json configs[1], RMAT scale-22 ef16, push BFS (LB advance + fused uniquify filter).
-N > 1: configs[3], RMAT scale-26 ef16, 1D vertex-range partition, one rank per GPU, NCCL frontier
-exchange (mini_b200.dist).  Prints ONE JSON line on rank 0.
+N > 1: configs[3], RMAT scale-26 ef16, cyclic 1D vertex partition, one rank per GPU, frontier exchange
+fused into the kernels over NVLink peer memory (mini_b200.p2p; --exchange nccl = the NCCL form,
+mini_b200.dist).  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -270,6 +271,11 @@ def main():
     ap.add_argument("--advance", default="quad", choices=["quad", "lbs"],
                     help="push-advance kernel: quad_advance.cuh (default) or the first-generation advance.cuh")
     ap.add_argument("--mg-mode", dest="mg_mode", default="beamer", choices=["push", "beamer"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1 frontier exchange: fused into the kernels over NVLink peer memory, or NCCL collectives")
+    ap.add_argument("--no-mg-other", dest="mg_other", action="store_false", help="N>1: skip the other traversal mode")
+    ap.add_argument("--no-mg-single", dest="mg_single", action="store_false",
+                    help="N>1: skip the same-graph single-GPU run on rank 0")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -1,6 +1,14 @@
 """bench.py leg for N > 1 GPUs: direction-optimising BFS on RMAT scale-26 ef16 (BASELINE.json
-configs[3]), cyclic 1D vertex partition, one rank per GPU, NCCL frontier exchange.  Strong scaling:
-the graph is fixed, each rank holds 1/N of the rows."""
+configs[3]), cyclic 1D vertex partition, one rank per GPU.  Strong scaling: the graph is fixed, each
+rank holds 1/N of the rows.
+
+Frontier exchange (`--exchange`):
+  p2p  (default)  the exchange is fused into the kernels over NVLink peer memory (mini_b200.p2p,
+                  csrc/p2p_bfs.cu): no collective call on the data path, one host sync per level;
+  nccl            alltoallv / allgather / allreduce through torch.distributed (mini_b200.dist) -- the
+                  baseline form of the same algorithm.
+torch.distributed (NCCL) is used in both for rendezvous, IPC-handle exchange, barriers and the
+max-over-ranks of the timings."""
 from __future__ import annotations
 
 import json
@@ -8,11 +16,16 @@ import os
 import time
 
 
+def _level_rows(levels):
+    return [dict(d=l["direction"], F=l["frontier"], arcs=l["arcs"], found=l["discovered"], sent=l["sent"]) for l in levels]
+
+
 def run(args) -> int:
     import torch
     import torch.distributed as dist
     import mini_b200 as mb
     from mini_b200 import dist as D
+    from mini_b200.p2p import P2PBfs
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -27,16 +40,44 @@ def run(args) -> int:
     t0 = time.time()
     g = D.build_rank_graph(ctx, scale, ef, 1, rank, world)
     build_s = time.time() - t0
-    rk = D.GpuRank(ctx, rank, world, n, g)
     comm = D.TorchComm(ctx.torch_device)
-    mode = "beamer" if args.mode in ("push", "beamer") and args.mg_mode == "beamer" else "push"
-    bfs = D.DistBFS(rk, comm, n, m, mode=mode)
+    mode = "beamer" if args.mg_mode == "beamer" else "push"
+    exchange = args.exchange
+
+    if exchange == "p2p":
+        rk = P2PBfs(ctx, rank, world, n, m, g)
+        rk.connect_torch_distributed()
+
+        def run_bfs(md=mode):
+            rk.run(0, md)
+            return rk.levels
+    else:
+        rk = D.GpuRank(ctx, rank, world, n, g)
+        drivers = {md: D.DistBFS(rk, comm, n, m, mode=md) for md in ("beamer", "push")}
+
+        def run_bfs(md=mode):
+            drivers[md].run(0)
+            return drivers[md].levels
 
     sampler = None
     if rank == 0:
         from bench import ClockSampler
         sampler = ClockSampler(dev)
         sampler.start()
+
+    import ctypes as C
+    from mini_b200 import lib as L
+
+    class _WS(C.Structure):   # prefix of b200_workspace up to `launches`
+        _fields_ = [("stream", C.c_void_p), ("device", C.c_int32), ("num_sms", C.c_int32), ("d_status", C.c_void_p),
+                    ("status_tiles", C.c_int64), ("d_tile_counter", C.c_void_p), ("epoch", C.c_uint), ("reserved", C.c_uint),
+                    ("d_counters", C.c_void_p), ("h_counters", C.c_void_p), ("d_scanned", C.c_void_p),
+                    ("scanned_capacity", C.c_int64), ("launches", C.c_int64)]
+
+    ws = C.cast(L.load_library().b200_ctx_workspace(ctx._h), C.POINTER(_WS))
+
+    def ctx_launches():
+        return int(ws.contents.launches)
 
     def timed(steps, fn):
         dist.barrier()
@@ -53,27 +94,17 @@ def run(args) -> int:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), ctx_launches() - launches0
 
-    import ctypes as C
-    from mini_b200 import lib as L
-
-    class _WS(C.Structure):   # prefix of b200_workspace up to `launches`
-        _fields_ = [("stream", C.c_void_p), ("device", C.c_int32), ("num_sms", C.c_int32), ("d_status", C.c_void_p),
-                    ("status_tiles", C.c_int64), ("d_tile_counter", C.c_void_p), ("epoch", C.c_uint), ("reserved", C.c_uint),
-                    ("d_counters", C.c_void_p), ("h_counters", C.c_void_p), ("d_scanned", C.c_void_p),
-                    ("scanned_capacity", C.c_int64), ("launches", C.c_int64)]
-
-    ws = C.cast(L.load_library().b200_ctx_workspace(ctx._h), C.POINTER(_WS))
-
-    def ctx_launches():
-        return int(ws.contents.launches)
-
     for _ in range(args.warmup):
-        bfs.run(0)
-    ms_total, launches = timed(args.steps, lambda: bfs.run(0))
-    levels = list(bfs.levels)
-    reached = comm.all_reduce_sum([rk.reached_degree_sum(), rk.reached_count()])
-    reached_arcs, reached_vertices = reached
+        run_bfs()
+    ms_total, launches = timed(args.steps, run_bfs)
+    levels = list(run_bfs())
+    level_ms = [round(l.get("level_ms", 0.0), 4) for l in levels]
+    if exchange == "p2p":                       # one more run with per-level events (outside the timed region)
+        rk.run(0, mode, timing=True)
+        level_ms = [round(l["level_ms"], 4) for l in rk.levels]
+    reached_arcs, reached_vertices = comm.all_reduce_sum([rk.reached_degree_sum(), rk.reached_count()])
     value = reached_arcs * args.steps / (ms_total * 1e-3) / 1e9
+    props_ok, level_hist = D.verify_bfs_properties(rk, comm, 0)
 
     # end to end: every step uploads the rank's initial labels from pinned host memory, runs, downloads labels
     h_init = torch.full((rk.n_local,), -1, dtype=torch.int32).pin_memory()
@@ -81,7 +112,7 @@ def run(args) -> int:
 
     def e2e_step():
         rk.labels.copy_(h_init, non_blocking=True)
-        bfs.run(0)
+        run_bfs()
         h_out.copy_(rk.labels, non_blocking=True)
         torch.cuda.synchronize()
 
@@ -96,37 +127,85 @@ def run(args) -> int:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
 
-    props_ok, level_hist = D.verify_bfs_properties(rk, comm, 0)
+    # the other traversal mode on the same partitioned graph (push-only when the headline is direction-optimising)
+    other = "push" if mode == "beamer" else "beamer"
+    other_line = None
+    if args.mg_other:
+        for _ in range(2):
+            run_bfs(other)
+        o_ms, _ = timed(max(2, args.steps // 2), lambda: run_bfs(other))
+        o_ms /= max(2, args.steps // 2)
+        o_levels = list(run_bfs(other))
+        other_line = {"mode": other, "ms_per_step": o_ms, "value": reached_arcs / (o_ms * 1e-3) / 1e9, "unit": "GTEPS",
+                      "sent_vertices": sum(l["sent"] for l in o_levels), "levels": len(o_levels)}
+
     all_launches = comm.all_reduce_sum([launches])[0]
     sent = sum(l["sent"] for l in levels)
+
+    # the same graph on ONE GPU (rank 0 builds the whole scale-26 CSR: 8 GiB + offsets), same modes: the
+    # denominator of "scaling from 1 to N GPUs on scale-26" (north_star); the other ranks wait at the barrier
+    single = None
+    if args.mg_single and rank == 0:
+        try:
+            g1 = ctx.rmat_graph(scale, ef, 1)
+            lab1 = torch.empty(g1.n, dtype=torch.int32, device=ctx.torch_device)
+            single = {}
+            for md, flag in (("beamer", mb.BFS_BEAMER), ("push", mb.BFS_PUSH)):
+                for _ in range(3):
+                    ctx.bfs(g1, 0, flag, 15.0, 18.0, labels=lab1)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = max(3, args.steps // 2)
+                e0.record()
+                for _ in range(reps):
+                    ctx.bfs(g1, 0, flag, 15.0, 18.0, labels=lab1)
+                e1.record()
+                torch.cuda.synchronize()
+                ms1 = e0.elapsed_time(e1) / reps
+                single[md] = {"ms_per_step": ms1, "value": reached_arcs / (ms1 * 1e-3) / 1e9, "unit": "GTEPS"}
+            del g1, lab1
+        except Exception as e:   # noqa: BLE001  (e.g. not enough free HBM next to the partition)
+            single = {"unavailable": repr(e)[:200]}
+    dist.barrier()
+
     if rank == 0:
         clocks = sampler.stop()
+        ex_text = ("frontier exchange fused into the kernels over NVLink peer memory (advance flush stores into the owner's "
+                   "inbox; gather+OR of bitmap slices; flag barriers) -- no NCCL on the data path") if exchange == "p2p" else \
+                  "NCCL alltoallv (push) / allgather of bitmap slices (pull)"
         line = {
             "metric": "bfs_gteps_rmat", "value": value, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": f"direction-optimising BFS from vertex 0, RMAT scale-{scale} ef16 symmetrised "
-                                   f"(n={n}, m={m}), cyclic 1D vertex partition over {world} GPUs, NCCL alltoallv "
-                                   "(push) / allgather of bitmap slices (pull)",
-                       "mode": mode, "teps_numerator": "sum of deg(v) over reached v", "reached_arcs": reached_arcs,
-                       "reached_vertices": reached_vertices, "parallelism": f"1d-cyclic x{world}",
+                                   f"(n={n}, m={m}), cyclic 1D vertex partition over {world} GPUs, {ex_text}",
+                       "mode": mode, "exchange": exchange, "teps_numerator": "sum of deg(v) over reached v",
+                       "reached_arcs": reached_arcs, "reached_vertices": reached_vertices,
+                       "parallelism": f"1d-cyclic x{world}",
                        "l2": "inputs larger than L2 (per-rank col_indices %d MiB)" % (g.m * 4 >> 20),
-                       "graph_build_s": round(build_s, 2),
-                       "levels": [dict(d=l["direction"], F=l["frontier"], arcs=l["arcs"], found=l["discovered"], sent=l["sent"])
-                                  for l in levels]},
+                       "graph_build_s": round(build_s, 2), "levels": _level_rows(levels), "level_ms": level_ms},
             "clocks": clocks,
             "e2e": {"value": reached_arcs * args.steps / e2e_s / 1e9, "unit": "GTEPS",
                     "h2d_bytes_per_step": rk.n_local * 4 * world, "d2h_bytes_per_step": rk.n_local * 4 * world,
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": all_launches,
             "roofline": {"bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
-                         "note": "per-kernel roofline is reported by the N=1 line; exchange volume: "
-                                 f"{sent * 4} bytes of vertex ids per BFS over NVLink"},
+                         "note": "per-kernel roofline is reported by the N=1 line",
+                         "nvlink": {"bytes_sent_per_bfs": sent * 4, "bitmap_bytes_gathered_per_pull_level_per_gpu":
+                                    (world - 1) * (n // 8) // world, "peak_gbs_per_direction": 900.0}},
             "cpu_baseline": None,
+            "other_mode": other_line,
+            "single_gpu_same_graph": single,
             "parity": {"bfs_properties_hold_at_full_scale": props_ok, "vertices_per_level": level_hist},
         }
+        if single and mode in single:
+            line["speedup_vs_1gpu_same_graph"] = single[mode]["ms_per_step"] / (ms_total / args.steps)
+            if other_line and other in single:
+                other_line["speedup_vs_1gpu_same_graph"] = single[other]["ms_per_step"] / other_line["ms_per_step"]
         print(json.dumps(line))
     dist.barrier()
+    if exchange == "p2p":
+        rk.close()
     ctx.close()
     dist.destroy_process_group()
     return 0 if props_ok else 1
