@@ -16,6 +16,7 @@
 #include "device_utils.cuh"
 #include "lbs.cuh"
 #include "workspace.h"
+#include "partition.cuh"
 
 namespace b200 {
 
@@ -241,22 +242,6 @@ struct SsspRelaxOp {
         if (stamp) return atomicExch(stamp + dst, iteration) != iteration;
         return true;
     }
-};
-
-// ---------------------------------------------------------------------------
-// Cyclic 1D vertex partition (multi-GPU): P = 2^log_p ranks, vertex v is owned by rank
-// v & (P-1) and is row v >> log_p of that rank's CSR (global column ids).  Every bitmap
-// is indexed "rank-major": bit(v) = owner(v) * n_local + (v >> log_p), so a rank's own
-// slice is the contiguous word range [me * n_local/32, (me+1) * n_local/32) and
-// ncclAllGather of the slices yields the whole bitmap in place.  P = 1 is the identity.
-// ---------------------------------------------------------------------------
-struct Partition {
-    uint32_t log_p;      // log2(P)
-    uint32_t me;         // this rank
-    uint32_t n_local;    // vertices per rank (multiple of 32)
-    __host__ __device__ __forceinline__ uint32_t owner(uint32_t v) const { return v & ((1u << log_p) - 1u); }
-    __host__ __device__ __forceinline__ uint32_t row(uint32_t v) const { return v >> log_p; }
-    __host__ __device__ __forceinline__ uint32_t bit(uint32_t v) const { return owner(v) * n_local + row(v); }
 };
 
 // BFS push on one rank's slice.  `known` is an n-bit map: exact "visited" for owned

@@ -232,12 +232,17 @@ int b200_pr_run(b200_ctx *ctx, const b200_graph *g, int max_iter, int scatter, f
                 float *d_reduced, int64_t *h_frontier_lens, int *iterations, b200_stats *stats);
 
 /* ---- multi-GPU BFS: per-rank steps (new; the reference is single-GPU by design, README.md:4) -------
- * Cyclic 1D vertex partition over P = 2^k <= 8 ranks: vertex v is owned by rank v mod P and is row
- * v / P of that rank's CSR (column ids stay global).  Bitmaps are indexed rank-major:
- * bit(v) = (v mod P) * n_local + v / P, so a rank's slice is contiguous and ncclAllGather of the
- * slices rebuilds the whole bitmap.  One process drives one GPU; between the calls below the host
+ * Swizzled-cyclic 1D vertex partition over P = 2^k <= 8 ranks (include/b200/partition.cuh): vertex v is
+ * row v >> k of its owner's CSR (column ids stay global) and owner(v) = (v & (P-1)) ^ swizzle(v >> k),
+ * swizzle(r) = top k bits of (r * 0x9E3779B1 mod 2^32) -- plain cyclic ownership gives rank 0 of 8
+ * 44 % of an un-permuted RMAT graph's arcs, the swizzle is within 0.2 % of m/P.  Bitmaps are indexed
+ * rank-major: bit(v) = owner(v) * n_local + (v >> k), so a rank's slice is contiguous and an all-gather
+ * of the slices rebuilds the whole bitmap.  One process drives one GPU; between the calls below the host
  * layer issues the NCCL collectives (alltoall of counts + alltoallv of vertex ids after a push
  * level, allgather of frontier-bitmap slices before a pull level). */
+/* The partition map itself (host arithmetic, no GPU): owner / local row of v, and the inverse. */
+int b200_partition_locate(int num_ranks, int64_t v, int32_t *owner, int64_t *row);
+int b200_partition_global_id(int num_ranks, int32_t rank, int64_t row, int64_t *v);
 typedef struct b200_mg_bfs_state {
     int32_t rank, num_ranks;
     int64_t n_global, n_local;        /* n_local = n_global / P, a multiple of 32 */

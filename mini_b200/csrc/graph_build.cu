@@ -5,6 +5,7 @@
 // the GPU and with offsets that can hold 2^31 arcs.  Not on the timed hot path:
 // uses cub::DeviceRadixSort (CUDA toolkit library) for the (src,dst) sort.
 #include <cub/device/device_radix_sort.cuh>
+#include "b200/partition.cuh"
 #include "engine.cuh"
 #include "rmat.cuh"
 
@@ -63,7 +64,7 @@ __global__ void keys_to_csr_kernel(const unsigned long long *keys, unsigned long
     }
 }
 
-// Cyclic 1D partition: keep the arcs whose tail is owned by `rank` (owner(v) = v & (P-1));
+// Swizzled-cyclic 1D partition (b200::Partition, advance.cuh): keep the arcs whose tail is owned by `rank`;
 // key = (local row << 32) | global column.  count_only => just count them.
 __global__ void rmat_part_keys_kernel(uint64_t key, int scale, unsigned long long npairs, uint32_t pmask, uint32_t log_p,
                                       uint32_t rank, unsigned long long *keys, unsigned long long *counter, int count_only) {
@@ -71,13 +72,14 @@ __global__ void rmat_part_keys_kernel(uint64_t key, int scale, unsigned long lon
     const unsigned long long rounds = (npairs + stride - 1) / stride;
     unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long local = 0;
+    const b200::Partition part{log_p, rank, 0u};
     for (unsigned long long r = 0; r < rounds; ++r, e += stride) {
         uint32_t u = 0, v = 0;
         bool fu = false, fv = false;
         if (e < npairs) {
             rmat_pair(key, e, scale, u, v);
-            fu = (u & pmask) == rank;   // arc u -> v lives here
-            fv = (v & pmask) == rank;   // arc v -> u lives here
+            fu = part.owner(u) == rank;   // arc u -> v lives here
+            fv = part.owner(v) == rank;   // arc v -> u lives here
         }
         if (count_only) {
             local += (fu ? 1 : 0) + (fv ? 1 : 0);

@@ -31,11 +31,11 @@ __global__ void mg_list_to_slice_kernel(const int32_t *list, uint32_t len, uint3
     }
 }
 
-struct SlicePred {   // bit r of the slice set -> emit global id r * P + me
+struct SlicePred {   // bit r of the slice set -> emit the global id of local row r
     const uint32_t *slice;
     Partition part;
     __device__ __forceinline__ bool operator()(uint32_t idx, int &item) const {
-        item = (int)((idx << part.log_p) | part.me);
+        item = (int)part.global_id(part.me, idx);
         return (slice[idx >> 5] >> (idx & 31)) & 1u;
     }
 };
@@ -56,6 +56,26 @@ Partition part_of(const b200_mg_bfs_state *s) {
 }  // namespace
 
 extern "C" {
+
+int b200_partition_locate(int num_ranks, int64_t v, int32_t *owner, int64_t *row) {
+    if (num_ranks < 1 || num_ranks > MAX_DEST || (num_ranks & (num_ranks - 1)) || v < 0 || v >= (1ll << 32)) return B200_ERR_INVALID;
+    uint32_t log_p = 0;
+    while ((1 << log_p) < num_ranks) ++log_p;
+    const Partition part{log_p, 0u, 0u};
+    if (owner) *owner = (int32_t)part.owner((uint32_t)v);
+    if (row) *row = (int64_t)part.row((uint32_t)v);
+    return B200_OK;
+}
+
+int b200_partition_global_id(int num_ranks, int32_t rank, int64_t row, int64_t *v) {
+    if (num_ranks < 1 || num_ranks > MAX_DEST || (num_ranks & (num_ranks - 1)) || rank < 0 || rank >= num_ranks || !v) return B200_ERR_INVALID;
+    uint32_t log_p = 0;
+    while ((1 << log_p) < num_ranks) ++log_p;
+    if (row < 0 || row >= (1ll << (32 - log_p))) return B200_ERR_INVALID;
+    const Partition part{log_p, 0u, 0u};
+    *v = (int64_t)part.global_id((uint32_t)rank, (uint32_t)row);
+    return B200_OK;
+}
 
 int b200_mg_bfs_init(b200_ctx *ctx, const b200_mg_bfs_state *s, int32_t src, int32_t *d_frontier, int64_t *frontier_len) {
     if (!ctx || !valid_state(s) || !d_frontier || !frontier_len || src < 0 || src >= s->n_global) return B200_ERR_INVALID;

@@ -232,11 +232,11 @@ __global__ void __launch_bounds__(256) p2p_gather_or_kernel(Peers peers, size_t 
     }
 }
 
-struct SliceListPred {   // bit r of the slice set -> emit global id r * P + me
+struct SliceListPred {   // bit r of the slice set -> emit the global id of local row r
     const uint32_t *slice;
     Partition part;
     __device__ __forceinline__ bool operator()(uint32_t idx, int &item) const {
-        item = (int)((idx << part.log_p) | part.me);
+        item = (int)part.global_id(part.me, idx);
         return (slice[idx >> 5] >> (idx & 31)) & 1u;
     }
 };

@@ -20,6 +20,8 @@ import ctypes as C
 import threading
 from typing import List, Optional, Sequence
 
+from . import partition as PT
+
 PUSH, PULL = 0, 1
 
 
@@ -323,8 +325,9 @@ def verify_bfs_properties(rank_backend, comm, src: int):
     off = r.g.row_offsets.to(torch.int64) & 0xFFFFFFFF
     deg = off[1:] - off[:-1]
     ok = True
-    if src % world == me:
-        ok &= int(r.labels[src // world].item()) == 0
+    log_p = PT.log2_ranks(world)
+    if int(PT.owner(src, world)) == me:
+        ok &= int(r.labels[src >> log_p].item()) == 0
     has_parent = torch.zeros(r.n_local, dtype=torch.bool, device=full.device)
     step = 1 << 22                                           # rows per chunk: bounds the temporaries
     for lo in range(0, r.n_local, step):
@@ -335,7 +338,9 @@ def verify_bfs_properties(rank_backend, comm, src: int):
         rows = torch.repeat_interleave(torch.arange(lo, hi, device=full.device), deg[lo:hi])
         cols = r.g.col_indices[a:b].long()
         lv = r.labels[rows]
-        lu = full[(cols % world) * r.n_local + cols // world]
+        crow = cols >> log_p                                  # b200::Partition::bit on the device
+        cown = (cols & (world - 1)) ^ ((((crow * PT.GOLDEN) & 0xFFFFFFFF) >> (32 - log_p)) if log_p else 0)
+        lu = full[cown * r.n_local + crow]
         ok &= bool(((lv >= 0) == (lu >= 0)).all())
         reached = lv >= 0
         if bool(reached.any()):

@@ -100,6 +100,8 @@ def load_library():
         "b200_bfs_run": ([vp, pg, i32, i32, f32, f32, vp, ps], i32),
         "b200_sssp_run": ([vp, pg, i32, vp, vp, ps], i32),
         "b200_pr_run": ([vp, pg, i32, i32, vp, vp, pi64, pi32, ps], i32),
+        "b200_partition_locate": ([i32, i64, pi32, pi64], i32),
+        "b200_partition_global_id": ([i32, i32, i64, pi64], i32),
         "b200_rmat_part_count": ([vp, i32, i32, u64, i32, i32, pi64], i32),
         "b200_rmat_build_csr_part": ([vp, i32, i32, u64, i32, i32, i64, vp, vp], i32),
         "b200_mg_bfs_init": ([vp, vp, i32, vp, pi64], i32),

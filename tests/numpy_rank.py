@@ -1,15 +1,18 @@
 """NumPy stand-in for mini_b200.dist.GpuRank (TEST INFRASTRUCTURE, CPU only): implements the per-rank
-steps of the partitioned BFS with the same partition rules (owner = v mod P, row = v // P, rank-major
-bitmaps) so the host-side control flow and the exchange protocol of DistBFS can run on gloo."""
+steps of the partitioned BFS with the same partition rules (mini_b200.partition: swizzled-cyclic owner, row = v >> log P,
+rank-major bitmaps) so the host-side control flow and the exchange protocol of DistBFS can run on gloo."""
 import numpy as np
 import torch
+
+from mini_b200 import partition as PT
 
 
 class NumpyRank:
     def __init__(self, csr, rank, world):
         self.rank, self.world = rank, world
         self.n, self.n_local = csr.n, csr.n // world
-        rows = np.arange(rank, csr.n, world)
+        rows = PT.global_ids(rank, world, csr.n // world)     # global id of every local row
+        self.gid = rows
         self.off = np.concatenate([[0], np.cumsum(csr.offsets[rows + 1] - csr.offsets[rows])])
         self.idx = np.concatenate([csr.indices[csr.offsets[v]:csr.offsets[v + 1]] for v in rows]) if len(rows) else np.zeros(0, np.int32)
         self.labels = np.full(self.n_local, -1, np.int32)
@@ -23,14 +26,20 @@ class NumpyRank:
 
     def bit(self, v):
         v = np.asarray(v, np.int64)
-        return (v % self.world) * self.n_local + v // self.world
+        return PT.bit(v, self.world, self.n_local).astype(np.int64)
+
+    def owner(self, v):
+        return int(PT.owner(int(v), self.world))
+
+    def row(self, v):
+        return int(v) >> PT.log2_ranks(self.world)
 
     def init(self, src):
         self.labels[:] = -1
         self.known[:] = False
         self.known[self.bit(src)] = True
-        if src % self.world == self.rank:
-            self.labels[src // self.world] = 0
+        if self.owner(src) == self.rank:
+            self.labels[self.row(src)] = 0
             self.frontier = np.array([src], np.int32)
             return 1
         self.frontier = np.zeros(0, np.int32)
@@ -40,17 +49,17 @@ class NumpyRank:
         boxes = [[] for _ in range(self.world)]
         arcs = deg = 0
         for v in self.frontier[:flen]:
-            r = v // self.world
+            r = self.row(v)
             for u in self.idx[self.off[r]:self.off[r + 1]]:
                 arcs += 1
                 b = self.bit(u)
                 if not self.known[b]:
                     self.known[b] = True
-                    p = u % self.world
+                    p = self.owner(u)
                     boxes[p].append(u)
                     if p == self.rank:
-                        self.labels[u // self.world] = level + 1
-                        deg += self.off[u // self.world + 1] - self.off[u // self.world]
+                        self.labels[self.row(u)] = level + 1
+                        deg += self.off[self.row(u) + 1] - self.off[self.row(u)]
         self.next = boxes[self.rank]
         self.boxes = [torch.tensor(b, dtype=torch.int32) for b in boxes]
         return [len(b) for b in boxes], arcs, int(deg)
@@ -74,9 +83,9 @@ class NumpyRank:
             b = self.bit(u)
             if not self.known[b]:
                 self.known[b] = True
-                self.labels[u // self.world] = level + 1
+                self.labels[self.row(u)] = level + 1
                 self.next.append(u)
-                deg += self.off[u // self.world + 1] - self.off[u // self.world]
+                deg += self.off[self.row(u) + 1] - self.off[self.row(u)]
         return len(self.next), int(deg)
 
     def swap(self):
@@ -84,7 +93,7 @@ class NumpyRank:
 
     def list_to_slice(self, flen):
         s = np.zeros(self.n_local, np.uint8)
-        s[self.frontier[:flen] // self.world] = 1
+        s[np.asarray(self.frontier[:flen], np.int64) >> PT.log2_ranks(self.world)] = 1
         self.next_slice = torch.from_numpy(s)
 
     def gather_buffers(self):
@@ -114,6 +123,6 @@ class NumpyRank:
 
     def slice_to_list(self):
         rows = np.flatnonzero(self.next_slice.numpy())
-        self.frontier = (rows * self.world + self.rank).astype(np.int32)
+        self.frontier = self.gid[rows].astype(np.int32)
         self.next = list(self.frontier)
         return len(rows)

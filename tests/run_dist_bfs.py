@@ -19,6 +19,7 @@ import torch
 import torch.distributed as dist
 
 import oracle
+from mini_b200 import partition as PT
 from mini_b200 import dist as D
 
 dist.init_process_group(a.backend)
@@ -51,7 +52,7 @@ else:
 if rank == 0:
     full = np.empty(n, np.int32)
     for r in range(world):
-        full[r::world] = gathered[r].numpy()
+        full[PT.global_ids(r, world, n // world)] = gathered[r].numpy()
     ref = oracle.bfs(o, a.src)
     assert np.array_equal(full, ref), "labels differ from the oracle"
     dirs = "".join("P" if l["direction"] == "pull" else "p" for l in bfs.levels)

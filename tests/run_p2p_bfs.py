@@ -20,6 +20,7 @@ import torch.distributed as dist
 
 import mini_b200 as mb
 import oracle
+from mini_b200 import partition as PT
 from mini_b200 import dist as D
 from mini_b200.p2p import P2PBfs
 
@@ -39,7 +40,7 @@ dist.all_gather(gl, bfs.labels)
 if rank == 0:
     full = np.empty(n, np.int32)
     for r in range(world):
-        full[r::world] = gl[r].cpu().numpy()
+        full[PT.global_ids(r, world, n // world)] = gl[r].cpu().numpy()
     o = oracle.rmat_csr(a.scale, ef, 1)
     ref = oracle.bfs(o, a.src)
     assert np.array_equal(full, ref), "labels differ from the oracle"

@@ -1,6 +1,6 @@
 """Partitioned (multi-GPU) BFS.
  * On ONE GPU: P virtual ranks run as threads over ThreadComm, exercising the partition-aware kernels
-   (cyclic owner mapping, rank-major bitmaps, in-kernel routing, absorb, partitioned pull) bit-exactly
+   (swizzled-cyclic owner mapping, rank-major bitmaps, in-kernel routing, absorb, partitioned pull) bit-exactly
    against the CPU oracle.
  * With >= 2 GPUs (gpurun --gpus N): the same driver over NCCL (tests/run_dist_bfs.py under torchrun)."""
 import os
@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 import oracle
+from mini_b200 import partition as PT
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
@@ -57,8 +58,8 @@ def test_partitioned_bfs_virtual_ranks(world, mode):
     n = 1 << scale
     labels = np.empty(n, np.int32)
     for r, (lab, off, idx, levels, stats) in enumerate(res):
-        labels[r::world] = lab                       # vertex v = row * P + rank
-        rows = np.arange(r, n, world)
+        rows = PT.global_ids(r, world, n // world)   # global id of every local row (swizzled-cyclic partition)
+        labels[rows] = lab
         # the rank's CSR is exactly its rows of the global CSR
         assert np.array_equal(np.diff(off), (o.offsets[rows + 1] - o.offsets[rows]))
         k = min(len(rows), 50)
@@ -81,7 +82,7 @@ def test_partitioned_bfs_other_sources(src):
     res = _virtual_ranks(scale, ef, seed, world, src, "beamer")
     labels = np.empty(1 << scale, np.int32)
     for r in range(world):
-        labels[r::world] = res[r][0]
+        labels[PT.global_ids(r, world, (1 << scale) // world)] = res[r][0]
     assert np.array_equal(labels, ref)
 
 
@@ -133,7 +134,7 @@ def test_p2p_bfs_virtual_ranks(world, mode):
     res = _virtual_ranks_p2p(scale, ef, seed, world, src, mode)
     labels = np.empty(1 << scale, np.int32)
     for r in range(world):
-        labels[r::world] = res[r][0]
+        labels[PT.global_ids(r, world, (1 << scale) // world)] = res[r][0]
     assert np.array_equal(labels, ref)
     stats = res[0][2]
     assert all(res[r][2] == stats or [dict(l, level_ms=0) for l in res[r][2]] == [dict(l, level_ms=0) for l in stats]
@@ -152,7 +153,7 @@ def test_p2p_bfs_other_sources(src):
     res = _virtual_ranks_p2p(scale, ef, seed, world, src, "beamer")
     labels = np.empty(1 << scale, np.int32)
     for r in range(world):
-        labels[r::world] = res[r][0]
+        labels[PT.global_ids(r, world, (1 << scale) // world)] = res[r][0]
     assert np.array_equal(labels, ref)
 
 
