@@ -92,6 +92,93 @@ def push_level_bytes(level, offset_bytes=4):
     return level["frontier_len"] * (4 + 2 * offset_bytes) + level["arcs"] * 8 + level["discovered"] * 8
 
 
+def sssp_level_bytes(level, offset_bytes=4):
+    """SURVEY.md 8d, SSSP advance: |F|(4+2*O+4) + m_l*(4 idx + 4 weight + 4 label) + improved*(4+4)."""
+    return level["frontier_len"] * (8 + 2 * offset_bytes) + level["arcs"] * 12 + level["discovered"] * 8
+
+
+def reduce_level_bytes(level, offset_bytes=4):
+    """SURVEY.md 8d, neighborhood_reduce fp32: |F|(4+2*O) + m_F*(4 idx + 4 gather) + |F|*4."""
+    return level["frontier_len"] * (4 + 2 * offset_bytes) + level["arcs"] * 8 + level["frontier_len"] * 4
+
+
+def _per_level(ctx_call, reps, bytes_fn, peak):
+    """Runs ctx_call(timing=True) reps times; per-level advance_ms averaged; roofline of the heaviest launch."""
+    lv, lv_ms = None, None
+    for _ in range(reps):
+        st = ctx_call()
+        if lv_ms is None:
+            lv, lv_ms = st.levels, [0.0] * len(st.levels)
+        for i, l in enumerate(st.levels):
+            lv_ms[i] += l["advance_ms"] / reps
+    top = max(range(len(lv)), key=lambda i: lv[i]["arcs"])
+    b = bytes_fn(lv[top])
+    gbs = b / (lv_ms[top] * 1e-3) / 1e9
+    tot_b, tot_ms = sum(bytes_fn(l) for l in lv), sum(lv_ms)
+    return {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+            "algorithmic_bytes_per_launch": b, "launch_ms": lv_ms[top], "arcs_per_launch": lv[top]["arcs"],
+            "all_launches": {"achieved": tot_b / (tot_ms * 1e-3) / 1e9, "frac": tot_b / (tot_ms * 1e-3) / 1e9 / peak,
+                             "kernel_ms_sum": tot_ms, "launches": len(lv)}}
+
+
+def run_sssp_leg(ctx, mb, args, peak):
+    """BASELINE.json configs[2]: SSSP, idempotent LB advance, RMAT scale-22 ef16, integer weights 1..64 (fp32)."""
+    import torch
+    scale = args.scale or 22
+    g = ctx.rmat_graph(scale, 16, 1, weighted=True)
+    dist = torch.empty(g.n, dtype=torch.float32, device=ctx.torch_device)
+    steps = max(3, min(args.steps, 20))
+    for _ in range(3):
+        ctx.sssp(g, 0, dist=dist)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    e0.record()
+    for _ in range(steps):
+        _, st = ctx.sssp(g, 0, dist=dist)
+        launches += st.launches
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    off = g.row_offsets.to(torch.int64) & 0xFFFFFFFF
+    reached_arcs = int((off[1:] - off[:-1])[dist < 3.0e38].sum().item())
+    roof = _per_level(lambda: ctx.sssp(g, 0, dist=dist, timing=True)[1], 5, sssp_level_bytes, peak)
+    roof["kernel"] = "quad_advance_kernel<SsspRelaxQ,COMPACT> (heaviest iteration)"
+    return {"workload": f"SSSP from vertex 0, RMAT scale-{scale} ef16 symmetrised, uniform integer weights [1,64] "
+                        "as fp32, idempotent LB advance (Bellman-Ford frontier iterations)",
+            "value": reached_arcs / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "iterations": st.num_levels, "relaxed_arcs": st.total_arcs, "reached_arcs": reached_arcs,
+            "gpu_launches": launches, "roofline": roof}
+
+
+def run_reduce_leg(ctx, mb, args, peak):
+    """BASELINE.json configs[4]: neighborhood_reduce PageRank-style fp32 pull-sum over dynamic frontiers,
+    RMAT scale-24 ef16, max_iter 10 (pr_enactor.hxx:41-79)."""
+    import torch
+    scale = args.reduce_scale
+    g = ctx.rmat_graph(scale, 16, 1)
+    for _ in range(2):
+        ctx.pr(g, 10, False)
+    torch.cuda.synchronize()
+    steps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launches = 0
+    for _ in range(steps):
+        _, _, lens, st = ctx.pr(g, 10, False)
+        launches += st.launches
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    roof = _per_level(lambda: ctx.pr(g, 10, False, timing=True)[3], 3, reduce_level_bytes, peak)
+    roof["kernel"] = "neighborhood reduce kernel, fp32 plus (heaviest iteration: frontier = all vertices)"
+    return {"workload": f"PageRank-style neighborhood_reduce fp32 pull-sum, RMAT scale-{scale} ef16 symmetrised "
+                        f"(n={g.n}, m={g.m}), 10 iterations over the filter's dynamic frontiers",
+            "value": st.total_arcs / (ms * 1e-3) / 1e9, "unit": "G arcs reduced/s", "ms_per_step": ms, "steps": steps,
+            "iterations": st.num_levels, "frontier_lens": lens, "reduced_arcs": st.total_arcs,
+            "gpu_launches": launches, "roofline": roof}
+
+
 def cpu_bfs_baseline(off64, idx, runs):
     """The reference's CPU validation BFS (bfs_problem.hxx:52-72) on this box's host cores:
     the unmodified reference code if oracle/_ref was built, else the oracle port."""
@@ -242,18 +329,31 @@ def run_single_gpu(args):
     else:
         parity, cpu = None, None
 
+    # ---- the other single-GPU configurations of BASELINE.json (own graphs; the BFS graph is released first)
+    gn, gm = g.n, g.m
+    del g, labels
+    torch.cuda.empty_cache()
+    extras = {}
+    if "sssp" in args.extras:
+        extras["sssp"] = run_sssp_leg(ctx, mb, args, peak)
+        torch.cuda.empty_cache()
+    if "reduce" in args.extras:
+        extras["neighborhood_reduce"] = run_reduce_leg(ctx, mb, args, peak)
+        torch.cuda.empty_cache()
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": f"BFS from vertex 0, RMAT scale-{scale} ef16 symmetrised (n={g.n}, m={g.m}), "
+        "config": {"workload": f"BFS from vertex 0, RMAT scale-{scale} ef16 symmetrised (n={gn}, m={gm}), "
                                f"{args.mode} (LB advance + fused uniquify filter)",
                    "teps_numerator": "sum of deg(v) over reached v", "reached_arcs": reached_arcs,
-                   "l2": "inputs larger than L2 (col_indices alone is %d MiB vs 126 MB L2)" % (g.m * 4 >> 20),
+                   "l2": "inputs larger than L2 (col_indices alone is %d MiB vs 126 MB L2)" % (gm * 4 >> 20),
                    "parallelism": "1 GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "parity": {"bfs_labels_bit_exact_vs_cpu": parity},
     }
+    line.update(extras)
     print(json.dumps(line))
     ctx.close()
     return 0 if parity in (True, None) else 1
@@ -270,6 +370,9 @@ def main():
     ap.add_argument("--cpu-runs", type=int, default=3)
     ap.add_argument("--advance", default="quad", choices=["quad", "lbs"],
                     help="push-advance kernel: quad_advance.cuh (default) or the first-generation advance.cuh")
+    ap.add_argument("--extras", default="sssp,reduce",
+                    help="N=1: extra legs after the BFS line: sssp (configs[2]) and/or reduce (configs[4]); '' = none")
+    ap.add_argument("--reduce-scale", dest="reduce_scale", type=int, default=24)
     ap.add_argument("--mg-mode", dest="mg_mode", default="beamer", choices=["push", "beamer"])
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1 frontier exchange: fused into the kernels over NVLink peer memory, or NCCL collectives")

@@ -9,6 +9,7 @@
 #include <cstring>
 #include "advance.cuh"
 #include "quad_advance.cuh"
+#include "quad_segreduce.cuh"
 #include "segreduce.cuh"
 #include "tile_scan.cuh"
 #include "workspace.h"
@@ -210,6 +211,31 @@ cudaError_t launch_lbs_segreduce(b200_workspace *ws, const LbsArgs &a, ValueFn v
     auto k = lbs_segreduce_kernel<Value, ROp, ValueFn, LBS_NT, LBS_VT, LBS_SEG_T>;
     const int grid = persistent_grid<SegTag<Value, ROp, ValueFn>>(k, LBS_NT, ws);
     k<<<grid, LBS_NT, 0, ws_stream(ws)>>>(a, vf, d_reduced, scatter);
+    ws->launches++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// quad neighbourhood reduce (quad_segreduce.cuh)
+// ---------------------------------------------------------------------------
+constexpr int QSEG_NT = B200_QSEG_NT, QSEG_VT = B200_QSEG_VT, QSEG_WSEG = B200_QSEG_WSEG;
+
+// quad scan of the frontier (+ row bounds into ws->d_rows, reduced[] preset), Q into counters[TOTAL].
+template <class Value>
+cudaError_t launch_neighborhood_quad_scan(b200_workspace *ws, const int *d_frontier, uint32_t len, const uint32_t *offsets,
+                                          Value *d_reduced, Value identity, Value neutral, int scatter) {
+    if ((int64_t)len > ws->scanned_capacity) return cudaErrorInvalidValue;
+    NeighborhoodQuads<Value> fn{d_frontier, offsets, reinterpret_cast<uint2 *>(ws->d_rows), d_reduced, identity, neutral, scatter};
+    return launch_scan(ws, fn, len, ws->d_scanned, ws->d_counters + B200_CNT_TOTAL);
+}
+
+// Reduce over a frontier whose neighbourhood quad scan is already in the workspace; the number of
+// arcs reduced is left in counters[B200_CNT_ARCS].
+template <class Value, class ROp, class ValueFn>
+cudaError_t launch_quad_segreduce(b200_workspace *ws, const QuadArgs &a, ValueFn vf, Value *d_reduced, int scatter) {
+    auto k = quad_segreduce_kernel<Value, ROp, ValueFn, QSEG_NT, QSEG_VT, QSEG_WSEG>;
+    const int grid = persistent_grid<SegTag<Value, ROp, ValueFn>>(k, QSEG_NT, ws);
+    k<<<grid, QSEG_NT, 0, ws_stream(ws)>>>(a, vf, d_reduced, scatter, ws->d_counters);
     ws->launches++;
     return cudaGetLastError();
 }

@@ -360,18 +360,28 @@ int b200_neighborhood_reduce_f32(b200_ctx *ctx, const b200_graph *g, const int32
     const int32_t *idx = push ? g->col_indices : (g->row_indices ? g->row_indices : g->col_indices);
     B200_CUDA(reset_counters(ws));
     const float neutral = op == B200_OP_PLUS ? PlusF32::neutral() : (op == B200_OP_MIN ? MinF32::neutral() : MaxF32::neutral());
-    NeighborhoodDegree<float> deg{d_in, off, d_reduced, identity, neutral, scatter};
-    B200_CUDA(launch_scan(ws, deg, (uint32_t)in_len, ws->d_scanned, ws->d_counters + B200_CNT_TOTAL));
-    const LbsArgs a = make_lbs_args(ws, d_in, (uint32_t)in_len, off, idx);
     FiniteValueFn vf{d_values};
     cudaError_t e;
-    if (op == B200_OP_PLUS) e = launch_lbs_segreduce<float, PlusF32>(ws, a, vf, d_reduced, scatter);
-    else if (op == B200_OP_MIN) e = launch_lbs_segreduce<float, MinF32>(ws, a, vf, d_reduced, scatter);
-    else if (op == B200_OP_MAX) e = launch_lbs_segreduce<float, MaxF32>(ws, a, vf, d_reduced, scatter);
-    else return B200_ERR_INVALID;
+    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(idx);
+    if (quad) {
+        B200_CUDA(launch_neighborhood_quad_scan<float>(ws, d_in, (uint32_t)in_len, off, d_reduced, identity, neutral, scatter));
+        const QuadArgs a = make_quad_args(ws, d_in, (uint32_t)in_len, off, idx, nullptr);
+        if (op == B200_OP_PLUS) e = launch_quad_segreduce<float, PlusF32>(ws, a, vf, d_reduced, scatter);
+        else if (op == B200_OP_MIN) e = launch_quad_segreduce<float, MinF32>(ws, a, vf, d_reduced, scatter);
+        else if (op == B200_OP_MAX) e = launch_quad_segreduce<float, MaxF32>(ws, a, vf, d_reduced, scatter);
+        else return B200_ERR_INVALID;
+    } else {
+        NeighborhoodDegree<float> deg{d_in, off, d_reduced, identity, neutral, scatter};
+        B200_CUDA(launch_scan(ws, deg, (uint32_t)in_len, ws->d_scanned, ws->d_counters + B200_CNT_TOTAL));
+        const LbsArgs a = make_lbs_args(ws, d_in, (uint32_t)in_len, off, idx);
+        if (op == B200_OP_PLUS) e = launch_lbs_segreduce<float, PlusF32>(ws, a, vf, d_reduced, scatter);
+        else if (op == B200_OP_MIN) e = launch_lbs_segreduce<float, MinF32>(ws, a, vf, d_reduced, scatter);
+        else if (op == B200_OP_MAX) e = launch_lbs_segreduce<float, MaxF32>(ws, a, vf, d_reduced, scatter);
+        else return B200_ERR_INVALID;
+    }
     B200_CUDA(e);
     B200_CUDA(read_counters(ws));
-    if (arcs) *arcs = (int64_t)ws->h_counters[B200_CNT_TOTAL];
+    if (arcs) *arcs = (int64_t)ws->h_counters[quad ? B200_CNT_ARCS : B200_CNT_TOTAL];
     return B200_OK;
 }
 
@@ -614,23 +624,31 @@ int b200_pr_run(b200_ctx *ctx, const b200_graph *g, int max_iter, int scatter, f
     B200_CUDA(cudaGetLastError());
     int sel = 0, it = 0;
     int64_t flen = n, total_arcs = 0;
+    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(idx);
     while (flen > 0 && it < max_iter) {
         b200_level_stat *ls = (stats && it < B200_MAX_LEVELS) ? &stats->level[it] : nullptr;
         const bool tl = timing && it < B200_MAX_LEVELS;
         if (tl && it == 0) B200_CUDA(cudaEventRecord(ev[0], st));
         B200_CUDA(reset_counters(ws));
-        NeighborhoodDegree<float> deg{ctx->frontier[sel], off, d_reduced, 0.0f, 0.0f, scatter};
-        B200_CUDA(launch_scan(ws, deg, (uint32_t)flen, ws->d_scanned, ws->d_counters + B200_CNT_TOTAL));
-        const LbsArgs a = make_lbs_args(ws, ctx->frontier[sel], (uint32_t)flen, off, idx);
-        if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 1], st));
-        B200_CUDA((launch_lbs_segreduce<float, PlusF32>(ws, a, FiniteValueFn{d_current}, d_reduced, scatter)));
+        if (quad) {
+            B200_CUDA(launch_neighborhood_quad_scan<float>(ws, ctx->frontier[sel], (uint32_t)flen, off, d_reduced, 0.0f, 0.0f, scatter));
+            const QuadArgs a = make_quad_args(ws, ctx->frontier[sel], (uint32_t)flen, off, idx, nullptr);
+            if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 1], st));
+            B200_CUDA((launch_quad_segreduce<float, PlusF32>(ws, a, FiniteValueFn{d_current}, d_reduced, scatter)));
+        } else {
+            NeighborhoodDegree<float> deg{ctx->frontier[sel], off, d_reduced, 0.0f, 0.0f, scatter};
+            B200_CUDA(launch_scan(ws, deg, (uint32_t)flen, ws->d_scanned, ws->d_counters + B200_CNT_TOTAL));
+            const LbsArgs a = make_lbs_args(ws, ctx->frontier[sel], (uint32_t)flen, off, idx);
+            if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 1], st));
+            B200_CUDA((launch_lbs_segreduce<float, PlusF32>(ws, a, FiniteValueFn{d_current}, d_reduced, scatter)));
+        }
         if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 2], st));
         B200_CUDA(launch_compact(ws, PrFilterPred{ctx->frontier[sel], d_current, d_reduced, nullptr, g->row_offsets},
                                  (uint32_t)flen, ctx->frontier[sel ^ 1], (unsigned long long)n,
                                  ws->d_counters + B200_CNT_OUT, ws->d_counters + B200_CNT_OVERFLOW));
         B200_CUDA(read_counters(ws));
         const int64_t out = (int64_t)ws->h_counters[B200_CNT_OUT];
-        const int64_t arcs = (int64_t)ws->h_counters[B200_CNT_TOTAL];
+        const int64_t arcs = (int64_t)ws->h_counters[quad ? B200_CNT_ARCS : B200_CNT_TOTAL];
         if (ls) {
             ls->direction = 1;
             ls->frontier_len = flen;
