@@ -239,6 +239,7 @@ def run_single_gpu(args):
     torch.cuda.set_device(dev)
     ctx = mb.Context(dev)
     ctx.set_advance_impl(mb.ADVANCE_LBS if args.advance == "lbs" else mb.ADVANCE_QUAD)
+    ctx.set_level_loop(mb.LOOP_HOST if args.loop == "host" else mb.LOOP_GRAPH)
     g = ctx.rmat_graph(scale, 16, 1)
     mode = {"push": mb.BFS_PUSH, "beamer": mb.BFS_BEAMER}[args.mode]
     sampler = ClockSampler(dev)
@@ -258,6 +259,7 @@ def run_single_gpu(args):
     e1.record()
     torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
+    loop_used = st.level_loop
     reached_arcs = g.degrees_sum_reached(labels)
     value = reached_arcs * args.steps / (ms_total * 1e-3) / 1e9
 
@@ -349,6 +351,9 @@ def run_single_gpu(args):
                                f"{args.mode} (LB advance + fused uniquify filter)",
                    "teps_numerator": "sum of deg(v) over reached v", "reached_arcs": reached_arcs,
                    "l2": "inputs larger than L2 (col_indices alone is %d MiB vs 126 MB L2)" % (gm * 4 >> 20),
+                   "level_loop": loop_used + (" (one CUDA graph per BFS: WHILE/IF/SWITCH conditional nodes set by a "
+                                                  "device-side decide kernel; one host sync per BFS)"
+                                                  if loop_used == "graph" else " (one counter read-back per level)"),
                    "parallelism": "1 GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "parity": {"bfs_labels_bit_exact_vs_cpu": parity},
@@ -370,6 +375,8 @@ def main():
     ap.add_argument("--cpu-runs", type=int, default=3)
     ap.add_argument("--advance", default="quad", choices=["quad", "lbs"],
                     help="push-advance kernel: quad_advance.cuh (default) or the first-generation advance.cuh")
+    ap.add_argument("--loop", default="graph", choices=["graph", "host"],
+                    help="N=1 BFS level loop: one CUDA graph with device-side decisions, or host-driven")
     ap.add_argument("--extras", default="sssp,reduce",
                     help="N=1: extra legs after the BFS line: sssp (configs[2]) and/or reduce (configs[4]); '' = none")
     ap.add_argument("--reduce-scale", dest="reduce_scale", type=int, default=24)

@@ -13,6 +13,7 @@
 //   bool probe (src, dst, edge_id)                       side-effect free, may over-approximate
 //   bool commit(src, dst, edge_id, rank, out_idx)        atomics / writes; true => emit dst
 #pragma once
+#include "loop_dyn.cuh"
 #include "device_utils.cuh"
 #include "lbs.cuh"
 #include "workspace.h"
@@ -324,12 +325,12 @@ static __global__ void bitmap_or_kernel(uint32_t *__restrict__ dst, const uint32
 // is the whole (all-gathered) frontier bitmap, `next_bm` / `visited_bm` point at this rank's
 // slice of the next-frontier / known bitmaps, labels are local.
 template <int NT>
-__global__ void __launch_bounds__(NT) bfs_pull_kernel(uint32_t n, const uint32_t *__restrict__ offsets,
-                                                      const int *__restrict__ indices,
-                                                      const uint32_t *__restrict__ frontier_bm,
-                                                      uint32_t *__restrict__ next_bm, uint32_t *__restrict__ visited_bm,
-                                                      int *__restrict__ labels, int next_label,
-                                                      unsigned long long *counters, Partition part) {
+__device__ __forceinline__ void bfs_pull_body(uint32_t n, const uint32_t *__restrict__ offsets,
+                                              const int *__restrict__ indices,
+                                              const uint32_t *__restrict__ frontier_bm,
+                                              uint32_t *__restrict__ next_bm, uint32_t *__restrict__ visited_bm,
+                                              int *__restrict__ labels, int next_label,
+                                              unsigned long long *counters, Partition part) {
     const uint32_t num_words = (n + 31) >> 5;
     const uint32_t warps_total = (gridDim.x * NT) >> 5;
     const unsigned lane = lane_id();
@@ -375,6 +376,39 @@ __global__ void __launch_bounds__(NT) bfs_pull_kernel(uint32_t n, const uint32_t
         for (int w = 0; w < NT / 32; ++w) s += red[threadIdx.x][w];
         const int slot = threadIdx.x == 0 ? B200_CNT_OUT : (threadIdx.x == 1 ? B200_CNT_ARCS : B200_CNT_AUX);
         if (s) atomicAdd(&counters[slot], s);
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) bfs_pull_kernel(uint32_t n, const uint32_t *__restrict__ offsets,
+                                                      const int *__restrict__ indices,
+                                                      const uint32_t *__restrict__ frontier_bm,
+                                                      uint32_t *__restrict__ next_bm, uint32_t *__restrict__ visited_bm,
+                                                      int *__restrict__ labels, int next_label,
+                                                      unsigned long long *counters, Partition part) {
+    bfs_pull_body<NT>(n, offsets, indices, frontier_bm, next_bm, visited_bm, labels, next_label, counters, part);
+}
+
+// Graph-driven level loop form: which bitmap is the frontier and the label come from the device (loop_dyn.cuh).
+template <int NT>
+__global__ void __launch_bounds__(NT) bfs_pull_dyn_kernel(uint32_t n, const uint32_t *__restrict__ offsets,
+                                                          const int *__restrict__ indices, uint32_t *bm0, uint32_t *bm1,
+                                                          uint32_t *__restrict__ visited_bm, int *__restrict__ labels,
+                                                          const LoopDyn *dyn, unsigned long long *counters, Partition part) {
+    if (!(dyn->run & LOOP_RUN_PULL)) return;
+    const uint32_t bsel = dyn->bsel;
+    bfs_pull_body<NT>(n, offsets, indices, bsel ? bm1 : bm0, bsel ? bm0 : bm1, visited_bm, labels, dyn->next_label,
+                      counters, part);
+}
+
+// frontier list -> bitmap (dynamic list and length; bitmap pre-cleared)
+static __global__ void sparse_to_bitmap_dyn_kernel(const LoopDyn *dyn, uint32_t *bitmap) {
+    if (!(dyn->run & LOOP_RUN_TO_PULL)) return;
+    const int *__restrict__ sparse = dyn->in;
+    const uint32_t len = dyn->len;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
+        const int v = sparse[i];
+        if (v >= 0) atomicOr(bitmap + (v >> 5), 1u << (v & 31));
     }
 }
 

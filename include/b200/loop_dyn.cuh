@@ -1,0 +1,30 @@
+// loop_dyn.cuh -- device-resident launch arguments of the graph-driven level loop.
+//
+// The reference's enactors branch on a count read back from the device after every operator
+// (bfs_enactor.hxx:54-115: two blocking read-backs and ~10 launches per level).  Here the whole
+// traversal can be ONE CUDA graph whose WHILE / IF conditional nodes are steered from the device
+// (level_loop.cu), so the arguments that change from level to level -- which ping-pong buffer is
+// the frontier, its length, the label to write, the look-back tag of the scan -- live in this
+// struct in device memory instead of in kernel parameters.  Kernels take a nullable pointer to
+// it; NULL means "use the by-value arguments" (the host-driven loop and the operator API).
+#pragma once
+#include <stdint.h>
+
+namespace b200 {
+
+struct LoopDyn {
+    const int *in;       // current frontier list
+    int *out;            // next frontier list
+    uint32_t len;        // |in|
+    uint32_t epoch;      // look-back tag of this level's scan (the bitmap -> list compaction uses epoch + 1)
+    int next_label;      // level + 1
+    uint32_t bsel;       // pull levels: which of the two frontier bitmaps is current
+    uint32_t run;        // LOOP_RUN_* bits: which kernels of the loop body have work (the others return at once)
+};
+
+// IF / SWITCH conditional nodes cost ~7 / ~4 us each on a B200 (profiles/microbench/graph_cond.cu) against
+// ~1.1 us for a kernel that returns immediately, so the loop body is a flat kernel sequence and every
+// kernel checks its bit.
+enum : uint32_t { LOOP_RUN_PUSH = 1u, LOOP_RUN_PULL = 2u, LOOP_RUN_TO_PULL = 4u, LOOP_RUN_TO_PUSH = 8u };
+
+}  // namespace b200

@@ -171,6 +171,7 @@ inline QuadArgs make_quad_args(const b200_workspace *ws, const int *d_frontier, 
     a.weights4 = reinterpret_cast<const float4 *>(weights);
     a.min_chunk = QUAD_MIN_CHUNK;
     a.row_shift = row_shift;
+    a.dyn = nullptr;
     return a;
 }
 

@@ -36,6 +36,7 @@
 //   int      finish(token, cand)                    vertex to emit, or -1
 #pragma once
 #include "advance.cuh"
+#include "loop_dyn.cuh"
 
 namespace b200 {
 
@@ -50,6 +51,7 @@ struct QuadArgs {
     const float4 *weights4;            // col_values viewed as aligned quads (weighted ops only)
     uint32_t min_chunk;                // lower bound on the work items per warp
     uint32_t row_shift;                // cyclic 1D partition: row of v is v >> row_shift
+    const LoopDyn *dyn;                // graph-driven level loop: frontier / num_segments / out come from here (else NULL)
 };
 
 // quads(v): number of aligned 16-byte quads of col_indices that row v touches.  Also leaves
@@ -105,6 +107,12 @@ quad_advance_kernel(QuadArgs a, Op op, int *__restrict__ out, unsigned long long
     __shared__ unsigned long long s_sum[2];
 
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5, lt_mask = lanemask_lt();
+    if (a.dyn) {                             // level arguments decided on the device (loop_dyn.cuh)
+        if (!(a.dyn->run & LOOP_RUN_PUSH)) return;
+        a.frontier = a.dyn->in;
+        a.num_segments = a.dyn->len;
+        out = a.dyn->out;
+    }
     const unsigned long long Q = *a.total;
     if (threadIdx.x < 2) s_sum[threadIdx.x] = 0;
     __syncthreads();
@@ -420,6 +428,16 @@ struct BfsPushQ {
     __device__ __forceinline__ int finish(Token old, const Cand &c) const {
         if ((old >> (c.w[0] & 31)) & 1u) return -1;
         labels[c.w[0]] = next_label;
+        return (int)c.w[0];
+    }
+};
+
+// BfsPushQ whose label comes from the device-resident level state (graph-driven loop).
+struct BfsPushQDyn : BfsPushQ {
+    const LoopDyn *dyn;
+    __device__ __forceinline__ int finish(Token old, const Cand &c) const {
+        if ((old >> (c.w[0] & 31)) & 1u) return -1;
+        labels[c.w[0]] = dyn->next_label;
         return (int)c.w[0];
     }
 };

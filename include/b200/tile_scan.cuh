@@ -11,6 +11,7 @@
 // reads and writes of consecutive lanes are consecutive addresses.
 #pragma once
 #include "device_utils.cuh"
+#include "loop_dyn.cuh"
 
 namespace b200 {
 
@@ -175,6 +176,111 @@ __global__ void __launch_bounds__(NT) compact_kernel(Pred pred, uint32_t count, 
     }
     if (over) *overflow_flag = 1ull;
     if (tile == st.num_tiles - 1 && threadIdx.x == 0) *total_out = (unsigned long long)excl + total;
+}
+
+// ---------------------------------------------------------------------------
+// Graph-driven level loop forms (loop_dyn.cuh): the item count and the look-back tag are read
+// from device memory, so the grid cannot be sized by the count -- a fixed persistent grid claims
+// tiles from the dynamic counter until they run out (predecessors of a claimed tile are always
+// resident, so the look-back cannot deadlock).  The counter is zeroed by the level's decide kernel.
+// ---------------------------------------------------------------------------
+template <int NT, int VT, class SizeFn>
+__global__ void __launch_bounds__(NT) scan_sizes_dyn_kernel(SizeFn fn, const LoopDyn *dyn, uint32_t run_bit,
+                                                            uint32_t *__restrict__ out, unsigned long long *status,
+                                                            unsigned int *tile_counter, unsigned long long *total_out) {
+    using TS = TileScan<NT, VT>;
+    __shared__ typename TS::Smem sm;
+    __shared__ uint32_t s_tile, s_bcast;
+    if (!(dyn->run & run_bit)) return;
+    const uint32_t count = dyn->len;
+    LookbackState st;
+    st.status = status;
+    st.tile_counter = tile_counter;
+    st.epoch = dyn->epoch;
+    st.num_tiles = (count + TS::NV - 1) / TS::NV;
+    if (count == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *total_out = 0ull;
+        return;
+    }
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= st.num_tiles) break;
+        const uint32_t base = tile * TS::NV + (threadIdx.x >> 5) * (32 * VT) + lane_id();
+        uint32_t v[VT], ex[VT];
+#pragma unroll
+        for (int i = 0; i < VT; ++i) {
+            const uint32_t idx = base + i * 32;
+            v[i] = idx < count ? fn(idx) : 0u;
+        }
+        const uint32_t total = TS::run(v, ex, sm);
+        const uint32_t excl = lookback_exclusive(st, tile, total, &s_bcast);
+#pragma unroll
+        for (int i = 0; i < VT; ++i) {
+            const uint32_t idx = base + i * 32;
+            if (idx < count) out[idx] = excl + ex[i];
+        }
+        if (tile == st.num_tiles - 1 && threadIdx.x == 0) *total_out = (unsigned long long)excl + total;
+        __syncthreads();   // s_tile, s_bcast and the scan scratch are reused by the next tile
+    }
+}
+
+// Stable compaction of idx in [0,count) into the list dyn->in (the frontier the next push level reads).
+// clear_words (nullable): a bitmap of count bits that is zeroed word by word once the word's 32 indices
+// have been tested (a warp's lanes hold exactly one word per item row).
+template <int NT, int VT, class Pred>
+__global__ void __launch_bounds__(NT) compact_dyn_kernel(Pred pred, uint32_t count, const LoopDyn *dyn, uint32_t run_bit,
+                                                         unsigned long long capacity, unsigned long long *status,
+                                                         unsigned int *tile_counter, unsigned long long *total_out,
+                                                         unsigned long long *overflow_flag, uint32_t *clear_words) {
+    using TS = TileScan<NT, VT>;
+    __shared__ typename TS::Smem sm;
+    __shared__ uint32_t s_tile, s_bcast;
+    if (!(dyn->run & run_bit)) return;
+    int *out = const_cast<int *>(dyn->in);
+    LookbackState st;
+    st.status = status;
+    st.tile_counter = tile_counter;
+    st.epoch = (dyn->epoch + 1u) & 0x3FFFFFFFu;
+    st.num_tiles = (count + TS::NV - 1) / TS::NV;
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= st.num_tiles) break;
+        const uint32_t base = tile * TS::NV + (threadIdx.x >> 5) * (32 * VT) + lane_id();
+        uint32_t v[VT], ex[VT];
+        int item[VT];
+#pragma unroll
+        for (int i = 0; i < VT; ++i) {
+            const uint32_t idx = base + i * 32;
+            item[i] = -1;
+            v[i] = (idx < count && pred(idx, item[i])) ? 1u : 0u;
+        }
+        if (clear_words) {
+            __syncwarp();
+            if (lane_id() == 0) {
+#pragma unroll
+                for (int i = 0; i < VT; ++i)
+                    if (base + i * 32 < count) clear_words[(base + i * 32) >> 5] = 0u;
+            }
+        }
+        const uint32_t total = TS::run(v, ex, sm);
+        const uint32_t excl = lookback_exclusive(st, tile, total, &s_bcast);
+        bool over = false;
+#pragma unroll
+        for (int i = 0; i < VT; ++i) {
+            if (v[i]) {
+                const unsigned long long dest = (unsigned long long)excl + ex[i];
+                if (dest < capacity) out[dest] = item[i];
+                else over = true;
+            }
+        }
+        if (over) *overflow_flag = 1ull;
+        if (tile == st.num_tiles - 1 && threadIdx.x == 0) *total_out = (unsigned long long)excl + total;
+        __syncthreads();
+    }
 }
 
 }  // namespace b200

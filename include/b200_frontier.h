@@ -104,7 +104,7 @@ typedef struct b200_stats {
     int64_t total_arcs;     /* out: sum of `arcs` over levels */
     int64_t launches;       /* out: kernels launched by this call */
     float device_ms;        /* out: device time source-in-frontier -> labels final */
-    float reserved;
+    int32_t level_loop;     /* out: B200_LOOP_GRAPH or B200_LOOP_HOST -- which level loop produced this run */
     b200_level_stat level[B200_MAX_LEVELS];
 } b200_stats;
 
@@ -135,6 +135,16 @@ int b200_ctx_l2_pin(b200_ctx *ctx, const void *d_ptr, int64_t bytes);
  *     taken automatically for B200_ADV_RAW_OUTPUT and for arrays that are not 16-byte aligned. */
 enum { B200_ADVANCE_QUAD = 0, B200_ADVANCE_LBS = 1 };
 int b200_ctx_set_advance_impl(b200_ctx *ctx, int impl);
+
+/* Who drives the level loop of b200_bfs_run (the role of the host loop in bfs_enactor_t::enact_pushpull,
+ * bfs_enactor.hxx:54-115, which reads a count back from the device after every operator):
+ *   B200_LOOP_GRAPH (default): the whole traversal is one CUDA graph; WHILE / IF / SWITCH conditional nodes are
+ *     set by a device-side decide kernel that applies the same push / pull / stop rules, so the host
+ *     synchronises once per traversal (mini_b200/csrc/level_loop.cu).  Taken when the quad advance is
+ *     usable and no per-level timing is requested; b200_stats.level_loop reports what ran;
+ *   B200_LOOP_HOST: one counter read-back and host decision per level (also the timing path). */
+enum { B200_LOOP_GRAPH = 0, B200_LOOP_HOST = 1 };
+int b200_ctx_set_level_loop(b200_ctx *ctx, int impl);
 
 /* ---- synthetic input (the reference has only load_graph, graph.hxx:96-223) */
 /* Symmetrised RMAT(0.57,0.19,0.19,0.05): n = 2^scale, m = 2*edge_factor*2^scale arcs,

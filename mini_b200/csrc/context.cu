@@ -10,6 +10,7 @@ namespace b200 {
 thread_local int g_last_cuda_error = 0;
 
 static void free_traversal_scratch(b200_ctx *ctx) {
+    level_loop_invalidate(ctx);
     for (int i = 0; i < 2; ++i) {
         if (ctx->frontier[i]) cudaFree(ctx->frontier[i]);
         if (ctx->bm_frontier[i]) cudaFree(ctx->bm_frontier[i]);
@@ -108,6 +109,7 @@ int b200_ctx_reserve(b200_ctx *ctx, int64_t max_items) {
     B200_CUDA(cudaSetDevice(ws.device));
     // smallest tile any scan-type kernel uses is 1024 items
     const int64_t tiles = (max_items + 1023) / 1024 + 1;
+    if (tiles > ws.status_tiles || max_items > ws.scanned_capacity) level_loop_invalidate(ctx);
     if (tiles > ws.status_tiles) {
         B200_CUDA(cudaStreamSynchronize((cudaStream_t)ws.stream));
         if (ws.d_status) cudaFree(ws.d_status);
@@ -150,6 +152,12 @@ int b200_ctx_set_advance_impl(b200_ctx *ctx, int impl) {
     return B200_OK;
 }
 
+int b200_ctx_set_level_loop(b200_ctx *ctx, int impl) {
+    if (!ctx || (impl != B200_LOOP_GRAPH && impl != B200_LOOP_HOST)) return B200_ERR_INVALID;
+    ctx->loop_impl = impl;
+    return B200_OK;
+}
+
 int b200_ctx_l2_pin(b200_ctx *ctx, const void *d_ptr, int64_t bytes) {
     if (!ctx || bytes < 0) return B200_ERR_INVALID;
     cudaStreamAttrValue attr;
@@ -183,6 +191,7 @@ int b200_ctx_destroy(b200_ctx *ctx) {
     cudaSetDevice(ctx->ws.device);
     cudaStreamSynchronize((cudaStream_t)ctx->ws.stream);
     if (ctx->l2_window_set) b200_ctx_l2_pin(ctx, nullptr, 0);
+    level_loop_destroy(ctx);
     free_traversal_scratch(ctx);
     if (ctx->ev_level) {
         for (int i = 0; i < ctx->ev_level_count; ++i) cudaEventDestroy(ctx->ev_level[i]);

@@ -397,6 +397,14 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
     cudaStream_t st = ws_stream(ws);
     const size_t words = (size_t)((n + 31) / 32);
     const bool timing = stats && stats->collect_timing;
+    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(g->col_indices);
+    if (alpha <= 0.f) alpha = 15.f;
+    if (beta <= 0.f) beta = 18.f;
+    if (quad && !timing && ctx->loop_impl == B200_LOOP_GRAPH) {
+        const int gs = bfs_run_graph(ctx, g, src, mode, alpha, beta, d_labels, stats);
+        if (gs != B200_ERR_UNSUPPORTED) return gs;   // unsupported: the graph could not be built, run the host loop
+    }
+    if (stats) stats->level_loop = B200_LOOP_HOST;
     cudaEvent_t *ev = timing ? level_events(ctx) : nullptr;
     const int64_t launches0 = ws->launches;
     const uint32_t *pull_off = g->col_offsets ? g->col_offsets : g->row_offsets;
@@ -411,12 +419,9 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
     B200_CUDA(cudaGetLastError());
 
     int sel = 0, bsel = 0, level = 0;
-    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(g->col_indices);
     int64_t flen = 1, unvisited = n - 1, reached = 1, total_arcs = 0;
     int64_t m_unexplored = g->m;
     bool pull = false;
-    if (alpha <= 0.f) alpha = 15.f;
-    if (beta <= 0.f) beta = 18.f;
 
     for (;;) {
         b200_level_stat *ls = (stats && level < B200_MAX_LEVELS) ? &stats->level[level] : nullptr;

@@ -5,6 +5,8 @@
 #include "b200/workspace.h"
 #include "b200_frontier.h"
 
+namespace b200 { struct LevelLoop; }
+
 struct b200_ctx {
     b200_workspace ws;
     bool own_stream;
@@ -21,6 +23,8 @@ struct b200_ctx {
     // L2 persistence
     bool l2_window_set;
     int adv_impl;              // B200_ADVANCE_QUAD | B200_ADVANCE_LBS
+    int loop_impl;             // B200_LOOP_GRAPH | B200_LOOP_HOST
+    b200::LevelLoop *loop;     // graph-driven level loop (level_loop.cu), created on first use
 };
 
 struct b200_host_graph {
@@ -57,5 +61,11 @@ inline int cuda_status(cudaError_t e) {
     } while (0)
 
 int ensure_traversal_scratch(b200_ctx *ctx, int64_t n);
+
+// level_loop.cu
+int bfs_run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, float alpha, float beta, int32_t *d_labels,
+                  b200_stats *stats);
+void level_loop_invalidate(b200_ctx *ctx);
+void level_loop_destroy(b200_ctx *ctx);
 
 }  // namespace b200

@@ -1,0 +1,456 @@
+// level_loop.cu -- the whole BFS as ONE CUDA graph whose level loop is steered from the device.
+//
+// bfs_enactor_t::enact_pushpull (bfs_enactor.hxx:41-117) returns to the host after every operator:
+// two blocking read-backs and ~10 launches per level.  The host-driven loop of engine.cu already cut
+// that to one read-back per level, but on a B200 a BFS level of a scale-22 graph is 10-200 us of
+// kernel time, so the ~35 us round trip (D2H copy + stream sync + relaunch) was a third of the
+// traversal.  Here the traversal is a graph
+//
+//     memset labels / visited / bitmap 0 -> init -> WHILE(run) { quad scan; quad advance; pull; decide;
+//                                                                list -> bitmap; bitmap -> list }
+//
+// built once per (graph, labels buffer, mode) and replayed by one cudaGraphLaunch: the `decide`
+// kernel reads the level's counters on the device, applies exactly the host loop's push / pull / stop
+// rules, flips the ping-pong buffers in the device-resident LoopDyn (loop_dyn.cuh), re-arms the
+// counters, sets the WHILE handle and the LOOP_RUN_* bits that tell each kernel of the flat body
+// whether it has work this level.  (First version: IF/ELSE around push | pull and a SWITCH around the
+// transitions -- measured 7 and 4 us per conditional node per level on a B200 against 1.1 us for a
+// kernel that returns at once, profiles/microbench/graph_cond.cu, so the body is flat now.)
+// Per-level statistics and the result land in mapped pinned memory; the host synchronises once.
+// Invariant: frontier bitmap 0 is all-zero during push levels (prologue memset; the bitmap -> list
+// compaction clears it again), so the list -> bitmap transition is a plain scatter.
+#include <cstring>
+#include <new>
+#include "b200/operators.cuh"
+#include "engine.cuh"
+
+using namespace b200;
+
+namespace b200 {
+
+struct LoopParams {      // mapped pinned: run parameters, read by the init kernel (not baked into the graph)
+    int32_t src, mode;
+    float alpha, beta;
+    long long m;
+    uint32_t epoch0, pad;
+};
+
+struct LoopLevelRec {
+    int32_t direction, pad;
+    long long frontier_len, arcs, discovered;
+};
+
+struct LoopResult {      // mapped pinned: written by the decide kernel
+    int32_t status, num_levels;
+    long long reached, total_arcs, launches;
+    LoopLevelRec level[B200_MAX_LEVELS];
+};
+
+struct LoopState {       // device
+    LoopDyn dyn;
+    int32_t level, pull, mode, pad;
+    float alpha, beta;
+    long long n, m_unexplored, unvisited, reached, total_arcs, flen, launches;
+};
+
+struct LevelLoop {
+    LoopState *d_state;
+    LoopParams *h_params, *d_params;
+    LoopResult *h_result, *d_result;
+    cudaStream_t cap_stream;
+    // one cached graph (rebuilt when the key changes)
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    const void *k_offsets, *k_indices, *k_labels, *k_scratch;
+    int64_t k_n;
+    int k_mode;
+    int failed;          // status of the last failed build (the caller falls back to the host loop)
+};
+
+}  // namespace b200
+
+namespace {
+
+constexpr int DYN_SCAN_CTAS_PER_SM = 4;
+
+struct FrontierQuadsDyn {   // FrontierQuads over the device-selected frontier list
+    const LoopDyn *dyn;
+    const uint32_t *offsets;
+    uint2 *rows;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
+        const int v = dyn->in[i];
+        uint32_t b = 0, e = 0;
+        if (v >= 0) {
+            b = __ldg(offsets + v);
+            e = __ldg(offsets + v + 1);
+        }
+        rows[i] = make_uint2(b, e);
+        return e > b ? ((e - 1) >> 2) - (b >> 2) + 1u : 0u;
+    }
+};
+
+struct BitmapPredDyn {      // bit idx of the device-selected frontier bitmap
+    const LoopDyn *dyn;
+    const uint32_t *bm0, *bm1;
+    __device__ __forceinline__ bool operator()(uint32_t idx, int &item) const {
+        const uint32_t *bm = dyn->bsel ? bm1 : bm0;
+        item = (int)idx;
+        return (bm[idx >> 5] >> (idx & 31)) & 1u;
+    }
+};
+
+// bfs_problem_t ctor (bfs_problem.hxx:38-42) + init_frontier (bfs_enactor.hxx:34-38) + the loop state
+__global__ void loop_init_kernel(const LoopParams *p, LoopState *s, int32_t *labels, uint32_t *visited, int32_t *f0,
+                                 int32_t *f1, long long n, unsigned long long *counters, unsigned int *tile_counters) {
+    const int src = p->src;
+    labels[src] = 0;
+    visited[src >> 5] |= 1u << (src & 31);
+    f0[0] = src;
+    s->dyn.in = f0;
+    s->dyn.out = f1;
+    s->dyn.len = 1u;
+    s->dyn.epoch = p->epoch0 & 0x3FFFFFFFu;
+    s->dyn.next_label = 1;
+    s->dyn.bsel = 0u;
+    s->dyn.run = LOOP_RUN_PUSH;
+    s->level = 0;
+    s->pull = 0;
+    s->mode = p->mode;
+    s->alpha = p->alpha;
+    s->beta = p->beta;
+    s->n = n;
+    s->m_unexplored = p->m;
+    s->unvisited = n - 1;
+    s->reached = 1;
+    s->total_arcs = 0;
+    s->flen = 1;
+    s->launches = 1;
+    for (int i = 0; i < B200_NUM_COUNTERS; ++i) counters[i] = 0ull;
+    tile_counters[0] = 0u;
+    tile_counters[1] = 0u;
+}
+
+// The host loop's per-level bookkeeping (engine.cu b200_bfs_run), on the device.
+__global__ void loop_decide_kernel(LoopState *s, unsigned long long *counters, unsigned int *tile_counters, LoopResult *res,
+                                   cudaGraphConditionalHandle h_while) {
+    const long long found = (long long)counters[B200_CNT_OUT], arcs = (long long)counters[B200_CNT_ARCS];
+    const long long next_deg = (long long)counters[B200_CNT_AUX];
+    const bool overflow = counters[B200_CNT_OVERFLOW] != 0ull;
+    const bool was_pull = s->pull != 0;
+    bool pull = was_pull;
+    int level = s->level;
+    if (level < B200_MAX_LEVELS) {
+        LoopLevelRec *r = &res->level[level];
+        r->direction = was_pull ? 1 : 0;
+        r->frontier_len = was_pull ? s->unvisited : s->flen;
+        r->arcs = arcs;
+        r->discovered = found;
+    }
+    s->total_arcs += arcs;
+    s->launches += s->mode == B200_BFS_PUSH ? 3 : 6;   // kernel nodes of the flat body (some return at once)
+    ++level;
+    s->level = level;
+    bool done = false;
+    uint32_t trans = 0u;
+    int status = B200_OK;
+    if (overflow) {
+        status = B200_ERR_OVERFLOW;
+        done = true;
+    } else if (found == 0) {
+        done = true;
+    } else {
+        const long long flen = s->flen, n = s->n;
+        s->reached += found;
+        s->unvisited -= found;
+        if (!was_pull) {
+            s->m_unexplored -= arcs;
+            const int *t = s->dyn.in;
+            s->dyn.in = s->dyn.out;
+            s->dyn.out = const_cast<int *>(t);
+            if (s->mode == B200_BFS_REF_ALPHA) {
+                if ((float)s->unvisited < (float)found * s->alpha) pull = true;   // bfs_enactor.hxx:68
+            } else if (s->mode == B200_BFS_BEAMER) {
+                if ((double)next_deg > (double)s->m_unexplored / s->alpha && found > flen) pull = true;
+            }
+        } else {
+            s->dyn.bsel ^= 1u;
+            if (s->mode == B200_BFS_BEAMER && (double)found < (double)n / s->beta && found < flen) pull = false;
+        }
+        s->flen = found;
+        s->dyn.len = (uint32_t)found;
+        if (pull && !was_pull) {
+            trans = LOOP_RUN_TO_PULL;   // sparse_to_dense_kernel (advance.hxx:69-84) into bitmap 0
+            s->dyn.bsel = 0u;
+        } else if (!pull && was_pull) {
+            trans = LOOP_RUN_TO_PUSH;   // bitmap -> list for the push levels that finish the traversal
+        }
+    }
+    s->pull = pull ? 1 : 0;
+    s->dyn.next_label = level + 1;
+    s->dyn.epoch = (s->dyn.epoch + 2u) & 0x3FFFFFFFu;
+    for (int i = 0; i < B200_NUM_COUNTERS; ++i) counters[i] = 0ull;
+    tile_counters[0] = 0u;
+    tile_counters[1] = 0u;
+    if (done) {
+        res->status = status;
+        res->num_levels = level;
+        res->reached = s->reached;
+        res->total_arcs = s->total_arcs;
+        res->launches = s->launches;
+        __threadfence_system();
+    }
+    s->dyn.run = done ? 0u : ((pull ? LOOP_RUN_PULL : LOOP_RUN_PUSH) | trans);
+    cudaGraphSetConditional(h_while, done ? 0u : 1u);
+}
+
+#define LL_CUDA(call)                                          \
+    do {                                                       \
+        cudaError_t _e = (call);                               \
+        if (_e != cudaSuccess) {                               \
+            st = ::b200::cuda_status(_e);                      \
+            goto fail;                                         \
+        }                                                      \
+    } while (0)
+
+// Ends a capture into `graph` and returns the nodes the next node of `graph` must depend on.
+int end_capture(cudaStream_t cs, cudaGraphNode_t *deps, size_t *ndeps, size_t max_deps) {
+    cudaStreamCaptureStatus cst;
+    const cudaGraphNode_t *d = nullptr;
+    size_t nd = 0;
+    cudaError_t e = cudaStreamGetCaptureInfo(cs, &cst, nullptr, nullptr, &d, &nd);
+    if (e == cudaSuccess && nd > max_deps) e = cudaErrorInvalidValue;
+    if (e == cudaSuccess) {
+        for (size_t i = 0; i < nd; ++i) deps[i] = d[i];
+        *ndeps = nd;
+    }
+    cudaGraph_t same = nullptr;
+    cudaError_t e2 = cudaStreamEndCapture(cs, &same);
+    if (e != cudaSuccess) return ::b200::cuda_status(e);
+    if (e2 != cudaSuccess) return ::b200::cuda_status(e2);
+    return B200_OK;
+}
+
+void drop_graph(LevelLoop *L) {
+    if (L->exec) cudaGraphExecDestroy(L->exec);
+    if (L->graph) cudaGraphDestroy(L->graph);
+    L->exec = nullptr;
+    L->graph = nullptr;
+    L->k_offsets = L->k_indices = L->k_labels = L->k_scratch = nullptr;
+}
+
+int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode) {
+    LevelLoop *L = ctx->loop;
+    b200_workspace *ws = &ctx->ws;
+    const int64_t n = g->n;
+    const size_t words = (size_t)((n + 31) / 32);
+    const bool deg = mode == B200_BFS_BEAMER;
+    const uint32_t *pull_off = g->col_offsets ? g->col_offsets : g->row_offsets;
+    const int32_t *pull_idx = g->row_indices ? g->row_indices : g->col_indices;
+    cudaStream_t cs = L->cap_stream;
+    void *const user_stream = ws->stream;
+    const int64_t launches0 = ws->launches;
+    int st = B200_OK;
+    bool capturing = false;
+    cudaGraph_t G = nullptr, body = nullptr;
+    cudaGraphConditionalHandle h_while;
+    cudaGraphNode_t deps[8], n_while;
+    size_t ndeps = 0;
+    cudaGraphNodeParams np_w = {};
+    const LoopDyn *dyn = &L->d_state->dyn;
+
+    drop_graph(L);
+    ws->stream = (void *)cs;   // the launchers below record into the capture stream
+    LL_CUDA(cudaGraphCreate(&G, 0));
+    LL_CUDA(cudaGraphConditionalHandleCreate(&h_while, G, 1, cudaGraphCondAssignDefault));
+
+    // ---- prologue
+    LL_CUDA(cudaStreamBeginCaptureToGraph(cs, G, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    capturing = true;
+    LL_CUDA(cudaMemsetAsync(d_labels, 0xFF, sizeof(int32_t) * (size_t)n, cs));
+    LL_CUDA(cudaMemsetAsync(ctx->bm_visited, 0, sizeof(uint32_t) * words, cs));
+    if (mode != B200_BFS_PUSH) LL_CUDA(cudaMemsetAsync(ctx->bm_frontier[0], 0, sizeof(uint32_t) * words, cs));
+    loop_init_kernel<<<1, 1, 0, cs>>>(L->d_params, L->d_state, d_labels, ctx->bm_visited, ctx->frontier[0], ctx->frontier[1],
+                                      (long long)n, ws->d_counters, ws->d_tile_counter);
+    LL_CUDA(cudaGetLastError());
+    capturing = false;
+    if ((st = end_capture(cs, deps, &ndeps, 8)) != B200_OK) goto fail;
+
+    // ---- WHILE(run)
+    np_w.type = cudaGraphNodeTypeConditional;
+    np_w.conditional.handle = h_while;
+    np_w.conditional.type = cudaGraphCondTypeWhile;
+    np_w.conditional.size = 1;
+    LL_CUDA(cudaGraphAddNode(&n_while, G, deps, ndeps, &np_w));
+    body = np_w.conditional.phGraph_out[0];
+
+    // ---- the flat body: every kernel returns at once unless its LOOP_RUN_* bit is set
+    LL_CUDA(cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    capturing = true;
+    {
+        // push level: quad scan + quad advance (fused uniquify filter)
+        const int64_t max_tiles = (n + SCAN_NT * SCAN_VT - 1) / (SCAN_NT * SCAN_VT);
+        int64_t grid = (int64_t)ws->num_sms * DYN_SCAN_CTAS_PER_SM;
+        if (grid > max_tiles) grid = max_tiles;
+        FrontierQuadsDyn fn{dyn, g->row_offsets, reinterpret_cast<uint2 *>(ws->d_rows)};
+        scan_sizes_dyn_kernel<SCAN_NT, SCAN_VT><<<(unsigned)grid, SCAN_NT, 0, cs>>>(
+            fn, dyn, (uint32_t)LOOP_RUN_PUSH, ws->d_scanned, ws->d_status, ws->d_tile_counter, ws->d_counters + B200_CNT_TOTAL);
+        LL_CUDA(cudaGetLastError());
+        QuadArgs a = make_quad_args(ws, ctx->frontier[0], 0u, g->row_offsets, g->col_indices, nullptr);
+        a.dyn = dyn;
+        BfsPushQDyn op{{ctx->bm_visited, d_labels, 0}, dyn};
+        if (deg) LL_CUDA((launch_quad_advance<OUT_COMPACT, true>(ws, a, op, ctx->frontier[1], (unsigned long long)n)));
+        else LL_CUDA((launch_quad_advance<OUT_COMPACT, false>(ws, a, op, ctx->frontier[1], (unsigned long long)n)));
+    }
+    if (mode != B200_BFS_PUSH) {
+        // pull level
+        bfs_pull_dyn_kernel<256><<<ws->num_sms * 8, 256, 0, cs>>>((uint32_t)n, pull_off, pull_idx, ctx->bm_frontier[0],
+                                                                  ctx->bm_frontier[1], ctx->bm_visited, d_labels, dyn,
+                                                                  ws->d_counters, Partition{0, 0, (uint32_t)n});
+        LL_CUDA(cudaGetLastError());
+    }
+    loop_decide_kernel<<<1, 1, 0, cs>>>(L->d_state, ws->d_counters, ws->d_tile_counter, L->d_result, h_while);
+    LL_CUDA(cudaGetLastError());
+    if (mode != B200_BFS_PUSH) {
+        // transitions: list -> bitmap 0 (all-zero by invariant) | bitmap -> list (+ clears bitmap 0)
+        sparse_to_bitmap_dyn_kernel<<<ws->num_sms * 4, 256, 0, cs>>>(dyn, ctx->bm_frontier[0]);
+        LL_CUDA(cudaGetLastError());
+        const int64_t max_tiles = (n + COMPACT_NT * COMPACT_VT - 1) / (COMPACT_NT * COMPACT_VT);
+        int64_t grid = (int64_t)ws->num_sms * DYN_SCAN_CTAS_PER_SM;
+        if (grid > max_tiles) grid = max_tiles;
+        BitmapPredDyn pred{dyn, ctx->bm_frontier[0], ctx->bm_frontier[1]};
+        compact_dyn_kernel<COMPACT_NT, COMPACT_VT><<<(unsigned)grid, COMPACT_NT, 0, cs>>>(
+            pred, (uint32_t)n, dyn, (uint32_t)LOOP_RUN_TO_PUSH, (unsigned long long)n, ws->d_status, ws->d_tile_counter + 1,
+            ws->d_counters + B200_CNT_AUX2, ws->d_counters + B200_CNT_OVERFLOW, ctx->bm_frontier[0]);
+        LL_CUDA(cudaGetLastError());
+    }
+    capturing = false;
+    if ((st = end_capture(cs, deps, &ndeps, 8)) != B200_OK) goto fail;
+
+    LL_CUDA(cudaGraphInstantiate(&L->exec, G, 0));
+    L->graph = G;
+    L->k_offsets = g->row_offsets;
+    L->k_indices = g->col_indices;
+    L->k_labels = d_labels;
+    L->k_scratch = ctx->frontier[0];
+    L->k_n = n;
+    L->k_mode = mode;
+    ws->stream = user_stream;
+    ws->launches = launches0;
+    return B200_OK;
+
+fail:
+    if (capturing) {
+        cudaGraph_t junk = nullptr;
+        cudaStreamEndCapture(cs, &junk);
+    }
+    (void)cudaGetLastError();
+    if (G) cudaGraphDestroy(G);
+    ws->stream = user_stream;
+    ws->launches = launches0;
+    return st;
+}
+
+}  // namespace
+
+namespace b200 {
+
+void level_loop_destroy(b200_ctx *ctx) {
+    LevelLoop *L = ctx->loop;
+    if (!L) return;
+    drop_graph(L);
+    if (L->cap_stream) cudaStreamDestroy(L->cap_stream);
+    if (L->d_state) cudaFree(L->d_state);
+    if (L->h_params) cudaFreeHost(L->h_params);
+    if (L->h_result) cudaFreeHost(L->h_result);
+    delete L;
+    ctx->loop = nullptr;
+}
+
+// The traversal scratch was reallocated: a cached graph holds dangling pointers.
+void level_loop_invalidate(b200_ctx *ctx) {
+    if (ctx->loop) drop_graph(ctx->loop);
+}
+
+static int level_loop_get(b200_ctx *ctx) {
+    if (ctx->loop) return B200_OK;
+    LevelLoop *L = new (std::nothrow) LevelLoop;
+    if (!L) return B200_ERR_NOMEM;
+    std::memset(L, 0, sizeof *L);
+    ctx->loop = L;
+    B200_CUDA(cudaStreamCreateWithFlags(&L->cap_stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaMalloc(&L->d_state, sizeof(LoopState)));
+    B200_CUDA(cudaHostAlloc(&L->h_params, sizeof(LoopParams), cudaHostAllocMapped));
+    B200_CUDA(cudaHostAlloc(&L->h_result, sizeof(LoopResult), cudaHostAllocMapped));
+    B200_CUDA(cudaHostGetDevicePointer(&L->d_params, L->h_params, 0));
+    B200_CUDA(cudaHostGetDevicePointer(&L->d_result, L->h_result, 0));
+    return B200_OK;
+}
+
+// b200_bfs_run through the graph.  Returns B200_ERR_UNSUPPORTED when the graph cannot be built on this
+// driver (the caller then runs the host-driven loop and reports level_loop = host in the stats).
+int bfs_run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, float alpha, float beta, int32_t *d_labels,
+                  b200_stats *stats) {
+    B200_TRY(level_loop_get(ctx));
+    LevelLoop *L = ctx->loop;
+    b200_workspace *ws = &ctx->ws;
+    cudaStream_t st = ws_stream(ws);
+    if (L->failed) return B200_ERR_UNSUPPORTED;
+    if (!L->exec || L->k_offsets != g->row_offsets || L->k_indices != g->col_indices || L->k_labels != d_labels ||
+        L->k_scratch != ctx->frontier[0] || L->k_n != g->n || L->k_mode != mode) {
+        B200_CUDA(cudaStreamSynchronize(st));   // a replay of the old graph may still be running
+        const int bs = build_graph(ctx, g, d_labels, mode);
+        if (bs != B200_OK) {
+            L->failed = bs;
+            return B200_ERR_UNSUPPORTED;
+        }
+    }
+    // look-back tags: the device consumes two per level; keep the host's counter ahead of them
+    if (ws->epoch > 0x3FFFFFFFu - 4u * (B200_MAX_LEVELS + 2)) {
+        B200_CUDA(cudaMemsetAsync(ws->d_status, 0, sizeof(unsigned long long) * (size_t)ws->status_tiles, st));
+        ws->epoch = 0;
+    }
+    L->h_params->src = src;
+    L->h_params->mode = mode;
+    L->h_params->alpha = alpha;
+    L->h_params->beta = beta;
+    L->h_params->m = g->m;
+    L->h_params->epoch0 = ws->epoch + 1;
+    L->h_result->status = -1;
+    L->h_result->num_levels = 0;
+    B200_CUDA(cudaEventRecord(ctx->ev_run[0], st));
+    B200_CUDA(cudaGraphLaunch(L->exec, st));
+    B200_CUDA(cudaEventRecord(ctx->ev_run[1], st));
+    B200_CUDA(cudaEventSynchronize(ctx->ev_run[1]));
+    const LoopResult *r = L->h_result;
+    if (r->status < 0) return B200_ERR_CUDA;    // the graph ended without the decide kernel reporting
+    const int levels = r->num_levels;
+    const unsigned used = 2u * (unsigned)levels + 2u;
+    if (used > 0x3FFFFFFFu - ws->epoch - 2u) {  // a traversal with ~2^29 levels: retire every tag
+        B200_CUDA(cudaMemsetAsync(ws->d_status, 0, sizeof(unsigned long long) * (size_t)ws->status_tiles, st));
+        ws->epoch = 0;
+    } else {
+        ws->epoch += used;
+    }
+    ws->launches += r->launches;
+    if (stats) {
+        stats->num_levels = levels;
+        stats->reached = r->reached;
+        stats->total_arcs = r->total_arcs;
+        stats->launches = r->launches;
+        stats->level_loop = B200_LOOP_GRAPH;
+        B200_CUDA(cudaEventElapsedTime(&stats->device_ms, ctx->ev_run[0], ctx->ev_run[1]));
+        const int nl = levels < B200_MAX_LEVELS ? levels : B200_MAX_LEVELS;
+        for (int l = 0; l < nl; ++l) {
+            b200_level_stat *ls = &stats->level[l];
+            ls->direction = r->level[l].direction;
+            ls->frontier_len = r->level[l].frontier_len;
+            ls->arcs = r->level[l].arcs;
+            ls->discovered = r->level[l].discovered;
+            ls->advance_ms = 0.f;
+            ls->level_ms = 0.f;
+        }
+    }
+    return r->status;
+}
+
+}  // namespace b200

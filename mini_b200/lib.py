@@ -14,6 +14,7 @@ OP_PLUS, OP_MIN, OP_MAX = 0, 1, 2
 PROBLEM_BFS, PROBLEM_SSSP, PROBLEM_PR = 1, 2, 3
 MAX_LEVELS = 512
 ADVANCE_QUAD, ADVANCE_LBS = 0, 1
+LOOP_GRAPH, LOOP_HOST = 0, 1
 
 
 class B200Error(RuntimeError):
@@ -45,7 +46,7 @@ class CLevelStat(C.Structure):
 class CStats(C.Structure):
     _fields_ = [("collect_timing", C.c_int32), ("num_levels", C.c_int32), ("reached", C.c_int64),
                 ("total_arcs", C.c_int64), ("launches", C.c_int64), ("device_ms", C.c_float),
-                ("reserved", C.c_float), ("level", CLevelStat * MAX_LEVELS)]
+                ("level_loop", C.c_int32), ("level", CLevelStat * MAX_LEVELS)]
 
 
 _lib = None
@@ -85,6 +86,7 @@ def load_library():
         "b200_ctx_num_sms": ([vp, pi32], i32),
         "b200_ctx_l2_pin": ([vp, vp, i64], i32),
         "b200_ctx_set_advance_impl": ([vp, i32], i32),
+        "b200_ctx_set_level_loop": ([vp, i32], i32),
         "b200_ctx_workspace": ([vp], vp),
         "b200_rmat_build_csr": ([vp, i32, i32, u64, vp, vp, vp, u64], i32),
         "b200_rmat_pairs": ([vp, i32, i32, u64, vp, vp], i32),
@@ -149,6 +151,7 @@ class Stats:
         self.total_arcs = c.total_arcs
         self.launches = c.launches
         self.device_ms = c.device_ms
+        self.level_loop = "graph" if c.level_loop == LOOP_GRAPH else "host"
         self.levels = [
             dict(direction="pull" if l.direction else "push", frontier_len=l.frontier_len, arcs=l.arcs,
                  discovered=l.discovered, advance_ms=l.advance_ms, level_ms=l.level_ms)
@@ -223,6 +226,10 @@ class Context:
     def set_advance_impl(self, impl: int):
         """ADVANCE_QUAD (default) or ADVANCE_LBS: which kernel runs the push advance (same results)."""
         _check(self._L.b200_ctx_set_advance_impl(self._h, impl), "b200_ctx_set_advance_impl")
+
+    def set_level_loop(self, impl: int):
+        """LOOP_GRAPH (default: one CUDA graph per traversal, device-side decisions) or LOOP_HOST."""
+        _check(self._L.b200_ctx_set_level_loop(self._h, impl), "b200_ctx_set_level_loop")
 
     def l2_pin(self, tensor):
         if tensor is None:

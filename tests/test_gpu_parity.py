@@ -17,12 +17,15 @@ FIXTURES = ["ref_fixture_bfs.json", "ref_fixture_sssp_directed.json",
 FLT_MAX = np.finfo(np.float32).max
 
 
-@pytest.fixture(scope="module", params=["quad", "lbs"])
+@pytest.fixture(scope="module", params=["quad", "lbs", "quad-hostloop"])
 def ctx(request):
-    """Every parity test runs against both push-advance kernels (quad_advance.cuh / advance.cuh)."""
+    """Every parity test runs against both push-advance kernels (quad_advance.cuh / advance.cuh) and, for the
+    quad kernel, against both level loops (one CUDA graph per traversal / host-driven)."""
     import mini_b200
     c = mini_b200.Context(0)
-    c.set_advance_impl(mini_b200.ADVANCE_QUAD if request.param == "quad" else mini_b200.ADVANCE_LBS)
+    c.set_advance_impl(mini_b200.ADVANCE_LBS if request.param == "lbs" else mini_b200.ADVANCE_QUAD)
+    c.set_level_loop(mini_b200.LOOP_HOST if request.param == "quad-hostloop" else mini_b200.LOOP_GRAPH)
+    c.variant = request.param
     yield c
     c.close()
 
@@ -147,6 +150,39 @@ def test_bfs_edge_cases(ctx, mode):
     lab, st = _bfs(ctx, _dev_graph(ctx, path), 0, mode)
     assert np.array_equal(lab.cpu().numpy(), np.arange(p, dtype=np.int32))
     assert st.num_levels == p
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_graph_level_loop_is_used_and_matches_host_loop(mode):
+    """The graph-driven loop must really run (no silent host-loop fallback) and report the same per-level
+    statistics as the host-driven loop, for several sources and across buffer / graph changes (graph cache)."""
+    import mini_b200 as mb
+    c = mb.Context(0)
+    try:
+        graphs = [c.rmat_graph(14, 16, 1), c.rmat_graph(12, 8, 3), c.rmat_graph(14, 16, 1)]
+        for g in graphs:
+            for src in (0, 1, 77, g.n - 1):
+                c.set_level_loop(mb.LOOP_GRAPH)
+                la, sa = _bfs(c, g, src, mode)
+                assert sa.level_loop == "graph"
+                c.set_level_loop(mb.LOOP_HOST)
+                lb, sb = _bfs(c, g, src, mode)
+                assert sb.level_loop == "host"
+                assert torch.equal(la, lb)
+                assert (sa.num_levels, sa.reached, sa.total_arcs) == (sb.num_levels, sb.reached, sb.total_arcs)
+                key = lambda st: [(l["direction"], l["frontier_len"], l["arcs"], l["discovered"]) for l in st.levels]
+                assert key(sa) == key(sb)
+                assert sa.launches > 0
+        # a long path: many levels through the same graph replay (tags, ping-pong, counters re-armed every level)
+        n = 3000
+        o = oracle.build_csr(n, np.arange(n - 1, dtype=np.int32), np.arange(1, n, dtype=np.int32), True, False)
+        g = _dev_graph(c, o)
+        c.set_level_loop(mb.LOOP_GRAPH)
+        la, sa = _bfs(c, g, 0, mode)
+        assert sa.level_loop == "graph" and sa.num_levels == n
+        assert np.array_equal(la.cpu().numpy(), np.arange(n, dtype=np.int32))
+    finally:
+        c.close()
 
 
 def test_bfs_scale22_bit_exact_and_properties(ctx):
