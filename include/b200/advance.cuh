@@ -33,6 +33,7 @@ struct RoutedOut {
     unsigned long long capacity[MAX_DEST];
     unsigned long long *count;   // [MAX_DEST] device counters
     int num_dest;
+    int self;                    // graph-driven loop: box[self] is replaced by LoopDyn::out (the local next frontier)
 };
 
 // DEG_SUM: also accumulate sum(deg(u)) over the emitted vertices into

@@ -112,6 +112,11 @@ quad_advance_kernel(QuadArgs a, Op op, int *__restrict__ out, unsigned long long
         a.frontier = a.dyn->in;
         a.num_segments = a.dyn->len;
         out = a.dyn->out;
+        if constexpr (OUT_MODE == OUT_ROUTED) {
+#pragma unroll
+            for (int p = 0; p < MAX_DEST; ++p)
+                if (p == routed.self) routed.box[p] = a.dyn->out;
+        }
     }
     const unsigned long long Q = *a.total;
     if (threadIdx.x < 2) s_sum[threadIdx.x] = 0;
@@ -498,6 +503,16 @@ struct BfsPushPartQ {
     }
     __device__ __forceinline__ int route(int u) const { return (int)part.owner((uint32_t)u); }
     __device__ __forceinline__ bool route_is_local(int d) const { return d == (int)part.me; }
+};
+
+// BfsPushPartQ whose label comes from the device-resident level state (graph-driven loop).
+struct BfsPushPartQDyn : BfsPushPartQ {
+    const LoopDyn *dyn;
+    __device__ __forceinline__ int finish(Token old, const Cand &c) const {
+        if ((old >> (part.bit(c.w[0]) & 31)) & 1u) return -1;
+        if (part.owner(c.w[0]) == part.me) labels[part.row(c.w[0])] = dyn->next_label;
+        return (int)c.w[0];
+    }
 };
 
 // SSSP relax (sssp_functor.hxx:20-34), see SsspRelaxOp.  dist[src] is read once per quad.

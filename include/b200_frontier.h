@@ -317,6 +317,11 @@ int b200_p2p_bfs_connect(b200_p2p_bfs *s, const void *ipc_handles, void *const *
 int b200_p2p_bfs_run(b200_p2p_bfs *s, const b200_graph *g_local, int64_t m_global, int32_t src, int mode,
                      float alpha, float beta, int32_t *d_labels_local, b200_stats *stats /* nullable */,
                      int64_t *sent_per_level /* nullable, [B200_MAX_LEVELS] vertices all ranks sent */);
+/* Optional: build (and upload) the traversal graph of the graph-driven level loop for (g, mode, labels buffer)
+ * ahead of the first b200_p2p_bfs_run, so that no rank is still instantiating a graph while its peers already
+ * spin in a flag barrier (ranks that are threads of ONE process share a CUDA context).  A no-op when the ctx
+ * uses B200_LOOP_HOST.  b200_p2p_bfs_run builds lazily if this was not called. */
+int b200_p2p_bfs_prepare(b200_p2p_bfs *s, const b200_graph *g_local, int mode, int32_t *d_labels_local);
 int b200_p2p_bfs_destroy(b200_p2p_bfs *s);
 
 /* ---- host-buffer entry points (what test_bfs.cu times + extract: H2D, run, D2H) */

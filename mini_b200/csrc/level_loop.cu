@@ -23,6 +23,7 @@
 #include <new>
 #include "b200/operators.cuh"
 #include "engine.cuh"
+#include "graph_util.cuh"
 
 using namespace b200;
 
@@ -201,33 +202,6 @@ __global__ void loop_decide_kernel(LoopState *s, unsigned long long *counters, u
     }
     s->dyn.run = done ? 0u : ((pull ? LOOP_RUN_PULL : LOOP_RUN_PUSH) | trans);
     cudaGraphSetConditional(h_while, done ? 0u : 1u);
-}
-
-#define LL_CUDA(call)                                          \
-    do {                                                       \
-        cudaError_t _e = (call);                               \
-        if (_e != cudaSuccess) {                               \
-            st = ::b200::cuda_status(_e);                      \
-            goto fail;                                         \
-        }                                                      \
-    } while (0)
-
-// Ends a capture into `graph` and returns the nodes the next node of `graph` must depend on.
-int end_capture(cudaStream_t cs, cudaGraphNode_t *deps, size_t *ndeps, size_t max_deps) {
-    cudaStreamCaptureStatus cst;
-    const cudaGraphNode_t *d = nullptr;
-    size_t nd = 0;
-    cudaError_t e = cudaStreamGetCaptureInfo(cs, &cst, nullptr, nullptr, &d, &nd);
-    if (e == cudaSuccess && nd > max_deps) e = cudaErrorInvalidValue;
-    if (e == cudaSuccess) {
-        for (size_t i = 0; i < nd; ++i) deps[i] = d[i];
-        *ndeps = nd;
-    }
-    cudaGraph_t same = nullptr;
-    cudaError_t e2 = cudaStreamEndCapture(cs, &same);
-    if (e != cudaSuccess) return ::b200::cuda_status(e);
-    if (e2 != cudaSuccess) return ::b200::cuda_status(e2);
-    return B200_OK;
 }
 
 void drop_graph(LevelLoop *L) {

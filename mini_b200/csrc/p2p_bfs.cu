@@ -28,6 +28,7 @@
 #include <new>
 #include "b200/operators.cuh"
 #include "engine.cuh"
+#include "graph_util.cuh"
 
 using namespace b200;
 
@@ -156,12 +157,12 @@ __global__ void __launch_bounds__(32) p2p_stats_kernel(Peers peers, int me, int 
 
 // Receiver side of the push exchange over ALL inbox segments in one launch (counts live on the
 // device): label-if-unvisited, survivors join the next frontier after the local discoveries.
-__global__ void __launch_bounds__(256) p2p_absorb_kernel(const int *__restrict__ inbox, size_t seg_stride,
-                                                         const unsigned long long *counts, int me, int P,
-                                                         uint32_t *known, int *labels, int next_label, Partition part,
-                                                         int *next_frontier, unsigned long long capacity,
-                                                         unsigned long long *next_count, unsigned long long *counters,
-                                                         const uint32_t *__restrict__ offsets) {
+__device__ __forceinline__ void p2p_absorb_body(const int *__restrict__ inbox, size_t seg_stride,
+                                                const unsigned long long *counts, int me, int P,
+                                                uint32_t *known, int *labels, int next_label, Partition part,
+                                                int *next_frontier, unsigned long long capacity,
+                                                unsigned long long *next_count, unsigned long long *counters,
+                                                const uint32_t *__restrict__ offsets) {
     const unsigned lane = lane_id();
     const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
     unsigned long long deg_sum = 0;
@@ -200,6 +201,15 @@ __global__ void __launch_bounds__(256) p2p_absorb_kernel(const int *__restrict__
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) deg_sum += __shfl_xor_sync(FULL_MASK, deg_sum, d);
     if (lane == 0 && deg_sum) atomicAdd(&counters[B200_CNT_AUX], deg_sum);
+}
+__global__ void __launch_bounds__(256) p2p_absorb_kernel(const int *__restrict__ inbox, size_t seg_stride,
+                                                         const unsigned long long *counts, int me, int P,
+                                                         uint32_t *known, int *labels, int next_label, Partition part,
+                                                         int *next_frontier, unsigned long long capacity,
+                                                         unsigned long long *next_count, unsigned long long *counters,
+                                                         const uint32_t *__restrict__ offsets) {
+    p2p_absorb_body(inbox, seg_stride, counts, me, P, known, labels, next_label, part, next_frontier, capacity, next_count,
+                    counters, offsets);
 }
 
 // next frontier list (length on the device) -> this rank's bitmap slice (pre-cleared)
@@ -241,6 +251,303 @@ struct SliceListPred {   // bit r of the slice set -> emit the global id of loca
     }
 };
 
+
+// ============================================================================================
+// Graph-driven level loop (see level_loop.cu for the single-GPU form and the measurements behind
+// it): the whole multi-GPU traversal is ONE CUDA graph per rank -- prologue, then a WHILE
+// conditional node whose flat body holds every kernel of a level; each kernel returns at once
+// unless its LOOP_RUN_* bit is set.  All ranks compute the same global level summary in
+// p2p_stats_decide_kernel (the in-heap allreduce) and apply the same push / pull / stop rules to
+// it on the device, so no rank returns to its host between levels: zero host synchronisations and
+// zero collectives per level.  Barrier epochs, the stats parity and the look-back tags live in
+// P2PLoopState instead of kernel parameters.
+// ============================================================================================
+struct P2PLoopParams {      // mapped pinned, read by the init kernel
+    int32_t src, mode;
+    float alpha, beta;
+    long long m_global;
+    unsigned long long bar_epoch0;
+    uint32_t lb_epoch0, stats_seq0;
+};
+struct P2PLevelRec {
+    int32_t direction, pad;
+    long long frontier_len, arcs, discovered, sent;
+};
+struct P2PLoopResult {      // mapped pinned, written by the decide step
+    int32_t status, num_levels;
+    long long reached, total_arcs, launches;
+    unsigned long long bar_epoch;
+    uint32_t stats_seq, pad;
+    P2PLevelRec level[B200_MAX_LEVELS];
+};
+struct P2PLoopState {       // device
+    LoopDyn dyn;            // in / out / len = this rank's frontier list; bsel = which slice holds the current frontier
+    unsigned long long bar_epoch;
+    uint32_t stats_seq, timeout;
+    int32_t level, pull, mode, kernels_per_level;
+    float alpha, beta;
+    long long n, m_unexplored, flen, reached, total_arcs, launches;
+};
+
+struct FrontierQuadsDynPart {   // FrontierQuads over the device-selected list, rows of a 1D partition
+    const LoopDyn *dyn;
+    const uint32_t *offsets;
+    uint2 *rows;
+    uint32_t row_shift;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
+        const int v = dyn->in[i];
+        uint32_t b = 0, e = 0;
+        if (v >= 0) {
+            const uint32_t r = (uint32_t)v >> row_shift;
+            b = __ldg(offsets + r);
+            e = __ldg(offsets + r + 1);
+        }
+        rows[i] = make_uint2(b, e);
+        return e > b ? ((e - 1) >> 2) - (b >> 2) + 1u : 0u;
+    }
+};
+
+struct SliceListPredDyn {   // SliceListPred over the device-selected slice
+    const LoopDyn *dyn;
+    const uint32_t *slice0, *slice1;
+    Partition part;
+    __device__ __forceinline__ bool operator()(uint32_t idx, int &item) const {
+        const uint32_t *slice = dyn->bsel ? slice1 : slice0;
+        item = (int)part.global_id(part.me, idx);
+        return (slice[idx >> 5] >> (idx & 31)) & 1u;
+    }
+};
+
+__global__ void p2p_loop_init_kernel(const P2PLoopParams *p, P2PLoopState *s, int32_t *labels, uint32_t *known, int32_t *f0,
+                                     int32_t *f1, long long n, Partition part, unsigned long long *counters,
+                                     unsigned int *tile_counters, unsigned long long *box_counts, int kernels_per_level) {
+    const int src = p->src;
+    const uint32_t b = part.bit((uint32_t)src);
+    known[b >> 5] |= 1u << (b & 31);
+    const bool mine = part.owner((uint32_t)src) == part.me;
+    if (mine) {
+        labels[part.row((uint32_t)src)] = 0;
+        f0[0] = src;
+    }
+    s->dyn.in = f0;
+    s->dyn.out = f1;
+    s->dyn.len = mine ? 1u : 0u;
+    s->dyn.epoch = p->lb_epoch0 & 0x3FFFFFFFu;
+    s->dyn.next_label = 1;
+    s->dyn.bsel = 0u;
+    s->dyn.run = LOOP_RUN_PUSH;
+    s->bar_epoch = p->bar_epoch0;
+    s->stats_seq = p->stats_seq0;
+    s->timeout = 0u;
+    s->level = 0;
+    s->pull = 0;
+    s->mode = p->mode;
+    s->kernels_per_level = kernels_per_level;
+    s->alpha = p->alpha;
+    s->beta = p->beta;
+    s->n = n;
+    s->m_unexplored = p->m_global;
+    s->flen = 1;
+    s->reached = 1;
+    s->total_arcs = 0;
+    s->launches = 1;
+    for (int i = 0; i < B200_NUM_COUNTERS; ++i) counters[i] = 0ull;
+    for (int i = 0; i < P2P_MAX; ++i) box_counts[i] = 0ull;
+    tile_counters[0] = 0u;
+    tile_counters[1] = 0u;
+}
+
+// the slice this level's discoveries are written to (slice[bsel ^ 1]) must start all-zero
+__global__ void p2p_clear_slice_dyn_kernel(const LoopDyn *dyn, uint4 *slice0, uint4 *slice1, uint32_t quads) {
+    if (!(dyn->run & LOOP_RUN_PUSH)) return;
+    uint4 *w = dyn->bsel ? slice0 : slice1;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += gridDim.x * blockDim.x) w[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+__global__ void __launch_bounds__(32) p2p_publish_counts_dyn_kernel(Peers peers, int me, int P, P2PLoopState *s,
+                                                                    const unsigned long long *box_counts) {
+    if (!(s->dyn.run & LOOP_RUN_PUSH)) return;
+    const int p = (int)lane_id();
+    const unsigned long long epoch = s->bar_epoch + 1ull;
+    __syncwarp();
+    if (p < P && p != me) st_relaxed_sys(&reinterpret_cast<Ctrl *>(peers.base[p])->counts[me], box_counts[p]);
+    const bool ok = p2p_signal_wait(peers, me, P, epoch);
+    if (p == 0) {
+        s->bar_epoch = epoch;
+        if (!ok) s->timeout = 1u;
+    }
+}
+
+__global__ void __launch_bounds__(256) p2p_absorb_dyn_kernel(const int *__restrict__ inbox, size_t seg_stride,
+                                                             const unsigned long long *counts, int me, int P, uint32_t *known,
+                                                             int *labels, const LoopDyn *dyn, Partition part,
+                                                             unsigned long long capacity, unsigned long long *next_count,
+                                                             unsigned long long *counters, const uint32_t *__restrict__ offsets) {
+    if (!(dyn->run & LOOP_RUN_PUSH)) return;
+    p2p_absorb_body(inbox, seg_stride, counts, me, P, known, labels, dyn->next_label, part, dyn->out, capacity, next_count,
+                    counters, offsets);
+}
+
+__global__ void p2p_list_to_slice_dyn_kernel(const LoopDyn *dyn, const unsigned long long *len_ptr, uint32_t *slice0,
+                                             uint32_t *slice1, Partition part) {
+    if (!(dyn->run & LOOP_RUN_PUSH)) return;
+    const int *__restrict__ list = dyn->out;
+    uint32_t *slice = dyn->bsel ? slice0 : slice1;
+    const unsigned long long len = *len_ptr;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+        const uint32_t r = part.row((uint32_t)list[i]);
+        atomicOr(slice + (r >> 5), 1u << (r & 31));
+    }
+}
+
+__global__ void __launch_bounds__(256) p2p_gather_or_dyn_kernel(Peers peers, size_t off_slice0, size_t off_slice1,
+                                                                uint32_t quads_per_slice, int P, const LoopDyn *dyn,
+                                                                uint32_t run_bit, uint4 *__restrict__ full,
+                                                                uint4 *__restrict__ known) {
+    if (!(dyn->run & run_bit)) return;
+    const size_t slice_off = dyn->bsel ? off_slice1 : off_slice0;
+    const size_t total = (size_t)quads_per_slice * (size_t)P;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint32_t p = (uint32_t)(i / quads_per_slice);
+        const uint32_t j = (uint32_t)(i - (size_t)p * quads_per_slice);
+        const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(peers.base[p] + slice_off) + j);
+        full[i] = v;
+        if (v.x | v.y | v.z | v.w) {
+            uint4 k = known[i];
+            k.x |= v.x; k.y |= v.y; k.z |= v.z; k.w |= v.w;
+            known[i] = k;
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) p2p_pull_dyn_kernel(uint32_t n_local, const uint32_t *__restrict__ offsets,
+                                                          const int *__restrict__ indices, const uint32_t *__restrict__ full,
+                                                          uint32_t *slice0, uint32_t *slice1, uint32_t *__restrict__ known_slice,
+                                                          int *__restrict__ labels, const LoopDyn *dyn,
+                                                          unsigned long long *counters, Partition part) {
+    if (!(dyn->run & LOOP_RUN_PULL)) return;
+    bfs_pull_body<NT>(n_local, offsets, indices, full, dyn->bsel ? slice0 : slice1, known_slice, labels, dyn->next_label,
+                      counters, part);
+}
+
+// Level summary (as p2p_stats_kernel) + the host loop's decision, on every rank identically.
+__global__ void __launch_bounds__(32) p2p_stats_decide_kernel(Peers peers, int me, int P, P2PLoopState *s,
+                                                              unsigned long long *counters, unsigned long long *box_counts,
+                                                              unsigned int *tile_counters, P2PLoopResult *res,
+                                                              cudaGraphConditionalHandle h_while) {
+    const int p = (int)lane_id();
+    const bool was_pull = s->pull != 0;
+    const unsigned long long epoch = s->bar_epoch + 1ull;
+    const int parity = (int)(s->stats_seq & 1u);
+    __syncwarp();
+    unsigned long long row[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) row[k] = 0;
+    if (!was_pull) {
+        row[ROW_NEXT] = box_counts[me];
+        for (int q = 0; q < P; ++q)
+            if (q != me) row[ROW_SENT] += box_counts[q];
+    } else {
+        row[ROW_NEXT] = counters[B200_CNT_OUT];
+    }
+    row[ROW_ARCS] = counters[B200_CNT_ARCS];
+    row[ROW_DEG] = counters[B200_CNT_AUX];
+    row[ROW_OVERFLOW] = counters[B200_CNT_OVERFLOW];
+    if (p < P) {
+        unsigned long long *dst = reinterpret_cast<Ctrl *>(peers.base[p])->stats[parity][me];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) st_relaxed_sys(dst + k, row[k]);
+    }
+    const bool ok = p2p_signal_wait(peers, me, P, epoch);
+    unsigned long long mysum = 0;
+    if (p < 8) {
+        const Ctrl *mine = reinterpret_cast<const Ctrl *>(peers.base[me]);
+        for (int q = 0; q < P; ++q) mysum += ld_relaxed_sys(&mine->stats[parity][q][p]);
+    }
+    const long long found = (long long)__shfl_sync(FULL_MASK, mysum, ROW_NEXT);
+    const long long arcs = (long long)__shfl_sync(FULL_MASK, mysum, ROW_ARCS);
+    const long long next_deg = (long long)__shfl_sync(FULL_MASK, mysum, ROW_DEG);
+    const long long sent = (long long)__shfl_sync(FULL_MASK, mysum, ROW_SENT);
+    const bool overflow = __shfl_sync(FULL_MASK, mysum, ROW_OVERFLOW) != 0ull;
+    if (p != 0) return;
+
+    const long long next_local = (long long)row[ROW_NEXT];
+    bool pull = was_pull;
+    int level = s->level;
+    if (level < B200_MAX_LEVELS) {
+        P2PLevelRec *r = &res->level[level];
+        r->direction = was_pull ? 1 : 0;
+        r->frontier_len = s->flen;
+        r->arcs = arcs;
+        r->discovered = found;
+        r->sent = sent;
+    }
+    s->total_arcs += arcs;
+    s->launches += s->kernels_per_level;
+    ++level;
+    s->level = level;
+    s->bar_epoch = epoch;
+    s->stats_seq += 1u;
+    bool done = false;
+    uint32_t trans = 0u;
+    int status = B200_OK;
+    if (!ok || s->timeout) {
+        status = B200_ERR_TIMEOUT;
+        done = true;
+    } else if (overflow) {
+        status = B200_ERR_OVERFLOW;
+        done = true;
+    } else if (found == 0) {
+        done = true;
+    } else {
+        const long long flen = s->flen;
+        s->reached += found;
+        if (!was_pull) {
+            s->m_unexplored -= arcs;
+            const int *t = s->dyn.in;
+            s->dyn.in = s->dyn.out;
+            s->dyn.out = const_cast<int *>(t);
+            s->dyn.len = (uint32_t)next_local;
+            if (s->mode == B200_BFS_BEAMER && (double)next_deg > (double)s->m_unexplored / s->alpha && found > flen) {
+                pull = true;
+                s->dyn.bsel ^= 1u;   // the slice written this level is the frontier of the first pull level
+            }
+        } else {
+            s->dyn.bsel ^= 1u;
+            if ((double)found < (double)s->n / s->beta && found < flen) {
+                // hand the (small) frontier back to push: the last pull discoveries of the peers become
+                // "known", this rank's slice becomes its frontier list (gather + compaction below)
+                trans = LOOP_RUN_TO_PUSH;
+                s->dyn.len = (uint32_t)next_local;
+                pull = false;
+            }
+        }
+        s->flen = found;
+    }
+    s->pull = pull ? 1 : 0;
+    s->dyn.next_label = level + 1;
+    s->dyn.epoch = (s->dyn.epoch + 2u) & 0x3FFFFFFFu;
+    for (int i = 0; i < B200_NUM_COUNTERS; ++i) counters[i] = 0ull;
+    for (int i = 0; i < P2P_MAX; ++i) box_counts[i] = 0ull;
+    tile_counters[0] = 0u;
+    tile_counters[1] = 0u;
+    if (done) {
+        res->status = status;
+        res->num_levels = level;
+        res->reached = s->reached;
+        res->total_arcs = s->total_arcs;
+        res->launches = s->launches;
+        res->bar_epoch = s->bar_epoch;
+        res->stats_seq = s->stats_seq;
+        __threadfence_system();
+    }
+    s->dyn.run = done ? 0u : ((pull ? LOOP_RUN_PULL : LOOP_RUN_PUSH) | trans);
+    cudaGraphSetConditional(h_while, done ? 0u : 1u);
+}
+
 // CUDA loads kernels lazily, and a load may have to wait for every kernel running in the context.
 // A rank that spins in a flag barrier while a peer rank OF THE SAME PROCESS (ranks as threads) is
 // about to launch a kernel for the first time would therefore deadlock: load everything up front.
@@ -263,6 +570,17 @@ cudaError_t preload_kernels() {
     if ((e = preload(scan_sizes_kernel<SCAN_NT, SCAN_VT, FrontierDegree>)) != cudaSuccess) return e;
     if ((e = preload(compact_kernel<COMPACT_NT, COMPACT_VT, SliceListPred>)) != cudaSuccess) return e;
     if ((e = preload(quad_advance_kernel<BfsPushPartQ, OUT_ROUTED, true, QUAD_NT, VT, QUAD_WSEG>)) != cudaSuccess) return e;
+    if ((e = preload(quad_advance_kernel<BfsPushPartQDyn, OUT_ROUTED, true, QUAD_NT, VT, QUAD_WSEG>)) != cudaSuccess) return e;
+    if ((e = preload(scan_sizes_dyn_kernel<SCAN_NT, SCAN_VT, FrontierQuadsDynPart>)) != cudaSuccess) return e;
+    if ((e = preload(compact_dyn_kernel<COMPACT_NT, COMPACT_VT, SliceListPredDyn>)) != cudaSuccess) return e;
+    if ((e = preload(p2p_loop_init_kernel)) != cudaSuccess) return e;
+    if ((e = preload(p2p_clear_slice_dyn_kernel)) != cudaSuccess) return e;
+    if ((e = preload(p2p_publish_counts_dyn_kernel)) != cudaSuccess) return e;
+    if ((e = preload(p2p_absorb_dyn_kernel)) != cudaSuccess) return e;
+    if ((e = preload(p2p_list_to_slice_dyn_kernel)) != cudaSuccess) return e;
+    if ((e = preload(p2p_gather_or_dyn_kernel)) != cudaSuccess) return e;
+    if ((e = preload(p2p_pull_dyn_kernel<256>)) != cudaSuccess) return e;
+    if ((e = preload(p2p_stats_decide_kernel)) != cudaSuccess) return e;
     if ((e = preload(lbs_advance_kernel<BfsPushPartOp, OUT_ROUTED, true, LBS_NT, LBS_VT, LBS_SEG_T>)) != cudaSuccess) return e;
     return cudaSuccess;
 }
@@ -288,7 +606,264 @@ struct b200_p2p_bfs {
     cudaEvent_t ev_run[2];
     cudaEvent_t ev_level[P2P_TIMED_LEVELS + 1];
     bool have_level_events;
+    // graph-driven level loop
+    P2PLoopState *d_lstate;
+    P2PLoopParams *h_lparams, *d_lparams;
+    P2PLoopResult *h_lresult, *d_lresult;
+    cudaStream_t cap_stream;
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    const void *k_offsets, *k_indices, *k_labels, *k_scratch;
+    int k_mode;
+    int graph_failed;
 };
+
+namespace {
+
+void p2p_drop_graph(b200_p2p_bfs *s) {
+    if (s->exec) cudaGraphExecDestroy(s->exec);
+    if (s->graph) cudaGraphDestroy(s->graph);
+    s->exec = nullptr;
+    s->graph = nullptr;
+    s->k_offsets = s->k_indices = s->k_labels = s->k_scratch = nullptr;
+}
+
+int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int mode) {
+    b200_ctx *ctx = s->ctx;
+    b200_workspace *ws = &ctx->ws;
+    const int me = s->rank, P = s->P;
+    const Partition part{s->log_p, (uint32_t)me, (uint32_t)s->n_local};
+    const bool beamer = mode == B200_BFS_BEAMER;
+    const uint32_t *pull_off = g->col_offsets ? g->col_offsets : g->row_offsets;
+    const int32_t *pull_idx = g->row_indices ? g->row_indices : g->col_indices;
+    Ctrl *my_ctrl = reinterpret_cast<Ctrl *>(s->heap);
+    int *my_inbox = reinterpret_cast<int *>(s->heap + s->off_inbox);
+    uint32_t *slice0 = reinterpret_cast<uint32_t *>(s->heap + s->off_slice[0]);
+    uint32_t *slice1 = reinterpret_cast<uint32_t *>(s->heap + s->off_slice[1]);
+    cudaStream_t cs = s->cap_stream;
+    void *const user_stream = ws->stream;
+    const int64_t launches0 = ws->launches;
+    int st = B200_OK;
+    bool capturing = false;
+    cudaGraph_t G = nullptr, body = nullptr;
+    cudaGraphConditionalHandle h_while;
+    cudaGraphNode_t deps[8], n_while;
+    size_t ndeps = 0;
+    cudaGraphNodeParams np_w = {};
+    const LoopDyn *dyn = &s->d_lstate->dyn;
+    const int kernels_per_level = 2 + (P > 1 ? 2 : 0) + (beamer ? 6 : 0) + 1;
+
+    p2p_drop_graph(s);
+    ws->stream = (void *)cs;
+    LL_CUDA(cudaGraphCreate(&G, 0));
+    LL_CUDA(cudaGraphConditionalHandleCreate(&h_while, G, 1, cudaGraphCondAssignDefault));
+
+    // ---- prologue
+    LL_CUDA(cudaStreamBeginCaptureToGraph(cs, G, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    capturing = true;
+    LL_CUDA(cudaMemsetAsync(d_labels, 0xFF, sizeof(int32_t) * (size_t)s->n_local, cs));
+    LL_CUDA(cudaMemsetAsync(s->known, 0, (size_t)(s->n_global / 8), cs));
+    p2p_loop_init_kernel<<<1, 1, 0, cs>>>(s->d_lparams, s->d_lstate, d_labels, s->known, ctx->frontier[0], ctx->frontier[1],
+                                          (long long)s->n_global, part, ws->d_counters, ws->d_tile_counter, s->box_counts,
+                                          kernels_per_level);
+    LL_CUDA(cudaGetLastError());
+    capturing = false;
+    if ((st = end_capture(cs, deps, &ndeps, 8)) != B200_OK) goto fail;
+
+    np_w.type = cudaGraphNodeTypeConditional;
+    np_w.conditional.handle = h_while;
+    np_w.conditional.type = cudaGraphCondTypeWhile;
+    np_w.conditional.size = 1;
+    LL_CUDA(cudaGraphAddNode(&n_while, G, deps, ndeps, &np_w));
+    body = np_w.conditional.phGraph_out[0];
+
+    // ---- the flat body of one level
+    LL_CUDA(cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    capturing = true;
+    {
+        // push level
+        if (beamer) {
+            p2p_clear_slice_dyn_kernel<<<ws->num_sms, 256, 0, cs>>>(dyn, reinterpret_cast<uint4 *>(slice0),
+                                                                     reinterpret_cast<uint4 *>(slice1), s->wl / 4);
+            LL_CUDA(cudaGetLastError());
+        }
+        const int64_t max_tiles = (s->n_local + SCAN_NT * SCAN_VT - 1) / (SCAN_NT * SCAN_VT);
+        int64_t grid = (int64_t)ws->num_sms * 4;
+        if (grid > max_tiles) grid = max_tiles;
+        FrontierQuadsDynPart fn{dyn, g->row_offsets, reinterpret_cast<uint2 *>(ws->d_rows), part.log_p};
+        scan_sizes_dyn_kernel<SCAN_NT, SCAN_VT><<<(unsigned)grid, SCAN_NT, 0, cs>>>(
+            fn, dyn, (uint32_t)LOOP_RUN_PUSH, ws->d_scanned, ws->d_status, ws->d_tile_counter, ws->d_counters + B200_CNT_TOTAL);
+        LL_CUDA(cudaGetLastError());
+        RoutedOut r;
+        std::memset(&r, 0, sizeof r);
+        r.num_dest = P;
+        r.count = s->box_counts;
+        r.self = me;
+        for (int p = 0; p < P; ++p) {
+            r.box[p] = p == me ? ctx->frontier[1]
+                               : reinterpret_cast<int *>(s->peers.base[p] + s->off_inbox) + (size_t)me * (size_t)s->n_local;
+            r.capacity[p] = (unsigned long long)s->n_local;
+        }
+        QuadArgs a = make_quad_args(ws, ctx->frontier[0], 0u, g->row_offsets, g->col_indices, nullptr, part.log_p);
+        a.dyn = dyn;
+        BfsPushPartQDyn op{{s->known, d_labels, 0, part}, dyn};
+        LL_CUDA((launch_quad_advance<OUT_ROUTED, true>(ws, a, op, nullptr, 0ull, &r)));
+        if (P > 1) {
+            p2p_publish_counts_dyn_kernel<<<1, 32, 0, cs>>>(s->peers, me, P, s->d_lstate, s->box_counts);
+            LL_CUDA(cudaGetLastError());
+            p2p_absorb_dyn_kernel<<<ws->num_sms * 2, 256, 0, cs>>>(my_inbox, (size_t)s->n_local, my_ctrl->counts, me, P, s->known,
+                                                                   d_labels, dyn, part, (unsigned long long)s->n_local,
+                                                                   s->box_counts + me, ws->d_counters, g->row_offsets);
+            LL_CUDA(cudaGetLastError());
+        }
+        if (beamer) {
+            p2p_list_to_slice_dyn_kernel<<<ws->num_sms, 256, 0, cs>>>(dyn, s->box_counts + me, slice0, slice1, part);
+            LL_CUDA(cudaGetLastError());
+            // pull level
+            p2p_gather_or_dyn_kernel<<<ws->num_sms * 4, 256, 0, cs>>>(s->peers, s->off_slice[0], s->off_slice[1], s->wl / 4, P, dyn,
+                                                                      (uint32_t)LOOP_RUN_PULL, reinterpret_cast<uint4 *>(s->full),
+                                                                      reinterpret_cast<uint4 *>(s->known));
+            LL_CUDA(cudaGetLastError());
+            p2p_pull_dyn_kernel<256><<<ws->num_sms * 8, 256, 0, cs>>>((uint32_t)s->n_local, pull_off, pull_idx, s->full, slice0, slice1,
+                                                                      s->known + (size_t)me * s->wl, d_labels, dyn, ws->d_counters, part);
+            LL_CUDA(cudaGetLastError());
+        }
+        // level summary across the ranks + decision
+        p2p_stats_decide_kernel<<<1, 32, 0, cs>>>(s->peers, me, P, s->d_lstate, ws->d_counters, s->box_counts, ws->d_tile_counter,
+                                                  s->d_lresult, h_while);
+        LL_CUDA(cudaGetLastError());
+        if (beamer) {
+            // pull -> push hand-over
+            p2p_gather_or_dyn_kernel<<<ws->num_sms * 4, 256, 0, cs>>>(s->peers, s->off_slice[0], s->off_slice[1], s->wl / 4, P, dyn,
+                                                                      (uint32_t)LOOP_RUN_TO_PUSH, reinterpret_cast<uint4 *>(s->full),
+                                                                      reinterpret_cast<uint4 *>(s->known));
+            LL_CUDA(cudaGetLastError());
+            const int64_t ctiles = (s->n_local + COMPACT_NT * COMPACT_VT - 1) / (COMPACT_NT * COMPACT_VT);
+            int64_t cgrid = (int64_t)ws->num_sms * 4;
+            if (cgrid > ctiles) cgrid = ctiles;
+            SliceListPredDyn pred{dyn, slice0, slice1, part};
+            compact_dyn_kernel<COMPACT_NT, COMPACT_VT><<<(unsigned)cgrid, COMPACT_NT, 0, cs>>>(
+                pred, (uint32_t)s->n_local, dyn, (uint32_t)LOOP_RUN_TO_PUSH, (unsigned long long)s->n_local, ws->d_status,
+                ws->d_tile_counter + 1, ws->d_counters + B200_CNT_AUX2, ws->d_counters + B200_CNT_OVERFLOW, nullptr);
+            LL_CUDA(cudaGetLastError());
+        }
+    }
+    capturing = false;
+    if ((st = end_capture(cs, deps, &ndeps, 8)) != B200_OK) goto fail;
+
+    LL_CUDA(cudaGraphInstantiate(&s->exec, G, 0));
+    s->graph = G;
+    s->k_offsets = g->row_offsets;
+    s->k_indices = g->col_indices;
+    s->k_labels = d_labels;
+    s->k_scratch = ctx->frontier[0];
+    s->k_mode = mode;
+    ws->stream = user_stream;
+    ws->launches = launches0;
+    return B200_OK;
+
+fail:
+    if (capturing) {
+        cudaGraph_t junk = nullptr;
+        cudaStreamEndCapture(cs, &junk);
+    }
+    (void)cudaGetLastError();
+    if (G) cudaGraphDestroy(G);
+    ws->stream = user_stream;
+    ws->launches = launches0;
+    return st;
+}
+
+// Builds (or reuses) the graph for (g, labels, mode).  B200_ERR_UNSUPPORTED if it cannot be built here.
+int p2p_ensure_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int mode) {
+    b200_ctx *ctx = s->ctx;
+    cudaStream_t st = ws_stream(&ctx->ws);
+    if (s->graph_failed) return B200_ERR_UNSUPPORTED;
+    if (!s->cap_stream) {
+        B200_CUDA(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+        B200_CUDA(cudaMalloc(&s->d_lstate, sizeof(P2PLoopState)));
+        B200_CUDA(cudaHostAlloc(&s->h_lparams, sizeof(P2PLoopParams), cudaHostAllocMapped));
+        B200_CUDA(cudaHostAlloc(&s->h_lresult, sizeof(P2PLoopResult), cudaHostAllocMapped));
+        B200_CUDA(cudaHostGetDevicePointer(&s->d_lparams, s->h_lparams, 0));
+        B200_CUDA(cudaHostGetDevicePointer(&s->d_lresult, s->h_lresult, 0));
+    }
+    if (!s->exec || s->k_offsets != g->row_offsets || s->k_indices != g->col_indices || s->k_labels != d_labels ||
+        s->k_scratch != ctx->frontier[0] || s->k_mode != mode) {
+        B200_CUDA(cudaStreamSynchronize(st));
+        const int bs = p2p_build_graph(s, g, d_labels, mode);
+        if (bs != B200_OK) {
+            s->graph_failed = bs;
+            return B200_ERR_UNSUPPORTED;
+        }
+        B200_CUDA(cudaGraphUpload(s->exec, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+    }
+    return B200_OK;
+}
+
+// b200_p2p_bfs_run through the graph; B200_ERR_UNSUPPORTED => the caller runs the host-driven loop.
+int p2p_run_graph(b200_p2p_bfs *s, const b200_graph *g, int64_t m_global, int32_t src, int mode, float alpha, float beta,
+                  int32_t *d_labels, b200_stats *stats, int64_t *sent_per_level) {
+    b200_ctx *ctx = s->ctx;
+    b200_workspace *ws = &ctx->ws;
+    cudaStream_t st = ws_stream(ws);
+    B200_TRY(p2p_ensure_graph(s, g, d_labels, mode));
+    if (ws->epoch > 0x3FFFFFFFu - 4u * (B200_MAX_LEVELS + 2)) {
+        B200_CUDA(cudaMemsetAsync(ws->d_status, 0, sizeof(unsigned long long) * (size_t)ws->status_tiles, st));
+        ws->epoch = 0;
+    }
+    P2PLoopParams *pr = s->h_lparams;
+    pr->src = src;
+    pr->mode = mode;
+    pr->alpha = alpha;
+    pr->beta = beta;
+    pr->m_global = m_global;
+    pr->bar_epoch0 = s->epoch;
+    pr->lb_epoch0 = ws->epoch + 1;
+    pr->stats_seq0 = s->stats_seq;
+    s->h_lresult->status = -1;
+    s->h_lresult->num_levels = 0;
+    B200_CUDA(cudaEventRecord(s->ev_run[0], st));
+    B200_CUDA(cudaGraphLaunch(s->exec, st));
+    B200_CUDA(cudaEventRecord(s->ev_run[1], st));
+    B200_CUDA(cudaEventSynchronize(s->ev_run[1]));
+    const P2PLoopResult *r = s->h_lresult;
+    if (r->status < 0) return B200_ERR_CUDA;
+    s->epoch = r->bar_epoch;
+    s->stats_seq = r->stats_seq;
+    const int levels = r->num_levels;
+    const unsigned used = 2u * (unsigned)levels + 2u;
+    if (used > 0x3FFFFFFFu - ws->epoch - 2u) {
+        B200_CUDA(cudaMemsetAsync(ws->d_status, 0, sizeof(unsigned long long) * (size_t)ws->status_tiles, st));
+        ws->epoch = 0;
+    } else {
+        ws->epoch += used;
+    }
+    ws->launches += r->launches;
+    const int nl = levels < B200_MAX_LEVELS ? levels : B200_MAX_LEVELS;
+    if (stats) {
+        stats->num_levels = levels;
+        stats->reached = r->reached;
+        stats->total_arcs = r->total_arcs;
+        stats->launches = r->launches;
+        stats->level_loop = B200_LOOP_GRAPH;
+        B200_CUDA(cudaEventElapsedTime(&stats->device_ms, s->ev_run[0], s->ev_run[1]));
+        for (int l = 0; l < nl; ++l) {
+            b200_level_stat *ls = &stats->level[l];
+            ls->direction = r->level[l].direction;
+            ls->frontier_len = r->level[l].frontier_len;
+            ls->arcs = r->level[l].arcs;
+            ls->discovered = r->level[l].discovered;
+            ls->advance_ms = 0.f;
+            ls->level_ms = 0.f;
+        }
+    }
+    if (sent_per_level)
+        for (int l = 0; l < nl; ++l) sent_per_level[l] = r->level[l].sent;
+    return r->status;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -400,8 +975,25 @@ int b200_p2p_bfs_destroy(b200_p2p_bfs *s) {
     if (s->ev_run[1]) cudaEventDestroy(s->ev_run[1]);
     if (s->have_level_events)
         for (int i = 0; i <= P2P_TIMED_LEVELS; ++i) cudaEventDestroy(s->ev_level[i]);
+    p2p_drop_graph(s);
+    if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
+    if (s->d_lstate) cudaFree(s->d_lstate);
+    if (s->h_lparams) cudaFreeHost(s->h_lparams);
+    if (s->h_lresult) cudaFreeHost(s->h_lresult);
     delete s;
     return B200_OK;
+}
+
+int b200_p2p_bfs_prepare(b200_p2p_bfs *s, const b200_graph *g, int mode, int32_t *d_labels) {
+    if (!s || !g || !d_labels || g->n != s->n_local) return B200_ERR_INVALID;
+    if (mode != B200_BFS_PUSH && mode != B200_BFS_BEAMER) return B200_ERR_INVALID;
+    if (s->P > 1 && !s->connected) return B200_ERR_INVALID;
+    b200_ctx *ctx = s->ctx;
+    B200_CUDA(cudaSetDevice(ctx->ws.device));
+    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(g->col_indices);
+    if (!quad || ctx->loop_impl != B200_LOOP_GRAPH) return B200_OK;   // host-driven loop: nothing to build
+    const int st = p2p_ensure_graph(s, g, d_labels, mode);
+    return st == B200_ERR_UNSUPPORTED ? B200_OK : st;                 // run() then takes the host-driven loop
 }
 
 int b200_p2p_bfs_run(b200_p2p_bfs *s, const b200_graph *g, int64_t m_global, int32_t src, int mode, float alpha, float beta,
@@ -429,6 +1021,12 @@ int b200_p2p_bfs_run(b200_p2p_bfs *s, const b200_graph *g, int64_t m_global, int
     int *my_inbox = reinterpret_cast<int *>(s->heap + s->off_inbox);
     if (alpha <= 0.f) alpha = 15.f;
     if (beta <= 0.f) beta = 18.f;
+    if (quad && !timing && ctx->loop_impl == B200_LOOP_GRAPH) {
+        // every rank takes the same branch: the choice depends only on settings the ranks share
+        const int gs = p2p_run_graph(s, g, m_global, src, mode, alpha, beta, d_labels, stats, sent_per_level);
+        if (gs != B200_ERR_UNSUPPORTED) return gs;
+    }
+    if (stats) stats->level_loop = B200_LOOP_HOST;
 
     B200_CUDA(cudaEventRecord(s->ev_run[0], st));
     B200_CUDA(cudaMemsetAsync(d_labels, 0xFF, sizeof(int32_t) * (size_t)s->n_local, st));

@@ -37,6 +37,7 @@ def run(args) -> int:
     ef = 16
     n, m = 1 << scale, (2 * ef) << scale
     ctx = mb.Context(dev)
+    ctx.set_level_loop(mb.LOOP_HOST if getattr(args, "loop", "graph") == "host" else mb.LOOP_GRAPH)
     t0 = time.time()
     g = D.build_rank_graph(ctx, scale, ef, 1, rank, world)
     build_s = time.time() - t0
@@ -47,6 +48,8 @@ def run(args) -> int:
     if exchange == "p2p":
         rk = P2PBfs(ctx, rank, world, n, m, g)
         rk.connect_torch_distributed()
+        rk.prepare(mode)
+        dist.barrier()
 
         def run_bfs(md=mode):
             rk.run(0, md)
@@ -97,6 +100,8 @@ def run(args) -> int:
     for _ in range(args.warmup):
         run_bfs()
     ms_total, launches = timed(args.steps, run_bfs)
+    if exchange == "p2p":
+        rk.level_loop_timed = rk.level_loop
     levels = list(run_bfs())
     level_ms = [round(l.get("level_ms", 0.0), 4) for l in levels]
     if exchange == "p2p":                       # one more run with per-level events (outside the timed region)
@@ -179,7 +184,8 @@ def run(args) -> int:
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": f"direction-optimising BFS from vertex 0, RMAT scale-{scale} ef16 symmetrised "
                                    f"(n={n}, m={m}), cyclic 1D vertex partition over {world} GPUs, {ex_text}",
-                       "mode": mode, "exchange": exchange, "teps_numerator": "sum of deg(v) over reached v",
+                       "mode": mode, "exchange": exchange,
+                       "level_loop": getattr(rk, "level_loop_timed", "host"), "teps_numerator": "sum of deg(v) over reached v",
                        "reached_arcs": reached_arcs, "reached_vertices": reached_vertices,
                        "parallelism": f"1d-cyclic x{world}",
                        "l2": "inputs larger than L2 (per-rank col_indices %d MiB)" % (g.m * 4 >> 20),

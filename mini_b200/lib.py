@@ -117,6 +117,7 @@ def load_library():
         "b200_p2p_bfs_create": ([vp, i32, i32, i64, C.POINTER(vp), vp, C.POINTER(vp)], i32),
         "b200_p2p_bfs_connect": ([vp, vp, vp], i32),
         "b200_p2p_bfs_run": ([vp, pg, i64, i32, i32, f32, f32, vp, ps, pi64], i32),
+        "b200_p2p_bfs_prepare": ([vp, pg, i32, vp], i32),
         "b200_p2p_bfs_destroy": ([vp], i32),
         "b200_host_graph_upload": ([vp, i64, i64, vp, vp, vp, C.POINTER(vp)], i32),
         "b200_host_graph_free": ([vp, vp], i32),

@@ -58,6 +58,11 @@ class P2PBfs:
         dist.barrier()
 
     # -- the traversal -----------------------------------------------------------------------
+    def prepare(self, mode: str = "beamer"):
+        """Builds the traversal graph ahead of the first run (call on every rank, then barrier)."""
+        m = L.BFS_BEAMER if mode == "beamer" else L.BFS_PUSH
+        L._check(self._L.b200_p2p_bfs_prepare(self._h, C.byref(self.cg), m, self.labels.data_ptr()), "b200_p2p_bfs_prepare")
+
     def run(self, src: int = 0, mode: str = "beamer", alpha: float = 15.0, beta: float = 18.0, timing: bool = False):
         cs = L.CStats()
         cs.collect_timing = int(timing)
@@ -68,7 +73,7 @@ class P2PBfs:
         st = L.Stats(cs)
         self.levels = [dict(direction=l["direction"], frontier=l["frontier_len"], arcs=l["arcs"], discovered=l["discovered"],
                             sent=int(sent[i]), level_ms=l["level_ms"]) for i, l in enumerate(st.levels)]
-        self.device_ms, self.launches = st.device_ms, st.launches
+        self.device_ms, self.launches, self.level_loop = st.device_ms, st.launches, st.level_loop
         return st.num_levels
 
     def close(self):

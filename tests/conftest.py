@@ -9,6 +9,12 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# The virtual-rank multi-GPU tests run up to 8 ranks as threads on ONE GPU, each replaying its own CUDA graph whose
+# kernels spin in cross-rank flag barriers.  With the default 8 hardware work queues two ranks' streams can share a
+# queue, and a rank spinning at the head of a queue then blocks the peer it is waiting for.  One process per GPU (the
+# deployment) never has this problem.  Must be set before CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")

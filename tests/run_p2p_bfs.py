@@ -33,6 +33,8 @@ ctx = mb.Context(dev)
 g = D.build_rank_graph(ctx, a.scale, ef, 1, rank, world)
 bfs = P2PBfs(ctx, rank, world, n, (2 * ef) << a.scale, g)
 bfs.connect_torch_distributed()
+bfs.prepare(a.mode)
+dist.barrier()
 for _ in range(a.repeat):               # repeated runs reuse the heap: epochs / double buffers must stay consistent
     levels = bfs.run(a.src, a.mode)
 gl = [torch.empty_like(bfs.labels) for _ in range(world)]

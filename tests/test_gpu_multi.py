@@ -86,7 +86,7 @@ def test_partitioned_bfs_other_sources(src):
     assert np.array_equal(labels, ref)
 
 
-def _virtual_ranks_p2p(scale, ef, seed, world, src, mode, repeat=2):
+def _virtual_ranks_p2p(scale, ef, seed, world, src, mode, repeat=2, loop="graph"):
     """P ranks as threads of this process, each with its OWN stream on GPU 0 (the cross-rank flag
     barriers spin inside kernels, so the ranks' kernels must be able to run concurrently); heaps are
     wired by address (b200_p2p_bfs_connect with peer_bases)."""
@@ -100,15 +100,18 @@ def _virtual_ranks_p2p(scale, ef, seed, world, src, mode, repeat=2):
     def work(rank):
         try:
             ctx = mb.Context(0, stream=None)
+            ctx.set_level_loop(mb.LOOP_GRAPH if loop == "graph" else mb.LOOP_HOST)
             g = D.build_rank_graph(ctx, scale, ef, seed, rank, world)
             bfs = P2PBfs(ctx, rank, world, n, (2 * ef) << scale, g)
             bases[rank] = bfs.heap_base
             bar.wait()
             if world > 1:
                 bfs.connect_local(bases)
+            bfs.prepare(mode)        # graph-driven loop: build the traversal graph before any rank spins in a barrier
             bar.wait()
             for _ in range(repeat):
                 levels = bfs.run(src, mode)
+                assert bfs.level_loop == loop, "the requested level loop did not run"
             ctx.sync()
             out[rank] = (bfs.labels.cpu().numpy(), levels, list(bfs.levels))
             bar.wait()
@@ -126,12 +129,13 @@ def _virtual_ranks_p2p(scale, ef, seed, world, src, mode, repeat=2):
     return out
 
 
+@pytest.mark.parametrize("loop", ["graph", "host"])
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
 @pytest.mark.parametrize("mode", ["push", "beamer"])
-def test_p2p_bfs_virtual_ranks(world, mode):
+def test_p2p_bfs_virtual_ranks(world, mode, loop):
     scale, ef, seed, src = 14, 16, 1, 0
     ref = oracle.bfs(oracle.rmat_csr(scale, ef, seed), src)
-    res = _virtual_ranks_p2p(scale, ef, seed, world, src, mode)
+    res = _virtual_ranks_p2p(scale, ef, seed, world, src, mode, loop=loop)
     labels = np.empty(1 << scale, np.int32)
     for r in range(world):
         labels[PT.global_ids(r, world, (1 << scale) // world)] = res[r][0]
