@@ -17,7 +17,7 @@
 namespace b200 {
 
 constexpr int SCAN_NT = 256, SCAN_VT = 4;
-constexpr int COMPACT_NT = 256, COMPACT_VT = 8;
+constexpr int COMPACT_NT = 256, COMPACT_VT = 8, BITLIST_VT = 4;
 constexpr int LBS_NT = 256, LBS_VT = 8, LBS_SEG_T = 512;
 constexpr uint32_t LBS_MIN_CHUNK = 2048;
 
@@ -65,6 +65,19 @@ cudaError_t launch_compact(b200_workspace *ws, Pred pred, uint32_t count, int *d
     if ((int64_t)tiles > ws->status_tiles) return cudaErrorInvalidValue;
     compact_kernel<COMPACT_NT, COMPACT_VT><<<tiles, COMPACT_NT, 0, ws_stream(ws)>>>(
         pred, count, d_out, capacity, next_lookback(ws, tiles), d_total, d_overflow);
+    ws->launches++;
+    return cudaGetLastError();
+}
+
+// bitmap (num_bits bits) -> ascending list of itf(idx) for every set bit idx.
+template <class WordFn, class ItemFn>
+cudaError_t launch_bitmap_list(b200_workspace *ws, WordFn wf, ItemFn itf, uint32_t num_bits, int *d_out, unsigned long long capacity,
+                               unsigned long long *d_total, unsigned long long *d_overflow) {
+    const uint32_t num_words = (num_bits + 31u) >> 5;
+    const uint32_t tiles = ceil_div<uint32_t>(num_words, COMPACT_NT * BITLIST_VT);
+    if ((int64_t)tiles > ws->status_tiles) return cudaErrorInvalidValue;
+    bitmap_list_kernel<COMPACT_NT, BITLIST_VT><<<tiles, COMPACT_NT, 0, ws_stream(ws)>>>(
+        wf, itf, num_words, d_out, capacity, next_lookback(ws, tiles), d_total, d_overflow, nullptr);
     ws->launches++;
     return cudaGetLastError();
 }

@@ -283,4 +283,99 @@ __global__ void __launch_bounds__(NT) compact_dyn_kernel(Pred pred, uint32_t cou
     }
 }
 
+// ---------------------------------------------------------------------------
+// Bitmap -> sorted list, one 32-bit WORD per thread item (popc + scan + bit walk) instead of one bit
+// per item through compact_kernel: 32x fewer scan items.  This is the pull -> push hand-over of the
+// direction-optimising BFS (the reference's dense frontier is an int per vertex, bfs_enactor.hxx:83,
+// and it never converts back); at scale 26 the bit-wise form took 0.24 ms of a 1.1 ms traversal.
+//   WordFn: uint32_t operator()(uint32_t w)   the w-th word of the bitmap
+//   ItemFn: int operator()(uint32_t idx)      the vertex id of bit idx
+// Stable (ascending idx).  clear_words (nullable): zeroed behind the read.
+// ---------------------------------------------------------------------------
+struct BitmapWords {          // a plain bitmap
+    const uint32_t *bm;
+    __device__ __forceinline__ uint32_t operator()(uint32_t w) const { return bm[w]; }
+};
+struct BitmapWordsDyn {       // one of two bitmaps, selected on the device (LoopDyn::bsel)
+    const LoopDyn *dyn;
+    const uint32_t *bm0, *bm1;
+    __device__ __forceinline__ uint32_t operator()(uint32_t w) const { return (dyn->bsel ? bm1 : bm0)[w]; }
+};
+struct IdentityItem {
+    __device__ __forceinline__ int operator()(uint32_t idx) const { return (int)idx; }
+};
+
+template <int NT, int VT, class WordFn, class ItemFn>
+__device__ __forceinline__ void bitmap_list_tile(const WordFn &wf, const ItemFn &itf, uint32_t num_words, uint32_t tile,
+                                                 const LookbackState &st, int *__restrict__ out, unsigned long long capacity,
+                                                 unsigned long long *total_out, unsigned long long *overflow_flag,
+                                                 uint32_t *clear_words, typename TileScan<NT, VT>::Smem &sm, uint32_t *s_bcast) {
+    using TS = TileScan<NT, VT>;
+    const uint32_t base = tile * TS::NV + (threadIdx.x >> 5) * (32 * VT) + lane_id();
+    uint32_t word[VT], c[VT], ex[VT];
+#pragma unroll
+    for (int i = 0; i < VT; ++i) {
+        const uint32_t w = base + i * 32;
+        word[i] = w < num_words ? wf(w) : 0u;
+        c[i] = __popc(word[i]);
+        if (clear_words && w < num_words) clear_words[w] = 0u;
+    }
+    const uint32_t total = TS::run(c, ex, sm);
+    const uint32_t excl = lookback_exclusive(st, tile, total, s_bcast);
+    bool over = false;
+#pragma unroll
+    for (int i = 0; i < VT; ++i) {
+        uint32_t bits = word[i];
+        unsigned long long dest = (unsigned long long)excl + ex[i];
+        const uint32_t idx0 = (base + i * 32) << 5;
+        while (bits) {
+            const uint32_t b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (dest < capacity) out[dest] = itf(idx0 + b);
+            else over = true;
+            ++dest;
+        }
+    }
+    if (over) *overflow_flag = 1ull;
+    if (tile == st.num_tiles - 1 && threadIdx.x == 0) *total_out = (unsigned long long)excl + total;
+}
+
+template <int NT, int VT, class WordFn, class ItemFn>
+__global__ void __launch_bounds__(NT) bitmap_list_kernel(WordFn wf, ItemFn itf, uint32_t num_words, int *__restrict__ out,
+                                                         unsigned long long capacity, LookbackState st,
+                                                         unsigned long long *total_out, unsigned long long *overflow_flag,
+                                                         uint32_t *clear_words) {
+    __shared__ typename TileScan<NT, VT>::Smem sm;
+    __shared__ uint32_t s_tile, s_bcast;
+    const uint32_t tile = claim_tile(st, &s_tile);
+    bitmap_list_tile<NT, VT>(wf, itf, num_words, tile, st, out, capacity, total_out, overflow_flag, clear_words, sm, &s_bcast);
+}
+
+// graph-driven loop form: writes the list dyn->in; persistent grid, look-back tag dyn->epoch + 1
+template <int NT, int VT, class WordFn, class ItemFn>
+__global__ void __launch_bounds__(NT) bitmap_list_dyn_kernel(WordFn wf, ItemFn itf, uint32_t num_words, const LoopDyn *dyn,
+                                                             uint32_t run_bit, unsigned long long capacity,
+                                                             unsigned long long *status, unsigned int *tile_counter,
+                                                             unsigned long long *total_out, unsigned long long *overflow_flag,
+                                                             uint32_t *clear_words) {
+    using TS = TileScan<NT, VT>;
+    __shared__ typename TS::Smem sm;
+    __shared__ uint32_t s_tile, s_bcast;
+    if (!(dyn->run & run_bit)) return;
+    int *out = const_cast<int *>(dyn->in);
+    LookbackState st;
+    st.status = status;
+    st.tile_counter = tile_counter;
+    st.epoch = (dyn->epoch + 1u) & 0x3FFFFFFFu;
+    st.num_tiles = (num_words + TS::NV - 1) / TS::NV;
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= st.num_tiles) break;
+        bitmap_list_tile<NT, VT>(wf, itf, num_words, tile, st, out, capacity, total_out, overflow_flag, clear_words, sm, &s_bcast);
+        __syncthreads();
+    }
+}
+
 }  // namespace b200

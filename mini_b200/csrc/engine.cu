@@ -503,8 +503,8 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
         } else if (!pull && was_pull) {
             // bitmap -> frontier list for the push levels that finish the traversal
             B200_CUDA(reset_counters(ws));
-            B200_CUDA(launch_compact(ws, BitmapPred{ctx->bm_frontier[bsel]}, (uint32_t)n, ctx->frontier[sel], (unsigned long long)n,
-                                     ws->d_counters + B200_CNT_OUT, ws->d_counters + B200_CNT_OVERFLOW));
+            B200_CUDA(launch_bitmap_list(ws, BitmapWords{ctx->bm_frontier[bsel]}, IdentityItem{}, (uint32_t)n, ctx->frontier[sel],
+                                         (unsigned long long)n, ws->d_counters + B200_CNT_OUT, ws->d_counters + B200_CNT_OVERFLOW));
         }
     }
     B200_CUDA(cudaEventRecord(ctx->ev_run[1], st));

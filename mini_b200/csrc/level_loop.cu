@@ -72,7 +72,7 @@ struct LevelLoop {
 
 namespace {
 
-constexpr int DYN_SCAN_CTAS_PER_SM = 4;
+constexpr int DYN_SCAN_CTAS_PER_SM = 8;   // 256-thread CTAs: the whole SM, as many tiles in flight as a count-sized grid has
 
 struct FrontierQuadsDyn {   // FrontierQuads over the device-selected frontier list
     const LoopDyn *dyn;
@@ -87,16 +87,6 @@ struct FrontierQuadsDyn {   // FrontierQuads over the device-selected frontier l
         }
         rows[i] = make_uint2(b, e);
         return e > b ? ((e - 1) >> 2) - (b >> 2) + 1u : 0u;
-    }
-};
-
-struct BitmapPredDyn {      // bit idx of the device-selected frontier bitmap
-    const LoopDyn *dyn;
-    const uint32_t *bm0, *bm1;
-    __device__ __forceinline__ bool operator()(uint32_t idx, int &item) const {
-        const uint32_t *bm = dyn->bsel ? bm1 : bm0;
-        item = (int)idx;
-        return (bm[idx >> 5] >> (idx & 31)) & 1u;
     }
 };
 
@@ -288,12 +278,13 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode)
         // transitions: list -> bitmap 0 (all-zero by invariant) | bitmap -> list (+ clears bitmap 0)
         sparse_to_bitmap_dyn_kernel<<<ws->num_sms * 4, 256, 0, cs>>>(dyn, ctx->bm_frontier[0]);
         LL_CUDA(cudaGetLastError());
-        const int64_t max_tiles = (n + COMPACT_NT * COMPACT_VT - 1) / (COMPACT_NT * COMPACT_VT);
+        const int64_t num_words = (n + 31) / 32;
+        const int64_t max_tiles = (num_words + COMPACT_NT * BITLIST_VT - 1) / (COMPACT_NT * BITLIST_VT);
         int64_t grid = (int64_t)ws->num_sms * DYN_SCAN_CTAS_PER_SM;
         if (grid > max_tiles) grid = max_tiles;
-        BitmapPredDyn pred{dyn, ctx->bm_frontier[0], ctx->bm_frontier[1]};
-        compact_dyn_kernel<COMPACT_NT, COMPACT_VT><<<(unsigned)grid, COMPACT_NT, 0, cs>>>(
-            pred, (uint32_t)n, dyn, (uint32_t)LOOP_RUN_TO_PUSH, (unsigned long long)n, ws->d_status, ws->d_tile_counter + 1,
+        bitmap_list_dyn_kernel<COMPACT_NT, BITLIST_VT><<<(unsigned)grid, COMPACT_NT, 0, cs>>>(
+            BitmapWordsDyn{dyn, ctx->bm_frontier[0], ctx->bm_frontier[1]}, IdentityItem{}, (uint32_t)num_words, dyn,
+            (uint32_t)LOOP_RUN_TO_PUSH, (unsigned long long)n, ws->d_status, ws->d_tile_counter + 1,
             ws->d_counters + B200_CNT_AUX2, ws->d_counters + B200_CNT_OVERFLOW, ctx->bm_frontier[0]);
         LL_CUDA(cudaGetLastError());
     }

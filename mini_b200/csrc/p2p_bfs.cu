@@ -242,13 +242,9 @@ __global__ void __launch_bounds__(256) p2p_gather_or_kernel(Peers peers, size_t 
     }
 }
 
-struct SliceListPred {   // bit r of the slice set -> emit the global id of local row r
-    const uint32_t *slice;
+struct PartItem {   // local row r of this rank -> its global vertex id
     Partition part;
-    __device__ __forceinline__ bool operator()(uint32_t idx, int &item) const {
-        item = (int)part.global_id(part.me, idx);
-        return (slice[idx >> 5] >> (idx & 31)) & 1u;
-    }
+    __device__ __forceinline__ int operator()(uint32_t idx) const { return (int)part.global_id(part.me, idx); }
 };
 
 
@@ -307,16 +303,6 @@ struct FrontierQuadsDynPart {   // FrontierQuads over the device-selected list, 
     }
 };
 
-struct SliceListPredDyn {   // SliceListPred over the device-selected slice
-    const LoopDyn *dyn;
-    const uint32_t *slice0, *slice1;
-    Partition part;
-    __device__ __forceinline__ bool operator()(uint32_t idx, int &item) const {
-        const uint32_t *slice = dyn->bsel ? slice1 : slice0;
-        item = (int)part.global_id(part.me, idx);
-        return (slice[idx >> 5] >> (idx & 31)) & 1u;
-    }
-};
 
 __global__ void p2p_loop_init_kernel(const P2PLoopParams *p, P2PLoopState *s, int32_t *labels, uint32_t *known, int32_t *f0,
                                      int32_t *f1, long long n, Partition part, unsigned long long *counters,
@@ -568,11 +554,11 @@ cudaError_t preload_kernels() {
     if ((e = preload(bfs_pull_kernel<256>)) != cudaSuccess) return e;
     if ((e = preload(scan_sizes_kernel<SCAN_NT, SCAN_VT, FrontierQuads>)) != cudaSuccess) return e;
     if ((e = preload(scan_sizes_kernel<SCAN_NT, SCAN_VT, FrontierDegree>)) != cudaSuccess) return e;
-    if ((e = preload(compact_kernel<COMPACT_NT, COMPACT_VT, SliceListPred>)) != cudaSuccess) return e;
+    if ((e = preload(bitmap_list_kernel<COMPACT_NT, BITLIST_VT, BitmapWords, PartItem>)) != cudaSuccess) return e;
     if ((e = preload(quad_advance_kernel<BfsPushPartQ, OUT_ROUTED, true, QUAD_NT, VT, QUAD_WSEG>)) != cudaSuccess) return e;
     if ((e = preload(quad_advance_kernel<BfsPushPartQDyn, OUT_ROUTED, true, QUAD_NT, VT, QUAD_WSEG>)) != cudaSuccess) return e;
     if ((e = preload(scan_sizes_dyn_kernel<SCAN_NT, SCAN_VT, FrontierQuadsDynPart>)) != cudaSuccess) return e;
-    if ((e = preload(compact_dyn_kernel<COMPACT_NT, COMPACT_VT, SliceListPredDyn>)) != cudaSuccess) return e;
+    if ((e = preload(bitmap_list_dyn_kernel<COMPACT_NT, BITLIST_VT, BitmapWordsDyn, PartItem>)) != cudaSuccess) return e;
     if ((e = preload(p2p_loop_init_kernel)) != cudaSuccess) return e;
     if ((e = preload(p2p_clear_slice_dyn_kernel)) != cudaSuccess) return e;
     if ((e = preload(p2p_publish_counts_dyn_kernel)) != cudaSuccess) return e;
@@ -688,7 +674,7 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
             LL_CUDA(cudaGetLastError());
         }
         const int64_t max_tiles = (s->n_local + SCAN_NT * SCAN_VT - 1) / (SCAN_NT * SCAN_VT);
-        int64_t grid = (int64_t)ws->num_sms * 4;
+        int64_t grid = (int64_t)ws->num_sms * 8;
         if (grid > max_tiles) grid = max_tiles;
         FrontierQuadsDynPart fn{dyn, g->row_offsets, reinterpret_cast<uint2 *>(ws->d_rows), part.log_p};
         scan_sizes_dyn_kernel<SCAN_NT, SCAN_VT><<<(unsigned)grid, SCAN_NT, 0, cs>>>(
@@ -738,13 +724,13 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
                                                                       (uint32_t)LOOP_RUN_TO_PUSH, reinterpret_cast<uint4 *>(s->full),
                                                                       reinterpret_cast<uint4 *>(s->known));
             LL_CUDA(cudaGetLastError());
-            const int64_t ctiles = (s->n_local + COMPACT_NT * COMPACT_VT - 1) / (COMPACT_NT * COMPACT_VT);
-            int64_t cgrid = (int64_t)ws->num_sms * 4;
+            const int64_t ctiles = ((int64_t)s->wl + COMPACT_NT * BITLIST_VT - 1) / (COMPACT_NT * BITLIST_VT);
+            int64_t cgrid = (int64_t)ws->num_sms * 8;
             if (cgrid > ctiles) cgrid = ctiles;
-            SliceListPredDyn pred{dyn, slice0, slice1, part};
-            compact_dyn_kernel<COMPACT_NT, COMPACT_VT><<<(unsigned)cgrid, COMPACT_NT, 0, cs>>>(
-                pred, (uint32_t)s->n_local, dyn, (uint32_t)LOOP_RUN_TO_PUSH, (unsigned long long)s->n_local, ws->d_status,
-                ws->d_tile_counter + 1, ws->d_counters + B200_CNT_AUX2, ws->d_counters + B200_CNT_OVERFLOW, nullptr);
+            bitmap_list_dyn_kernel<COMPACT_NT, BITLIST_VT><<<(unsigned)cgrid, COMPACT_NT, 0, cs>>>(
+                BitmapWordsDyn{dyn, slice0, slice1}, PartItem{part}, s->wl, dyn, (uint32_t)LOOP_RUN_TO_PUSH,
+                (unsigned long long)s->n_local, ws->d_status, ws->d_tile_counter + 1, ws->d_counters + B200_CNT_AUX2,
+                ws->d_counters + B200_CNT_OVERFLOW, nullptr);
             LL_CUDA(cudaGetLastError());
         }
     }
@@ -1141,9 +1127,9 @@ int b200_p2p_bfs_run(b200_p2p_bfs *s, const b200_graph *g, int64_t m_global, int
                 ws->launches++;
                 B200_CUDA(cudaGetLastError());
                 B200_CUDA(reset_counters(ws));
-                B200_CUDA(launch_compact(ws, SliceListPred{reinterpret_cast<const uint32_t *>(s->heap + s->off_slice[sb]), part},
-                                         (uint32_t)s->n_local, ctx->frontier[sel], (unsigned long long)s->n_local,
-                                         ws->d_counters + B200_CNT_OUT, ws->d_counters + B200_CNT_OVERFLOW));
+                B200_CUDA(launch_bitmap_list(ws, BitmapWords{reinterpret_cast<const uint32_t *>(s->heap + s->off_slice[sb])},
+                                             PartItem{part}, (uint32_t)s->n_local, ctx->frontier[sel], (unsigned long long)s->n_local,
+                                             ws->d_counters + B200_CNT_OUT, ws->d_counters + B200_CNT_OVERFLOW));
                 flen_local = next_local;
                 pull = false;
             }
