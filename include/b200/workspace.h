@@ -16,6 +16,7 @@ enum {
     B200_CNT_ARCS = 3,      /* arcs inspected (pull) */
     B200_CNT_AUX = 4,       /* next frontier's degree sum (fused), etc. */
     B200_CNT_AUX2 = 5,
+    B200_CNT_WORK = 6,      /* dynamic work claim of a kernel (pull: next bitmap chunk); zero at launch */
     B200_NUM_COUNTERS = 8
 };
 

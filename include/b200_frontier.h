@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 1
+#define B200_ABI_VERSION 2
 
 enum {
     B200_OK = 0,
@@ -62,6 +62,16 @@ typedef struct b200_graph {
     const uint32_t *col_offsets; /* d_col_offsets  [n+1] (CSC) */
     const int32_t *row_indices;  /* d_row_indices  [m]   (CSC) */
     const float *row_values;     /* d_row_values   [m] or NULL */
+    const uint32_t *no_in_arc_bitmap; /* optional derived data, like graph_device_t::d_scanned_row_offsets
+                                    (graph.hxx:52): [(n+31)/32] words, bit v set iff vertex v has no in-arc, built
+                                    once per graph by b200_graph_no_in_arc_bitmap; the direction-optimising BFS
+                                    starts its visited set from it so pull levels skip vertices nobody can reach.
+                                    NULL => computed at the start of every such traversal (one pass over the offsets) */
+    const int32_t *first_in_neighbor; /* optional derived data: [n], the first in-neighbour of every vertex (row_indices[
+                                    col_offsets[v]]) or -1, built once per graph by b200_graph_first_in_neighbor.  A pull
+                                    level resolves most vertices at their first in-arc (scale-26 level 1: 28 M of 32 M);
+                                    with this contiguous array they touch neither the offsets nor a random 32-byte
+                                    sector of the index array.  NULL => the pull kernel reads the CSC itself */
 } b200_graph;
 
 /* Built-in problems = the reference's data_slice_t structs, as one POD.
@@ -145,6 +155,17 @@ int b200_ctx_set_advance_impl(b200_ctx *ctx, int impl);
  *   B200_LOOP_HOST: one counter read-back and host decision per level (also the timing path). */
 enum { B200_LOOP_GRAPH = 0, B200_LOOP_HOST = 1 };
 int b200_ctx_set_level_loop(b200_ctx *ctx, int impl);
+
+/* The graph-driven level loop caches the instantiated traversal graph keyed by the addresses of the b200_graph
+ * arrays and of the labels buffer; array CONTENTS are read afresh by every traversal, so rewriting a graph in place
+ * needs nothing.  This drops the cached traversal graph (e.g. before freeing the buffers it references). */
+int b200_ctx_forget_graph(b200_ctx *ctx);
+
+/* Fills d_bitmap[(n+31)/32] for b200_graph::no_in_arc_bitmap (bit v set iff in-degree(v) == 0, from col_offsets --
+ * the CSC the pull advance walks, advance.hxx:108-160).  One-time per graph, beside graph_to_device (graph.hxx:60-83). */
+int b200_graph_no_in_arc_bitmap(b200_ctx *ctx, const b200_graph *g, uint32_t *d_bitmap);
+/* Fills d_out[n] for b200_graph::first_in_neighbor.  One-time per graph. */
+int b200_graph_first_in_neighbor(b200_ctx *ctx, const b200_graph *g, int32_t *d_out);
 
 /* ---- synthetic input (the reference has only load_graph, graph.hxx:96-223) */
 /* Symmetrised RMAT(0.57,0.19,0.19,0.05): n = 2^scale, m = 2*edge_factor*2^scale arcs,

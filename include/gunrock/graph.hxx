@@ -74,6 +74,8 @@ struct graph_device_t {
         g.col_offsets = reinterpret_cast<const uint32_t *>(d_col_offsets.data());
         g.row_indices = d_row_indices.data();
         g.row_values = d_row_values.data();
+        g.no_in_arc_bitmap = nullptr;   // the engine derives it per traversal
+        g.first_in_neighbor = nullptr;
         return g;
     }
 };

@@ -24,6 +24,46 @@ static void free_traversal_scratch(b200_ctx *ctx) {
     ctx->scratch_n = 0;
 }
 
+static __global__ void isolated_bitmap_kernel(const uint32_t *__restrict__ offsets, uint32_t n, uint32_t num_words, uint32_t *bm) {
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    for (uint32_t word = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; word < num_words; word += warps_total) {
+        const uint32_t v = (word << 5) + lane;
+        const bool iso = v < n && offsets[v + 1] == offsets[v];
+        const unsigned mask = __ballot_sync(0xffffffffu, iso);
+        if (lane == 0) bm[word] = mask;
+    }
+}
+
+static __global__ void first_in_neighbor_kernel(const uint32_t *__restrict__ offsets, const int32_t *__restrict__ indices,
+                                                unsigned long long n, int32_t *__restrict__ out) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+        const uint32_t b = offsets[v], e = offsets[v + 1];
+        out[v] = e > b ? indices[b] : -1;
+    }
+}
+
+cudaError_t launch_first_in_neighbor(b200_workspace *ws, const uint32_t *pull_offsets, const int32_t *pull_indices, int64_t n,
+                                     int32_t *d_out) {
+    first_in_neighbor_kernel<<<ws->num_sms * 8, 256, 0, (cudaStream_t)ws->stream>>>(pull_offsets, pull_indices,
+                                                                                    (unsigned long long)n, d_out);
+    ws->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t preload_no_in_arc_kernel() {
+    cudaFuncAttributes a;
+    return cudaFuncGetAttributes(&a, isolated_bitmap_kernel);
+}
+
+cudaError_t launch_no_in_arc_bitmap(b200_workspace *ws, const uint32_t *pull_offsets, int64_t n, uint32_t *d_bitmap) {
+    const int64_t words = (n + 31) / 32;
+    isolated_bitmap_kernel<<<ws->num_sms * 8, 256, 0, (cudaStream_t)ws->stream>>>(pull_offsets, (uint32_t)n, (uint32_t)words, d_bitmap);
+    ws->launches++;
+    return cudaGetLastError();
+}
+
 int ensure_traversal_scratch(b200_ctx *ctx, int64_t n) {
     if (n <= ctx->scratch_n) return B200_OK;
     B200_CUDA(cudaStreamSynchronize((cudaStream_t)ctx->ws.stream));
@@ -155,6 +195,27 @@ int b200_ctx_set_advance_impl(b200_ctx *ctx, int impl) {
 int b200_ctx_set_level_loop(b200_ctx *ctx, int impl) {
     if (!ctx || (impl != B200_LOOP_GRAPH && impl != B200_LOOP_HOST)) return B200_ERR_INVALID;
     ctx->loop_impl = impl;
+    return B200_OK;
+}
+
+int b200_ctx_forget_graph(b200_ctx *ctx) {
+    if (!ctx) return B200_ERR_INVALID;
+    level_loop_invalidate(ctx);
+    return B200_OK;
+}
+
+int b200_graph_first_in_neighbor(b200_ctx *ctx, const b200_graph *g, int32_t *d_out) {
+    if (!ctx || !g || !d_out || g->n < 1 || g->n > (1ll << 31)) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->ws.device));
+    B200_CUDA(launch_first_in_neighbor(&ctx->ws, g->col_offsets ? g->col_offsets : g->row_offsets,
+                                       g->row_indices ? g->row_indices : g->col_indices, g->n, d_out));
+    return B200_OK;
+}
+
+int b200_graph_no_in_arc_bitmap(b200_ctx *ctx, const b200_graph *g, uint32_t *d_bitmap) {
+    if (!ctx || !g || !d_bitmap || g->n < 1 || g->n > (1ll << 31)) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->ws.device));
+    B200_CUDA(launch_no_in_arc_bitmap(&ctx->ws, g->col_offsets ? g->col_offsets : g->row_offsets, g->n, d_bitmap));
     return B200_OK;
 }
 

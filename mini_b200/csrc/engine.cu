@@ -413,7 +413,13 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
     B200_CUDA(cudaEventRecord(ctx->ev_run[0], st));
     // bfs_problem_t ctor (bfs_problem.hxx:38-42) + init_frontier (bfs_enactor.hxx:34-38)
     B200_CUDA(cudaMemsetAsync(d_labels, 0xFF, sizeof(int32_t) * (size_t)n, st));
-    B200_CUDA(cudaMemsetAsync(ctx->bm_visited, 0, sizeof(uint32_t) * words, st));
+    if (mode == B200_BFS_PUSH) {
+        B200_CUDA(cudaMemsetAsync(ctx->bm_visited, 0, sizeof(uint32_t) * words, st));
+    } else if (g->no_in_arc_bitmap) {   // vertices without in-arcs start "visited": pull levels skip them (engine.cuh)
+        B200_CUDA(cudaMemcpyAsync(ctx->bm_visited, g->no_in_arc_bitmap, sizeof(uint32_t) * words, cudaMemcpyDeviceToDevice, st));
+    } else {
+        B200_CUDA(launch_no_in_arc_bitmap(ws, pull_off, n, ctx->bm_visited));
+    }
     bfs_init_kernel<<<1, 1, 0, st>>>(d_labels, ctx->bm_visited, ctx->frontier[0], src);
     ws->launches++;
     B200_CUDA(cudaGetLastError());
@@ -457,7 +463,8 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
             if (tl) B200_CUDA(cudaEventRecord(ev[3 * level + 1], st));
             bfs_pull_kernel<256><<<ws->num_sms * 8, 256, 0, st>>>((uint32_t)n, pull_off, pull_idx, ctx->bm_frontier[bsel],
                                                                   ctx->bm_frontier[bsel ^ 1], ctx->bm_visited, d_labels,
-                                                                  level + 1, ws->d_counters, Partition{0, 0, (uint32_t)n});
+                                                                  level + 1, ws->d_counters, Partition{0, 0, (uint32_t)n},
+                                                                  g->first_in_neighbor);
             ws->launches++;
             B200_CUDA(cudaGetLastError());
             if (tl) B200_CUDA(cudaEventRecord(ev[3 * level + 2], st));
@@ -703,6 +710,10 @@ int b200_host_graph_upload(b200_ctx *ctx, int64_t n, int64_t m, const uint32_t *
         if ((s = cuda_status(cudaMemcpyAsync(hg->d_row_offsets, h_row_offsets, sizeof(uint32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st)))) break;
         if (m && (s = cuda_status(cudaMemcpyAsync(hg->d_col_indices, h_col_indices, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, st)))) break;
         if (m && h_col_values && (s = cuda_status(cudaMemcpyAsync(hg->d_col_values, h_col_values, sizeof(float) * (size_t)m, cudaMemcpyHostToDevice, st)))) break;
+        if ((s = cuda_status(cudaMalloc(&hg->d_no_in_arc, sizeof(uint32_t) * (size_t)((n + 31) / 32 + 1))))) break;
+        if ((s = cuda_status(launch_no_in_arc_bitmap(&ctx->ws, hg->d_row_offsets, n, hg->d_no_in_arc)))) break;
+        if ((s = cuda_status(cudaMalloc(&hg->d_first_in_nbr, sizeof(int32_t) * (size_t)n)))) break;
+        if ((s = cuda_status(launch_first_in_neighbor(&ctx->ws, hg->d_row_offsets, hg->d_col_indices, n, hg->d_first_in_nbr)))) break;
         s = cuda_status(cudaStreamSynchronize(st));
     } while (0);
     if (s != B200_OK) {
@@ -722,6 +733,8 @@ int b200_host_graph_free(b200_ctx *ctx, b200_host_graph *hg) {
     cudaFree(hg->d_labels);
     cudaFree(hg->d_dist);
     cudaFree(hg->d_preds);
+    cudaFree(hg->d_no_in_arc);
+    cudaFree(hg->d_first_in_nbr);
     delete hg;
     return B200_OK;
 }
@@ -736,6 +749,8 @@ int b200_host_graph_view(const b200_host_graph *hg, b200_graph *out) {
     out->col_offsets = hg->d_row_offsets;   // symmetric graphs: CSC aliases CSR (graph.hxx:75-80)
     out->row_indices = hg->d_col_indices;
     out->row_values = hg->d_col_values;
+    out->no_in_arc_bitmap = hg->d_no_in_arc;
+    out->first_in_neighbor = hg->d_first_in_nbr;
     return B200_OK;
 }
 

@@ -35,6 +35,8 @@ struct b200_host_graph {
     int32_t *d_labels;   // result staging (BFS)
     float *d_dist;       // result staging (SSSP)
     int32_t *d_preds;
+    uint32_t *d_no_in_arc;   // b200_graph::no_in_arc_bitmap, built once at upload
+    int32_t *d_first_in_nbr; // b200_graph::first_in_neighbor
 };
 
 namespace b200 {
@@ -61,6 +63,16 @@ inline int cuda_status(cudaError_t e) {
     } while (0)
 
 int ensure_traversal_scratch(b200_ctx *ctx, int64_t n);
+// Pull levels walk every unvisited vertex; on RMAT half of them have no arc at all (scale 26: 34 M of 67 M) and
+// were re-inspected at every pull level.  The visited bitmap of a direction-optimising traversal therefore STARTS
+// as "vertex has no in-arc" instead of all-zero: such a vertex cannot be anybody's child, so no result changes
+// (labels stay -1), and whole words of them are skipped with one 4-byte read.  Source: b200_graph::no_in_arc_bitmap
+// if the caller built it once (b200_graph_no_in_arc_bitmap), else one pass over the offsets per traversal.
+cudaError_t launch_no_in_arc_bitmap(b200_workspace *ws, const uint32_t *pull_offsets, int64_t n, uint32_t *d_bitmap);
+// b200_graph::first_in_neighbor: out[v] = first in-neighbour of v, or -1 (see the pull kernel, advance.cuh)
+cudaError_t launch_first_in_neighbor(b200_workspace *ws, const uint32_t *pull_offsets, const int32_t *pull_indices, int64_t n,
+                                     int32_t *d_out);
+cudaError_t preload_no_in_arc_kernel();   // lazy module loading vs. spinning peer kernels, see p2p_bfs.cu
 
 // level_loop.cu
 int bfs_run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, float alpha, float beta, int32_t *d_labels,

@@ -62,7 +62,7 @@ struct LevelLoop {
     // one cached graph (rebuilt when the key changes)
     cudaGraph_t graph;
     cudaGraphExec_t exec;
-    const void *k_offsets, *k_indices, *k_labels, *k_scratch;
+    const void *k_offsets, *k_indices, *k_labels, *k_scratch, *k_iso, *k_first;
     int64_t k_n;
     int k_mode;
     int failed;          // status of the last failed build (the caller falls back to the host loop)
@@ -199,10 +199,10 @@ void drop_graph(LevelLoop *L) {
     if (L->graph) cudaGraphDestroy(L->graph);
     L->exec = nullptr;
     L->graph = nullptr;
-    L->k_offsets = L->k_indices = L->k_labels = L->k_scratch = nullptr;
+    L->k_offsets = L->k_indices = L->k_labels = L->k_scratch = L->k_iso = L->k_first = nullptr;
 }
 
-int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode) {
+int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode, const uint32_t *iso) {
     LevelLoop *L = ctx->loop;
     b200_workspace *ws = &ctx->ws;
     const int64_t n = g->n;
@@ -231,8 +231,13 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode)
     LL_CUDA(cudaStreamBeginCaptureToGraph(cs, G, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
     capturing = true;
     LL_CUDA(cudaMemsetAsync(d_labels, 0xFF, sizeof(int32_t) * (size_t)n, cs));
-    LL_CUDA(cudaMemsetAsync(ctx->bm_visited, 0, sizeof(uint32_t) * words, cs));
-    if (mode != B200_BFS_PUSH) LL_CUDA(cudaMemsetAsync(ctx->bm_frontier[0], 0, sizeof(uint32_t) * words, cs));
+    if (mode == B200_BFS_PUSH) {
+        LL_CUDA(cudaMemsetAsync(ctx->bm_visited, 0, sizeof(uint32_t) * words, cs));
+    } else {   // vertices without in-arcs start "visited" (engine.cuh); frontier bitmap 0 starts clean
+        if (iso) LL_CUDA(cudaMemcpyAsync(ctx->bm_visited, iso, sizeof(uint32_t) * words, cudaMemcpyDeviceToDevice, cs));
+        else LL_CUDA(launch_no_in_arc_bitmap(ws, pull_off, n, ctx->bm_visited));
+        LL_CUDA(cudaMemsetAsync(ctx->bm_frontier[0], 0, sizeof(uint32_t) * words, cs));
+    }
     loop_init_kernel<<<1, 1, 0, cs>>>(L->d_params, L->d_state, d_labels, ctx->bm_visited, ctx->frontier[0], ctx->frontier[1],
                                       (long long)n, ws->d_counters, ws->d_tile_counter);
     LL_CUDA(cudaGetLastError());
@@ -269,7 +274,8 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode)
         // pull level
         bfs_pull_dyn_kernel<256><<<ws->num_sms * 8, 256, 0, cs>>>((uint32_t)n, pull_off, pull_idx, ctx->bm_frontier[0],
                                                                   ctx->bm_frontier[1], ctx->bm_visited, d_labels, dyn,
-                                                                  ws->d_counters, Partition{0, 0, (uint32_t)n});
+                                                                  ws->d_counters, Partition{0, 0, (uint32_t)n},
+                                                                  g->first_in_neighbor);
         LL_CUDA(cudaGetLastError());
     }
     loop_decide_kernel<<<1, 1, 0, cs>>>(L->d_state, ws->d_counters, ws->d_tile_counter, L->d_result, h_while);
@@ -297,6 +303,8 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode)
     L->k_indices = g->col_indices;
     L->k_labels = d_labels;
     L->k_scratch = ctx->frontier[0];
+    L->k_iso = iso;
+    L->k_first = g->first_in_neighbor;
     L->k_n = n;
     L->k_mode = mode;
     ws->stream = user_stream;
@@ -360,10 +368,12 @@ int bfs_run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, flo
     b200_workspace *ws = &ctx->ws;
     cudaStream_t st = ws_stream(ws);
     if (L->failed) return B200_ERR_UNSUPPORTED;
+    const uint32_t *iso = mode != B200_BFS_PUSH ? g->no_in_arc_bitmap : nullptr;
     if (!L->exec || L->k_offsets != g->row_offsets || L->k_indices != g->col_indices || L->k_labels != d_labels ||
-        L->k_scratch != ctx->frontier[0] || L->k_n != g->n || L->k_mode != mode) {
+        L->k_scratch != ctx->frontier[0] || L->k_n != g->n || L->k_mode != mode || L->k_iso != iso ||
+        L->k_first != g->first_in_neighbor) {
         B200_CUDA(cudaStreamSynchronize(st));   // a replay of the old graph may still be running
-        const int bs = build_graph(ctx, g, d_labels, mode);
+        const int bs = build_graph(ctx, g, d_labels, mode, iso);
         if (bs != B200_OK) {
             L->failed = bs;
             return B200_ERR_UNSUPPORTED;

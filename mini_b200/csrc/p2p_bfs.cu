@@ -409,14 +409,15 @@ __global__ void __launch_bounds__(256) p2p_gather_or_dyn_kernel(Peers peers, siz
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) p2p_pull_dyn_kernel(uint32_t n_local, const uint32_t *__restrict__ offsets,
+__global__ void __launch_bounds__(NT, B200_PULL_MINB) p2p_pull_dyn_kernel(uint32_t n_local, const uint32_t *__restrict__ offsets,
                                                           const int *__restrict__ indices, const uint32_t *__restrict__ full,
                                                           uint32_t *slice0, uint32_t *slice1, uint32_t *__restrict__ known_slice,
                                                           int *__restrict__ labels, const LoopDyn *dyn,
-                                                          unsigned long long *counters, Partition part) {
+                                                          unsigned long long *counters, Partition part,
+                                                          const int *__restrict__ first_nbr) {
     if (!(dyn->run & LOOP_RUN_PULL)) return;
     bfs_pull_body<NT>(n_local, offsets, indices, full, dyn->bsel ? slice0 : slice1, known_slice, labels, dyn->next_label,
-                      counters, part);
+                      counters, part, first_nbr);
 }
 
 // Level summary (as p2p_stats_kernel) + the host loop's decision, on every rank identically.
@@ -545,6 +546,7 @@ cudaError_t preload(K k) {
 cudaError_t preload_kernels() {
     cudaError_t e;
     constexpr int VT = B200_QUAD_VT;
+    if ((e = preload_no_in_arc_kernel()) != cudaSuccess) return e;
     if ((e = preload(p2p_init_kernel)) != cudaSuccess) return e;
     if ((e = preload(p2p_publish_counts_kernel)) != cudaSuccess) return e;
     if ((e = preload(p2p_stats_kernel)) != cudaSuccess) return e;
@@ -599,7 +601,7 @@ struct b200_p2p_bfs {
     cudaStream_t cap_stream;
     cudaGraph_t graph;
     cudaGraphExec_t exec;
-    const void *k_offsets, *k_indices, *k_labels, *k_scratch;
+    const void *k_offsets, *k_indices, *k_labels, *k_scratch, *k_iso, *k_first;
     int k_mode;
     int graph_failed;
 };
@@ -611,7 +613,7 @@ void p2p_drop_graph(b200_p2p_bfs *s) {
     if (s->graph) cudaGraphDestroy(s->graph);
     s->exec = nullptr;
     s->graph = nullptr;
-    s->k_offsets = s->k_indices = s->k_labels = s->k_scratch = nullptr;
+    s->k_offsets = s->k_indices = s->k_labels = s->k_scratch = s->k_iso = s->k_first = nullptr;
 }
 
 int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int mode) {
@@ -649,6 +651,13 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
     capturing = true;
     LL_CUDA(cudaMemsetAsync(d_labels, 0xFF, sizeof(int32_t) * (size_t)s->n_local, cs));
     LL_CUDA(cudaMemsetAsync(s->known, 0, (size_t)(s->n_global / 8), cs));
+    if (beamer) {   // own rows without in-arcs start "known": pull levels skip them (engine.cuh)
+        uint32_t *own = s->known + (size_t)me * s->wl;
+        if (g->no_in_arc_bitmap)
+            LL_CUDA(cudaMemcpyAsync(own, g->no_in_arc_bitmap, sizeof(uint32_t) * (size_t)s->wl, cudaMemcpyDeviceToDevice, cs));
+        else
+            LL_CUDA(launch_no_in_arc_bitmap(ws, pull_off, s->n_local, own));
+    }
     p2p_loop_init_kernel<<<1, 1, 0, cs>>>(s->d_lparams, s->d_lstate, d_labels, s->known, ctx->frontier[0], ctx->frontier[1],
                                           (long long)s->n_global, part, ws->d_counters, ws->d_tile_counter, s->box_counts,
                                           kernels_per_level);
@@ -711,7 +720,8 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
                                                                       reinterpret_cast<uint4 *>(s->known));
             LL_CUDA(cudaGetLastError());
             p2p_pull_dyn_kernel<256><<<ws->num_sms * 8, 256, 0, cs>>>((uint32_t)s->n_local, pull_off, pull_idx, s->full, slice0, slice1,
-                                                                      s->known + (size_t)me * s->wl, d_labels, dyn, ws->d_counters, part);
+                                                                      s->known + (size_t)me * s->wl, d_labels, dyn, ws->d_counters, part,
+                                                                      g->first_in_neighbor);
             LL_CUDA(cudaGetLastError());
         }
         // level summary across the ranks + decision
@@ -743,6 +753,8 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
     s->k_indices = g->col_indices;
     s->k_labels = d_labels;
     s->k_scratch = ctx->frontier[0];
+    s->k_iso = g->no_in_arc_bitmap;
+    s->k_first = g->first_in_neighbor;
     s->k_mode = mode;
     ws->stream = user_stream;
     ws->launches = launches0;
@@ -774,7 +786,8 @@ int p2p_ensure_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, in
         B200_CUDA(cudaHostGetDevicePointer(&s->d_lresult, s->h_lresult, 0));
     }
     if (!s->exec || s->k_offsets != g->row_offsets || s->k_indices != g->col_indices || s->k_labels != d_labels ||
-        s->k_scratch != ctx->frontier[0] || s->k_mode != mode) {
+        s->k_scratch != ctx->frontier[0] || s->k_mode != mode || s->k_iso != g->no_in_arc_bitmap ||
+        s->k_first != g->first_in_neighbor) {
         B200_CUDA(cudaStreamSynchronize(st));
         const int bs = p2p_build_graph(s, g, d_labels, mode);
         if (bs != B200_OK) {
@@ -1017,6 +1030,13 @@ int b200_p2p_bfs_run(b200_p2p_bfs *s, const b200_graph *g, int64_t m_global, int
     B200_CUDA(cudaEventRecord(s->ev_run[0], st));
     B200_CUDA(cudaMemsetAsync(d_labels, 0xFF, sizeof(int32_t) * (size_t)s->n_local, st));
     B200_CUDA(cudaMemsetAsync(s->known, 0, (size_t)(n / 8), st));
+    if (mode == B200_BFS_BEAMER) {   // own rows without in-arcs start "known": pull levels skip them (engine.cuh)
+        uint32_t *own = s->known + (size_t)me * s->wl;
+        if (g->no_in_arc_bitmap)
+            B200_CUDA(cudaMemcpyAsync(own, g->no_in_arc_bitmap, sizeof(uint32_t) * (size_t)s->wl, cudaMemcpyDeviceToDevice, st));
+        else
+            B200_CUDA(launch_no_in_arc_bitmap(ws, pull_off, s->n_local, own));
+    }
     p2p_init_kernel<<<1, 1, 0, st>>>(d_labels, s->known, ctx->frontier[0], src, part);
     ws->launches++;
     B200_CUDA(cudaGetLastError());
@@ -1075,7 +1095,8 @@ int b200_p2p_bfs_run(b200_p2p_bfs *s, const b200_graph *g, int64_t m_global, int
             p2p_gather_or_kernel<<<ws->num_sms * 4, 256, 0, st>>>(s->peers, s->off_slice[sb], s->wl / 4, P,
                                                                   reinterpret_cast<uint4 *>(s->full), reinterpret_cast<uint4 *>(s->known));
             bfs_pull_kernel<256><<<ws->num_sms * 8, 256, 0, st>>>((uint32_t)s->n_local, pull_off, pull_idx, s->full, slice_w,
-                                                                  s->known + (size_t)me * s->wl, d_labels, level + 1, ws->d_counters, part);
+                                                                  s->known + (size_t)me * s->wl, d_labels, level + 1, ws->d_counters, part,
+                                                                  g->first_in_neighbor);
             ws->launches += 2;
             B200_CUDA(cudaGetLastError());
         }

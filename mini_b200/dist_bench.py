@@ -39,7 +39,7 @@ def run(args) -> int:
     ctx = mb.Context(dev)
     ctx.set_level_loop(mb.LOOP_HOST if getattr(args, "loop", "graph") == "host" else mb.LOOP_GRAPH)
     t0 = time.time()
-    g = D.build_rank_graph(ctx, scale, ef, 1, rank, world)
+    g = ctx.prepare_graph(D.build_rank_graph(ctx, scale, ef, 1, rank, world))
     build_s = time.time() - t0
     comm = D.TorchComm(ctx.torch_device)
     mode = "beamer" if args.mg_mode == "beamer" else "push"
@@ -152,7 +152,7 @@ def run(args) -> int:
     single = None
     if args.mg_single and rank == 0:
         try:
-            g1 = ctx.rmat_graph(scale, ef, 1)
+            g1 = ctx.prepare_graph(ctx.rmat_graph(scale, ef, 1))
             lab1 = torch.empty(g1.n, dtype=torch.int32, device=ctx.torch_device)
             single = {}
             for md, flag in (("beamer", mb.BFS_BEAMER), ("push", mb.BFS_PUSH)):

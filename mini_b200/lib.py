@@ -28,7 +28,7 @@ class B200Error(RuntimeError):
 class CGraph(C.Structure):
     _fields_ = [("n", C.c_int64), ("m", C.c_int64), ("row_offsets", C.c_void_p), ("col_indices", C.c_void_p),
                 ("col_values", C.c_void_p), ("col_offsets", C.c_void_p), ("row_indices", C.c_void_p),
-                ("row_values", C.c_void_p)]
+                ("row_values", C.c_void_p), ("no_in_arc_bitmap", C.c_void_p), ("first_in_neighbor", C.c_void_p)]
 
 
 class CProblem(C.Structure):
@@ -87,6 +87,9 @@ def load_library():
         "b200_ctx_l2_pin": ([vp, vp, i64], i32),
         "b200_ctx_set_advance_impl": ([vp, i32], i32),
         "b200_ctx_set_level_loop": ([vp, i32], i32),
+        "b200_ctx_forget_graph": ([vp], i32),
+        "b200_graph_no_in_arc_bitmap": ([vp, pg, vp], i32),
+        "b200_graph_first_in_neighbor": ([vp, pg, vp], i32),
         "b200_ctx_workspace": ([vp], vp),
         "b200_rmat_build_csr": ([vp, i32, i32, u64, vp, vp, vp, u64], i32),
         "b200_rmat_pairs": ([vp, i32, i32, u64, vp, vp], i32),
@@ -167,10 +170,13 @@ class Graph:
     def __init__(self, n: int, m: int, row_offsets, col_indices, col_values=None):
         self.n, self.m = int(n), int(m)
         self.row_offsets, self.col_indices, self.col_values = row_offsets, col_indices, col_values
+        self.no_in_arc = None   # derived data (Context.prepare_graph), like graph_device_t::d_scanned_row_offsets
+        self.first_in_nbr = None
 
     def cview(self) -> CGraph:
         return CGraph(self.n, self.m, _ptr(self.row_offsets), _ptr(self.col_indices), _ptr(self.col_values),
-                      _ptr(self.row_offsets), _ptr(self.col_indices), _ptr(self.col_values))
+                      _ptr(self.row_offsets), _ptr(self.col_indices), _ptr(self.col_values), _ptr(self.no_in_arc),
+                      _ptr(self.first_in_nbr))
 
     def offsets_host(self):
         import numpy as np
@@ -270,6 +276,19 @@ class Context:
         _check(self._L.b200_build_csr_from_pairs(self._h, n, k, _ptr(src), _ptr(dst), int(symmetrize), off.data_ptr(),
                                                  idx.data_ptr(), _ptr(w), weight_seed), "b200_build_csr_from_pairs")
         return Graph(n, m, off, idx[:m], None if w is None else w[:m])
+
+    def prepare_graph(self, g: Graph) -> Graph:
+        """One-time derived data of a graph (b200_graph_no_in_arc_bitmap, b200_graph_first_in_neighbor): lets the
+        pull levels of the direction-optimising BFS skip vertices without in-arcs and resolve most vertices from a
+        contiguous array.  Optional -- without it the engine derives the bitmap per traversal and reads the CSC."""
+        import torch
+        bm = torch.empty((g.n + 31) // 32 + 1, dtype=torch.int32, device=self.torch_device)
+        cg = g.cview()
+        _check(self._L.b200_graph_no_in_arc_bitmap(self._h, C.byref(cg), bm.data_ptr()), "b200_graph_no_in_arc_bitmap")
+        first = torch.empty(g.n, dtype=torch.int32, device=self.torch_device)
+        _check(self._L.b200_graph_first_in_neighbor(self._h, C.byref(cg), first.data_ptr()), "b200_graph_first_in_neighbor")
+        g.no_in_arc, g.first_in_nbr = bm, first
+        return g
 
     def graph_from_host(self, offsets, indices, weights=None) -> Graph:
         """numpy CSR (any integer offsets < 2^32) -> device Graph."""

@@ -11,14 +11,17 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=int, default=22)
 ap.add_argument("--runs", type=int, default=2)
 ap.add_argument("--prim", default="bfs")
+ap.add_argument("--loop", default="graph", choices=["graph", "host"])
+ap.add_argument("--timing", action="store_true", help="per-level CUDA-event timings (host loop)")
 a = ap.parse_args()
 ctx = mb.Context(0)
-g = ctx.rmat_graph(a.scale, 16, 1, weighted=a.prim == "sssp")
+ctx.set_level_loop(mb.LOOP_HOST if a.loop == "host" else mb.LOOP_GRAPH)
+g = ctx.prepare_graph(ctx.rmat_graph(a.scale, 16, 1, weighted=a.prim == "sssp"))
 for _ in range(a.runs):
     if a.prim == "bfs":
-        _, st = ctx.bfs(g, 0, mb.BFS_PUSH)
+        _, st = ctx.bfs(g, 0, mb.BFS_PUSH, timing=a.timing)
     elif a.prim == "bfs_beamer":
-        _, st = ctx.bfs(g, 0, mb.BFS_BEAMER, 15.0, 18.0)
+        _, st = ctx.bfs(g, 0, mb.BFS_BEAMER, 15.0, 18.0, timing=a.timing)
     elif a.prim == "sssp":
         _, st = ctx.sssp(g, 0)
     else:

@@ -37,7 +37,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_status_strings(lib):
-    assert lib.b200_abi_version() == 1
+    assert lib.b200_abi_version() == 2
     assert lib.b200_status_string(0) == b"ok"
     assert b"capacity" in lib.b200_status_string(3)
 

@@ -102,6 +102,8 @@ def _virtual_ranks_p2p(scale, ef, seed, world, src, mode, repeat=2, loop="graph"
             ctx = mb.Context(0, stream=None)
             ctx.set_level_loop(mb.LOOP_GRAPH if loop == "graph" else mb.LOOP_HOST)
             g = D.build_rank_graph(ctx, scale, ef, seed, rank, world)
+            if world in (2, 8):
+                g = ctx.prepare_graph(g)   # caller-owned "no in-arc" bitmap; the other worlds let the engine derive it
             bfs = P2PBfs(ctx, rank, world, n, (2 * ef) << scale, g)
             bases[rank] = bfs.heap_base
             bar.wait()

@@ -159,7 +159,8 @@ def test_graph_level_loop_is_used_and_matches_host_loop(mode):
     import mini_b200 as mb
     c = mb.Context(0)
     try:
-        graphs = [c.rmat_graph(14, 16, 1), c.rmat_graph(12, 8, 3), c.rmat_graph(14, 16, 1)]
+        # with and without the caller-owned "no in-arc" bitmap (b200_graph::no_in_arc_bitmap)
+        graphs = [c.rmat_graph(14, 16, 1), c.prepare_graph(c.rmat_graph(12, 8, 3)), c.prepare_graph(c.rmat_graph(14, 16, 1))]
         for g in graphs:
             for src in (0, 1, 77, g.n - 1):
                 c.set_level_loop(mb.LOOP_GRAPH)
