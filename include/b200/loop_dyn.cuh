@@ -20,7 +20,22 @@ struct LoopDyn {
     int next_label;      // level + 1
     uint32_t bsel;       // pull levels: which of the two frontier bitmaps is current
     uint32_t run;        // LOOP_RUN_* bits: which kernels of the loop body have work (the others return at once)
+    unsigned long long *trace;   // debug aid (B200_LOOP_TRACE=1): trace[0] = entries used, then (globaltimer ns << 8 | kernel id)
+    uint32_t trace_cap;
 };
+
+// Kernel-entry timestamps of the graph-driven loop: with no host between the levels there is nothing to hang CUDA
+// events on, so the kernels log their own start times (one thread, one atomic) when a trace buffer is attached.
+__device__ __forceinline__ void loop_trace(const LoopDyn *dyn, unsigned id) {
+#ifdef __CUDA_ARCH__
+    if (dyn->trace && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const unsigned long long k = atomicAdd(dyn->trace, 1ull);
+        if (k + 1 < dyn->trace_cap) dyn->trace[k + 1] = (t << 8) | id;
+    }
+#endif
+}
 
 // IF / SWITCH conditional nodes cost ~7 / ~4 us each on a B200 (profiles/microbench/graph_cond.cu) against
 // ~1.1 us for a kernel that returns immediately, so the loop body is a flat kernel sequence and every

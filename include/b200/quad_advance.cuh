@@ -108,6 +108,7 @@ quad_advance_kernel(QuadArgs a, Op op, int *__restrict__ out, unsigned long long
 
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5, lt_mask = lanemask_lt();
     if (a.dyn) {                             // level arguments decided on the device (loop_dyn.cuh)
+        loop_trace(a.dyn, 3);
         if (!(a.dyn->run & LOOP_RUN_PUSH)) return;
         a.frontier = a.dyn->in;
         a.num_segments = a.dyn->len;

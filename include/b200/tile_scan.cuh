@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(NT) scan_sizes_dyn_kernel(SizeFn fn, const Loo
     using TS = TileScan<NT, VT>;
     __shared__ typename TS::Smem sm;
     __shared__ uint32_t s_tile, s_bcast;
+    loop_trace(dyn, 2);
     if (!(dyn->run & run_bit)) return;
     const uint32_t count = dyn->len;
     LookbackState st;
@@ -361,6 +362,7 @@ __global__ void __launch_bounds__(NT) bitmap_list_dyn_kernel(WordFn wf, ItemFn i
     using TS = TileScan<NT, VT>;
     __shared__ typename TS::Smem sm;
     __shared__ uint32_t s_tile, s_bcast;
+    loop_trace(dyn, 11);
     if (!(dyn->run & run_bit)) return;
     int *out = const_cast<int *>(dyn->in);
     LookbackState st;

@@ -104,6 +104,8 @@ __global__ void loop_init_kernel(const LoopParams *p, LoopState *s, int32_t *lab
     s->dyn.next_label = 1;
     s->dyn.bsel = 0u;
     s->dyn.run = LOOP_RUN_PUSH;
+    s->dyn.trace = nullptr;
+    s->dyn.trace_cap = 0u;
     s->level = 0;
     s->pull = 0;
     s->mode = p->mode;

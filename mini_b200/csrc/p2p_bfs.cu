@@ -24,6 +24,8 @@
 // reaches after its own absorb.  Barrier waits carry a wall-clock timeout (B200_ERR_TIMEOUT)
 // so a lost peer cannot hang the GPU.
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "b200/operators.cuh"
@@ -264,6 +266,8 @@ struct P2PLoopParams {      // mapped pinned, read by the init kernel
     long long m_global;
     unsigned long long bar_epoch0;
     uint32_t lb_epoch0, stats_seq0;
+    unsigned long long *trace;
+    uint32_t trace_cap, pad;
 };
 struct P2PLevelRec {
     int32_t direction, pad;
@@ -322,6 +326,9 @@ __global__ void p2p_loop_init_kernel(const P2PLoopParams *p, P2PLoopState *s, in
     s->dyn.next_label = 1;
     s->dyn.bsel = 0u;
     s->dyn.run = LOOP_RUN_PUSH;
+    s->dyn.trace = p->trace;
+    s->dyn.trace_cap = p->trace_cap;
+    if (p->trace) p->trace[0] = 0ull;
     s->bar_epoch = p->bar_epoch0;
     s->stats_seq = p->stats_seq0;
     s->timeout = 0u;
@@ -345,6 +352,7 @@ __global__ void p2p_loop_init_kernel(const P2PLoopParams *p, P2PLoopState *s, in
 
 // the slice this level's discoveries are written to (slice[bsel ^ 1]) must start all-zero
 __global__ void p2p_clear_slice_dyn_kernel(const LoopDyn *dyn, uint4 *slice0, uint4 *slice1, uint32_t quads) {
+    loop_trace(dyn, 1);
     if (!(dyn->run & LOOP_RUN_PUSH)) return;
     uint4 *w = dyn->bsel ? slice0 : slice1;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += gridDim.x * blockDim.x) w[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -352,6 +360,7 @@ __global__ void p2p_clear_slice_dyn_kernel(const LoopDyn *dyn, uint4 *slice0, ui
 
 __global__ void __launch_bounds__(32) p2p_publish_counts_dyn_kernel(Peers peers, int me, int P, P2PLoopState *s,
                                                                     const unsigned long long *box_counts) {
+    loop_trace(&s->dyn, 4);
     if (!(s->dyn.run & LOOP_RUN_PUSH)) return;
     const int p = (int)lane_id();
     const unsigned long long epoch = s->bar_epoch + 1ull;
@@ -359,6 +368,7 @@ __global__ void __launch_bounds__(32) p2p_publish_counts_dyn_kernel(Peers peers,
     if (p < P && p != me) st_relaxed_sys(&reinterpret_cast<Ctrl *>(peers.base[p])->counts[me], box_counts[p]);
     const bool ok = p2p_signal_wait(peers, me, P, epoch);
     if (p == 0) {
+        loop_trace(&s->dyn, 13);
         s->bar_epoch = epoch;
         if (!ok) s->timeout = 1u;
     }
@@ -369,6 +379,7 @@ __global__ void __launch_bounds__(256) p2p_absorb_dyn_kernel(const int *__restri
                                                              int *labels, const LoopDyn *dyn, Partition part,
                                                              unsigned long long capacity, unsigned long long *next_count,
                                                              unsigned long long *counters, const uint32_t *__restrict__ offsets) {
+    loop_trace(dyn, 5);
     if (!(dyn->run & LOOP_RUN_PUSH)) return;
     p2p_absorb_body(inbox, seg_stride, counts, me, P, known, labels, dyn->next_label, part, dyn->out, capacity, next_count,
                     counters, offsets);
@@ -376,6 +387,7 @@ __global__ void __launch_bounds__(256) p2p_absorb_dyn_kernel(const int *__restri
 
 __global__ void p2p_list_to_slice_dyn_kernel(const LoopDyn *dyn, const unsigned long long *len_ptr, uint32_t *slice0,
                                              uint32_t *slice1, Partition part) {
+    loop_trace(dyn, 6);
     if (!(dyn->run & LOOP_RUN_PUSH)) return;
     const int *__restrict__ list = dyn->out;
     uint32_t *slice = dyn->bsel ? slice0 : slice1;
@@ -391,6 +403,7 @@ __global__ void __launch_bounds__(256) p2p_gather_or_dyn_kernel(Peers peers, siz
                                                                 uint32_t quads_per_slice, int P, const LoopDyn *dyn,
                                                                 uint32_t run_bit, uint4 *__restrict__ full,
                                                                 uint4 *__restrict__ known) {
+    loop_trace(dyn, run_bit == LOOP_RUN_PULL ? 7 : 10);
     if (!(dyn->run & run_bit)) return;
     const size_t slice_off = dyn->bsel ? off_slice1 : off_slice0;
     const size_t total = (size_t)quads_per_slice * (size_t)P;
@@ -415,6 +428,7 @@ __global__ void __launch_bounds__(NT, B200_PULL_MINB) p2p_pull_dyn_kernel(uint32
                                                           int *__restrict__ labels, const LoopDyn *dyn,
                                                           unsigned long long *counters, Partition part,
                                                           const int *__restrict__ first_nbr) {
+    loop_trace(dyn, 8);
     if (!(dyn->run & LOOP_RUN_PULL)) return;
     bfs_pull_body<NT>(n_local, offsets, indices, full, dyn->bsel ? slice0 : slice1, known_slice, labels, dyn->next_label,
                       counters, part, first_nbr);
@@ -426,6 +440,7 @@ __global__ void __launch_bounds__(32) p2p_stats_decide_kernel(Peers peers, int m
                                                               unsigned int *tile_counters, P2PLoopResult *res,
                                                               cudaGraphConditionalHandle h_while) {
     const int p = (int)lane_id();
+    loop_trace(&s->dyn, 9);
     const bool was_pull = s->pull != 0;
     const unsigned long long epoch = s->bar_epoch + 1ull;
     const int parity = (int)(s->stats_seq & 1u);
@@ -449,6 +464,7 @@ __global__ void __launch_bounds__(32) p2p_stats_decide_kernel(Peers peers, int m
         for (int k = 0; k < 8; ++k) st_relaxed_sys(dst + k, row[k]);
     }
     const bool ok = p2p_signal_wait(peers, me, P, epoch);
+    if (p == 0) loop_trace(&s->dyn, 12);
     unsigned long long mysum = 0;
     if (p < 8) {
         const Ctrl *mine = reinterpret_cast<const Ctrl *>(peers.base[me]);
@@ -601,6 +617,7 @@ struct b200_p2p_bfs {
     cudaStream_t cap_stream;
     cudaGraph_t graph;
     cudaGraphExec_t exec;
+    unsigned long long *d_trace;
     const void *k_offsets, *k_indices, *k_labels, *k_scratch, *k_iso, *k_first;
     int k_mode;
     int graph_failed;
@@ -820,6 +837,11 @@ int p2p_run_graph(b200_p2p_bfs *s, const b200_graph *g, int64_t m_global, int32_
     pr->bar_epoch0 = s->epoch;
     pr->lb_epoch0 = ws->epoch + 1;
     pr->stats_seq0 = s->stats_seq;
+    static const bool want_trace = getenv("B200_LOOP_TRACE") != nullptr;
+    constexpr uint32_t TRACE_CAP = 4096;
+    if (want_trace && !s->d_trace) B200_CUDA(cudaMalloc(&s->d_trace, sizeof(unsigned long long) * TRACE_CAP));
+    pr->trace = want_trace ? s->d_trace : nullptr;
+    pr->trace_cap = TRACE_CAP;
     s->h_lresult->status = -1;
     s->h_lresult->num_levels = 0;
     B200_CUDA(cudaEventRecord(s->ev_run[0], st));
@@ -828,6 +850,15 @@ int p2p_run_graph(b200_p2p_bfs *s, const b200_graph *g, int64_t m_global, int32_
     B200_CUDA(cudaEventSynchronize(s->ev_run[1]));
     const P2PLoopResult *r = s->h_lresult;
     if (r->status < 0) return B200_ERR_CUDA;
+    if (want_trace && s->rank == 0) {   // debug aid: kernel-entry timeline of rank 0 (ids: see loop_trace call sites)
+        static unsigned long long h[TRACE_CAP];
+        B200_CUDA(cudaMemcpy(h, s->d_trace, sizeof h, cudaMemcpyDeviceToHost));
+        const unsigned long long cnt = h[0] < TRACE_CAP - 1 ? h[0] : TRACE_CAP - 1;
+        fprintf(stderr, "B200_LOOP_TRACE rank0 %llu entries (us since first, kernel id):", cnt);
+        for (unsigned long long i = 1; i <= cnt; ++i)
+            fprintf(stderr, " %.1f:%llu", (double)((h[i] >> 8) - (h[1] >> 8)) * 1e-3, h[i] & 255ull);
+        fprintf(stderr, "\n");
+    }
     s->epoch = r->bar_epoch;
     s->stats_seq = r->stats_seq;
     const int levels = r->num_levels;
@@ -977,6 +1008,7 @@ int b200_p2p_bfs_destroy(b200_p2p_bfs *s) {
     p2p_drop_graph(s);
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
     if (s->d_lstate) cudaFree(s->d_lstate);
+    if (s->d_trace) cudaFree(s->d_trace);
     if (s->h_lparams) cudaFreeHost(s->h_lparams);
     if (s->h_lresult) cudaFreeHost(s->h_lresult);
     delete s;
