@@ -170,7 +170,14 @@ def run_reduce_leg(ctx, mb, args, peak):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     roof = _per_level(lambda: ctx.pr(g, 10, False, timing=True)[3], 3, reduce_level_bytes, peak)
-    roof["kernel"] = "neighborhood reduce kernel, fp32 plus (heaviest iteration: frontier = all vertices)"
+    roof["kernel"] = "quad_segreduce_kernel<float,PlusF32> (heaviest iteration: frontier = all vertices)"
+    roof["traffic"] = None
+    tp = os.path.join(ROOT, "profiles", "advance_traffic.json")
+    if scale == 24 and os.path.exists(tp):
+        try:
+            roof["traffic"] = json.load(open(tp)).get("scale24_reduce_top_launch_dram_bytes")
+        except Exception:
+            pass
     return {"workload": f"PageRank-style neighborhood_reduce fp32 pull-sum, RMAT scale-{scale} ef16 symmetrised "
                         f"(n={g.n}, m={g.m}), 10 iterations over the filter's dynamic frontiers",
             "value": st.total_arcs / (ms * 1e-3) / 1e9, "unit": "G arcs reduced/s", "ms_per_step": ms, "steps": steps,

@@ -548,6 +548,18 @@ struct SsspRelaxQ {
     }
 };
 
+// SsspRelaxQ whose iteration stamp comes from the device-resident level state (graph-driven loop).
+struct SsspRelaxQDyn : SsspRelaxQ {
+    const LoopDyn *dyn;
+    __device__ __forceinline__ int finish(Token old, const Cand &c) const {
+        if (!(__int_as_float((int)c.w[1]) < old)) return -1;
+        if (preds) preds[c.w[0]] = (int)c.w[2];
+        const int it = dyn->next_label - 1;
+        if (stamp && atomicExch(stamp + c.w[0], it) == it) return -1;
+        return (int)c.w[0];
+    }
+};
+
 // Deterministic predecessors once the distances are final: the smallest u with
 // dist[u] + w(u,v) == dist[v] (the reference's GPU preds are a race).
 struct SsspPredQ {

@@ -5,6 +5,7 @@
 #include <climits>
 #include <cmath>
 #include <cstring>
+#include <new>
 #include "b200/operators.cuh"
 #include "engine.cuh"
 
@@ -318,7 +319,19 @@ int b200_sparse_to_dense(b200_ctx *ctx, int64_t n, const int32_t *d_sparse, int6
 int b200_dense_to_sparse(b200_ctx *ctx, int64_t n, const uint32_t *d_bitmap, int32_t *d_sparse, int64_t capacity,
                          int64_t *out_len) {
     if (!ctx || !d_bitmap || !d_sparse) return B200_ERR_INVALID;
-    return compact_op(ctx, BitmapPred{d_bitmap}, n, d_sparse, capacity, out_len);
+    if (out_len) *out_len = 0;
+    if (n <= 0) return n == 0 ? B200_OK : B200_ERR_INVALID;
+    B200_TRY(check_counts(ctx, n));
+    b200_workspace *ws = &ctx->ws;
+    B200_CUDA(cudaSetDevice(ws->device));
+    B200_CUDA(reset_counters(ws));
+    // word-wise (tile_scan.cuh bitmap_list_kernel); bits past n in the last word must be clear
+    B200_CUDA(launch_bitmap_list(ws, BitmapWords{d_bitmap}, IdentityItem{}, (uint32_t)n, d_sparse, (unsigned long long)capacity,
+                                 ws->d_counters + B200_CNT_OUT, ws->d_counters + B200_CNT_OVERFLOW));
+    B200_CUDA(read_counters(ws));
+    if (ws->h_counters[B200_CNT_OVERFLOW]) return B200_ERR_OVERFLOW;
+    if (out_len) *out_len = (int64_t)ws->h_counters[B200_CNT_OUT];
+    return B200_OK;
 }
 
 int b200_gen_unvisited(b200_ctx *ctx, const b200_problem *p, int64_t n, int32_t *d_unvisited, int64_t capacity,
@@ -539,16 +552,33 @@ int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist
     cudaEvent_t *ev = timing ? level_events(ctx) : nullptr;
     const int64_t launches0 = ws->launches;
 
+    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(g->col_indices) && quad_aligned(g->col_values);
+    bool graph_done = false;
+    int sel = 0, it = 0;
+    int64_t flen = 1, total_arcs = 0;
+    if (quad && !timing && ctx->loop_impl == B200_LOOP_GRAPH) {
+        // the frontier iterations as one CUDA graph (level_loop.cu); the predecessor pass follows below
+        b200_stats *gst = stats ? stats : new (std::nothrow) b200_stats;
+        if (!gst) return B200_ERR_NOMEM;
+        const int gs = sssp_run_graph(ctx, g, src, d_dist, gst);
+        if (gs == B200_OK) {
+            graph_done = true;
+            it = gst->num_levels;
+            total_arcs = gst->total_arcs;
+        }
+        if (!stats) delete gst;
+        if (gs != B200_OK && gs != B200_ERR_UNSUPPORTED) {
+            return gs;
+        }
+    }
+    if (!graph_done) {
+    if (stats) stats->level_loop = B200_LOOP_HOST;
     B200_CUDA(cudaEventRecord(ctx->ev_run[0], st));
     // sssp_problem_t ctor (sssp_problem.hxx:44-49) + init_frontier (sssp_enactor.hxx:33-37)
     sssp_init_kernel<<<ws->num_sms * 4, 256, 0, st>>>(d_dist, d_preds, ctx->stamp, (unsigned long long)n);
     sssp_seed_kernel<<<1, 1, 0, st>>>(d_dist, ctx->frontier[0], src);
     ws->launches += 2;
     B200_CUDA(cudaGetLastError());
-
-    int sel = 0, it = 0;
-    int64_t flen = 1, total_arcs = 0;
-    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(g->col_indices) && quad_aligned(g->col_values);
     for (;;) {
         b200_level_stat *ls = (stats && it < B200_MAX_LEVELS) ? &stats->level[it] : nullptr;
         const bool tl = timing && it < B200_MAX_LEVELS;
@@ -585,6 +615,7 @@ int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist
         sel ^= 1;
         flen = found;
     }
+    }   // !graph_done
     if (d_preds) {
         iota_fill_kernel<<<ws->num_sms * 4, 256, 0, st>>>(ctx->frontier[0], d_preds, (unsigned long long)n);
         ws->launches++;

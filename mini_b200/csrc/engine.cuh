@@ -77,6 +77,7 @@ cudaError_t preload_no_in_arc_kernel();   // lazy module loading vs. spinning pe
 // level_loop.cu
 int bfs_run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, float alpha, float beta, int32_t *d_labels,
                   b200_stats *stats);
+int sssp_run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist, b200_stats *stats);
 void level_loop_invalidate(b200_ctx *ctx);
 void level_loop_destroy(b200_ctx *ctx);
 

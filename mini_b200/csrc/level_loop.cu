@@ -59,14 +59,17 @@ struct LevelLoop {
     LoopParams *h_params, *d_params;
     LoopResult *h_result, *d_result;
     cudaStream_t cap_stream;
-    // one cached graph (rebuilt when the key changes)
-    cudaGraph_t graph;
-    cudaGraphExec_t exec;
-    const void *k_offsets, *k_indices, *k_labels, *k_scratch, *k_iso, *k_first;
-    int64_t k_n;
-    int k_mode;
+    // one cached graph per primitive (rebuilt when its key changes)
+    struct Slot {
+        cudaGraph_t graph;
+        cudaGraphExec_t exec;
+        const void *k_offsets, *k_indices, *k_labels, *k_scratch, *k_iso, *k_first, *k_weights;
+        int64_t k_n;
+        int k_mode;
+    } slot[2];
     int failed;          // status of the last failed build (the caller falls back to the host loop)
 };
+enum { SLOT_BFS = 0, SLOT_SSSP = 1, MODE_SSSP = 100 };
 
 }  // namespace b200
 
@@ -90,12 +93,22 @@ struct FrontierQuadsDyn {   // FrontierQuads over the device-selected frontier l
     }
 };
 
-// bfs_problem_t ctor (bfs_problem.hxx:38-42) + init_frontier (bfs_enactor.hxx:34-38) + the loop state
+__global__ void sssp_loop_fill_kernel(float *dist, int32_t *stamp, unsigned long long n) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        dist[i] = 3.402823466e+38f;
+        stamp[i] = -1;
+    }
+}
+
+// bfs_problem_t ctor (bfs_problem.hxx:38-42) + init_frontier (bfs_enactor.hxx:34-38) + the loop state;
+// SSSP: labels holds float distances (sssp_problem.hxx:44-46: source 0.0f)
+template <bool SSSP>
 __global__ void loop_init_kernel(const LoopParams *p, LoopState *s, int32_t *labels, uint32_t *visited, int32_t *f0,
                                  int32_t *f1, long long n, unsigned long long *counters, unsigned int *tile_counters) {
     const int src = p->src;
-    labels[src] = 0;
-    visited[src >> 5] |= 1u << (src & 31);
+    labels[src] = 0;                         // depth 0 / +0.0f
+    if (!SSSP) visited[src >> 5] |= 1u << (src & 31);
     f0[0] = src;
     s->dyn.in = f0;
     s->dyn.out = f1;
@@ -140,7 +153,7 @@ __global__ void loop_decide_kernel(LoopState *s, unsigned long long *counters, u
         r->discovered = found;
     }
     s->total_arcs += arcs;
-    s->launches += s->mode == B200_BFS_PUSH ? 3 : 6;   // kernel nodes of the flat body (some return at once)
+    s->launches += (s->mode == B200_BFS_PUSH || s->mode == MODE_SSSP) ? 3 : 6;   // kernel nodes of the flat body (some return at once)
     ++level;
     s->level = level;
     bool done = false;
@@ -196,16 +209,22 @@ __global__ void loop_decide_kernel(LoopState *s, unsigned long long *counters, u
     cudaGraphSetConditional(h_while, done ? 0u : 1u);
 }
 
+void drop_slot(LevelLoop::Slot *S) {
+    if (S->exec) cudaGraphExecDestroy(S->exec);
+    if (S->graph) cudaGraphDestroy(S->graph);
+    std::memset(S, 0, sizeof *S);
+}
 void drop_graph(LevelLoop *L) {
-    if (L->exec) cudaGraphExecDestroy(L->exec);
-    if (L->graph) cudaGraphDestroy(L->graph);
-    L->exec = nullptr;
-    L->graph = nullptr;
-    L->k_offsets = L->k_indices = L->k_labels = L->k_scratch = L->k_iso = L->k_first = nullptr;
+    drop_slot(&L->slot[SLOT_BFS]);
+    drop_slot(&L->slot[SLOT_SSSP]);
 }
 
+// mode: a B200_BFS_* mode (d_labels = int32 labels) or MODE_SSSP (d_labels = float distances, reinterpreted)
 int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode, const uint32_t *iso) {
     LevelLoop *L = ctx->loop;
+    LevelLoop::Slot *S = &L->slot[mode == MODE_SSSP ? SLOT_SSSP : SLOT_BFS];
+    const bool sssp = mode == MODE_SSSP;
+    const bool has_pull = !sssp && mode != B200_BFS_PUSH;
     b200_workspace *ws = &ctx->ws;
     const int64_t n = g->n;
     const size_t words = (size_t)((n + 31) / 32);
@@ -224,7 +243,7 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
     cudaGraphNodeParams np_w = {};
     const LoopDyn *dyn = &L->d_state->dyn;
 
-    drop_graph(L);
+    drop_slot(S);
     ws->stream = (void *)cs;   // the launchers below record into the capture stream
     LL_CUDA(cudaGraphCreate(&G, 0));
     LL_CUDA(cudaGraphConditionalHandleCreate(&h_while, G, 1, cudaGraphCondAssignDefault));
@@ -232,16 +251,24 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
     // ---- prologue
     LL_CUDA(cudaStreamBeginCaptureToGraph(cs, G, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
     capturing = true;
-    LL_CUDA(cudaMemsetAsync(d_labels, 0xFF, sizeof(int32_t) * (size_t)n, cs));
-    if (mode == B200_BFS_PUSH) {
-        LL_CUDA(cudaMemsetAsync(ctx->bm_visited, 0, sizeof(uint32_t) * words, cs));
-    } else {   // vertices without in-arcs start "visited" (engine.cuh); frontier bitmap 0 starts clean
-        if (iso) LL_CUDA(cudaMemcpyAsync(ctx->bm_visited, iso, sizeof(uint32_t) * words, cudaMemcpyDeviceToDevice, cs));
-        else LL_CUDA(launch_no_in_arc_bitmap(ws, pull_off, n, ctx->bm_visited));
-        LL_CUDA(cudaMemsetAsync(ctx->bm_frontier[0], 0, sizeof(uint32_t) * words, cs));
+    if (sssp) {
+        // sssp_problem_t ctor (sssp_problem.hxx:44-49) + init_frontier (sssp_enactor.hxx:33-37)
+        sssp_loop_fill_kernel<<<ws->num_sms * 4, 256, 0, cs>>>(reinterpret_cast<float *>(d_labels), ctx->stamp, (unsigned long long)n);
+        LL_CUDA(cudaGetLastError());
+        loop_init_kernel<true><<<1, 1, 0, cs>>>(L->d_params, L->d_state, d_labels, nullptr, ctx->frontier[0], ctx->frontier[1],
+                                                (long long)n, ws->d_counters, ws->d_tile_counter);
+    } else {
+        LL_CUDA(cudaMemsetAsync(d_labels, 0xFF, sizeof(int32_t) * (size_t)n, cs));
+        if (mode == B200_BFS_PUSH) {
+            LL_CUDA(cudaMemsetAsync(ctx->bm_visited, 0, sizeof(uint32_t) * words, cs));
+        } else {   // vertices without in-arcs start "visited" (engine.cuh); frontier bitmap 0 starts clean
+            if (iso) LL_CUDA(cudaMemcpyAsync(ctx->bm_visited, iso, sizeof(uint32_t) * words, cudaMemcpyDeviceToDevice, cs));
+            else LL_CUDA(launch_no_in_arc_bitmap(ws, pull_off, n, ctx->bm_visited));
+            LL_CUDA(cudaMemsetAsync(ctx->bm_frontier[0], 0, sizeof(uint32_t) * words, cs));
+        }
+        loop_init_kernel<false><<<1, 1, 0, cs>>>(L->d_params, L->d_state, d_labels, ctx->bm_visited, ctx->frontier[0],
+                                                 ctx->frontier[1], (long long)n, ws->d_counters, ws->d_tile_counter);
     }
-    loop_init_kernel<<<1, 1, 0, cs>>>(L->d_params, L->d_state, d_labels, ctx->bm_visited, ctx->frontier[0], ctx->frontier[1],
-                                      (long long)n, ws->d_counters, ws->d_tile_counter);
     LL_CUDA(cudaGetLastError());
     capturing = false;
     if ((st = end_capture(cs, deps, &ndeps, 8)) != B200_OK) goto fail;
@@ -266,13 +293,18 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
         scan_sizes_dyn_kernel<SCAN_NT, SCAN_VT><<<(unsigned)grid, SCAN_NT, 0, cs>>>(
             fn, dyn, (uint32_t)LOOP_RUN_PUSH, ws->d_scanned, ws->d_status, ws->d_tile_counter, ws->d_counters + B200_CNT_TOTAL);
         LL_CUDA(cudaGetLastError());
-        QuadArgs a = make_quad_args(ws, ctx->frontier[0], 0u, g->row_offsets, g->col_indices, nullptr);
+        QuadArgs a = make_quad_args(ws, ctx->frontier[0], 0u, g->row_offsets, g->col_indices, sssp ? g->col_values : nullptr);
         a.dyn = dyn;
-        BfsPushQDyn op{{ctx->bm_visited, d_labels, 0}, dyn};
-        if (deg) LL_CUDA((launch_quad_advance<OUT_COMPACT, true>(ws, a, op, ctx->frontier[1], (unsigned long long)n)));
-        else LL_CUDA((launch_quad_advance<OUT_COMPACT, false>(ws, a, op, ctx->frontier[1], (unsigned long long)n)));
+        if (sssp) {
+            SsspRelaxQDyn op{{reinterpret_cast<float *>(d_labels), nullptr, ctx->stamp, 0}, dyn};   // preds: one exact pass at the end
+            LL_CUDA((launch_quad_advance<OUT_COMPACT, false>(ws, a, op, ctx->frontier[1], (unsigned long long)n)));
+        } else {
+            BfsPushQDyn op{{ctx->bm_visited, d_labels, 0}, dyn};
+            if (deg) LL_CUDA((launch_quad_advance<OUT_COMPACT, true>(ws, a, op, ctx->frontier[1], (unsigned long long)n)));
+            else LL_CUDA((launch_quad_advance<OUT_COMPACT, false>(ws, a, op, ctx->frontier[1], (unsigned long long)n)));
+        }
     }
-    if (mode != B200_BFS_PUSH) {
+    if (has_pull) {
         // pull level
         bfs_pull_dyn_kernel<256><<<ws->num_sms * 8, 256, 0, cs>>>((uint32_t)n, pull_off, pull_idx, ctx->bm_frontier[0],
                                                                   ctx->bm_frontier[1], ctx->bm_visited, d_labels, dyn,
@@ -282,7 +314,7 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
     }
     loop_decide_kernel<<<1, 1, 0, cs>>>(L->d_state, ws->d_counters, ws->d_tile_counter, L->d_result, h_while);
     LL_CUDA(cudaGetLastError());
-    if (mode != B200_BFS_PUSH) {
+    if (has_pull) {
         // transitions: list -> bitmap 0 (all-zero by invariant) | bitmap -> list (+ clears bitmap 0)
         sparse_to_bitmap_dyn_kernel<<<ws->num_sms * 4, 256, 0, cs>>>(dyn, ctx->bm_frontier[0]);
         LL_CUDA(cudaGetLastError());
@@ -299,16 +331,17 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
     capturing = false;
     if ((st = end_capture(cs, deps, &ndeps, 8)) != B200_OK) goto fail;
 
-    LL_CUDA(cudaGraphInstantiate(&L->exec, G, 0));
-    L->graph = G;
-    L->k_offsets = g->row_offsets;
-    L->k_indices = g->col_indices;
-    L->k_labels = d_labels;
-    L->k_scratch = ctx->frontier[0];
-    L->k_iso = iso;
-    L->k_first = g->first_in_neighbor;
-    L->k_n = n;
-    L->k_mode = mode;
+    LL_CUDA(cudaGraphInstantiate(&S->exec, G, 0));
+    S->graph = G;
+    S->k_offsets = g->row_offsets;
+    S->k_indices = g->col_indices;
+    S->k_weights = g->col_values;
+    S->k_labels = d_labels;
+    S->k_scratch = ctx->frontier[0];
+    S->k_iso = iso;
+    S->k_first = g->first_in_neighbor;
+    S->k_n = n;
+    S->k_mode = mode;
     ws->stream = user_stream;
     ws->launches = launches0;
     return B200_OK;
@@ -361,19 +394,20 @@ static int level_loop_get(b200_ctx *ctx) {
     return B200_OK;
 }
 
-// b200_bfs_run through the graph.  Returns B200_ERR_UNSUPPORTED when the graph cannot be built on this
+// b200_bfs_run / b200_sssp_run through the graph.  Returns B200_ERR_UNSUPPORTED when the graph cannot be built on this
 // driver (the caller then runs the host-driven loop and reports level_loop = host in the stats).
-int bfs_run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, float alpha, float beta, int32_t *d_labels,
-                  b200_stats *stats) {
+static int run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, float alpha, float beta, int32_t *d_labels,
+                     b200_stats *stats) {
     B200_TRY(level_loop_get(ctx));
     LevelLoop *L = ctx->loop;
+    LevelLoop::Slot *S = &L->slot[mode == MODE_SSSP ? SLOT_SSSP : SLOT_BFS];
     b200_workspace *ws = &ctx->ws;
     cudaStream_t st = ws_stream(ws);
     if (L->failed) return B200_ERR_UNSUPPORTED;
-    const uint32_t *iso = mode != B200_BFS_PUSH ? g->no_in_arc_bitmap : nullptr;
-    if (!L->exec || L->k_offsets != g->row_offsets || L->k_indices != g->col_indices || L->k_labels != d_labels ||
-        L->k_scratch != ctx->frontier[0] || L->k_n != g->n || L->k_mode != mode || L->k_iso != iso ||
-        L->k_first != g->first_in_neighbor) {
+    const uint32_t *iso = (mode != B200_BFS_PUSH && mode != MODE_SSSP) ? g->no_in_arc_bitmap : nullptr;
+    if (!S->exec || S->k_offsets != g->row_offsets || S->k_indices != g->col_indices || S->k_labels != d_labels ||
+        S->k_scratch != ctx->frontier[0] || S->k_n != g->n || S->k_mode != mode || S->k_iso != iso ||
+        S->k_first != g->first_in_neighbor || S->k_weights != g->col_values) {
         B200_CUDA(cudaStreamSynchronize(st));   // a replay of the old graph may still be running
         const int bs = build_graph(ctx, g, d_labels, mode, iso);
         if (bs != B200_OK) {
@@ -395,7 +429,7 @@ int bfs_run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, flo
     L->h_result->status = -1;
     L->h_result->num_levels = 0;
     B200_CUDA(cudaEventRecord(ctx->ev_run[0], st));
-    B200_CUDA(cudaGraphLaunch(L->exec, st));
+    B200_CUDA(cudaGraphLaunch(S->exec, st));
     B200_CUDA(cudaEventRecord(ctx->ev_run[1], st));
     B200_CUDA(cudaEventSynchronize(ctx->ev_run[1]));
     const LoopResult *r = L->h_result;
@@ -428,6 +462,17 @@ int bfs_run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, flo
         }
     }
     return r->status;
+}
+
+int bfs_run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, float alpha, float beta, int32_t *d_labels,
+                  b200_stats *stats) {
+    return run_graph(ctx, g, src, mode, alpha, beta, d_labels, stats);
+}
+
+// The Bellman-Ford frontier iterations of b200_sssp_run (sssp_enactor.hxx:40-72) through the graph: distances final at
+// return; the caller adds the predecessor pass.  ev_run[0] is recorded at the start of the traversal.
+int sssp_run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist, b200_stats *stats) {
+    return run_graph(ctx, g, src, MODE_SSSP, 0.f, 0.f, reinterpret_cast<int32_t *>(d_dist), stats);
 }
 
 }  // namespace b200

@@ -174,6 +174,15 @@ def test_graph_level_loop_is_used_and_matches_host_loop(mode):
                 key = lambda st: [(l["direction"], l["frontier_len"], l["arcs"], l["discovered"]) for l in st.levels]
                 assert key(sa) == key(sb)
                 assert sa.launches > 0
+        # SSSP: the Bellman-Ford frontier iterations replay as a graph too (bit-identical distances)
+        gw = c.rmat_graph(13, 16, 1, weighted=True)
+        c.set_level_loop(mb.LOOP_GRAPH)
+        da, sa = c.sssp(gw, 0)
+        assert sa.level_loop == "graph"
+        c.set_level_loop(mb.LOOP_HOST)
+        db, sb = c.sssp(gw, 0)
+        assert sb.level_loop == "host"
+        assert da.cpu().numpy().tobytes() == db.cpu().numpy().tobytes()
         # a long path: many levels through the same graph replay (tags, ping-pong, counters re-armed every level)
         n = 3000
         o = oracle.build_csr(n, np.arange(n - 1, dtype=np.int32), np.arange(1, n, dtype=np.int32), True, False)
@@ -434,6 +443,64 @@ def test_neighborhood_reduce_vs_fp64(ctx, op):
                 assert np.array_equal(got, ref.astype(np.float32))          # min/max are exact
             empty = (o.offsets[frontier + 1] - o.offsets[frontier]) == 0
             assert np.all(got[empty] == -3.0)                               # identity only for empty segments
+
+
+def test_neighborhood_reduce_holes_hub_rows_and_scatter(ctx):
+    """Frontier holes (-1) read as empty neighbourhoods; one row far longer than a warp / CTA chunk next to many
+    one-arc rows (partials from many warps meet in one slot); vertex-indexed (scatter) output."""
+    import mini_b200 as mb
+    rng = np.random.default_rng(11)
+    n, hub_deg = 70000, 60000
+    src = np.concatenate([np.zeros(hub_deg, np.int32), rng.integers(1, n, 20000).astype(np.int32)])
+    dst = np.concatenate([rng.permutation(np.arange(1, n, dtype=np.int32))[:hub_deg], rng.integers(1, n, 20000).astype(np.int32)])
+    o = oracle.build_csr(n, src, dst, True, False)
+    g = _dev_graph(ctx, o)
+    vals = (rng.random(n) + 0.25).astype(np.float32)
+    frontier = rng.permutation(n)[: n // 2].astype(np.int32)
+    frontier[0] = 0                                   # the hub
+    holes = rng.random(len(frontier)) < 0.1
+    holes[0] = False
+    f_h = np.where(holes, -1, frontier).astype(np.int32)
+    ref, asum = oracle.neighborhood_reduce(o, frontier, vals.astype(np.float64), "plus", identity=-7.0)
+    ref = np.where(holes, -7.0, ref)
+    red = torch.full((len(f_h),), 99.0, dtype=torch.float32, device="cuda")
+    arcs = ctx.neighborhood_reduce(g, torch.from_numpy(f_h).cuda(), torch.from_numpy(vals).cuda(), red, identity=-7.0,
+                                   op=mb.OP_PLUS)
+    deg = o.offsets[frontier + 1] - o.offsets[frontier]
+    assert arcs == int(deg[~holes].sum())
+    _check_reduce(red.cpu().numpy(), ref, np.where(holes, 0.0, asum))
+    for opn, opc in (("min", mb.OP_MIN), ("max", mb.OP_MAX)):
+        r2, _ = oracle.neighborhood_reduce(o, frontier, vals.astype(np.float64), opn, identity=-7.0)
+        r2 = np.where(holes, -7.0, r2).astype(np.float32)
+        ctx.neighborhood_reduce(g, torch.from_numpy(f_h).cuda(), torch.from_numpy(vals).cuda(), red, identity=-7.0, op=opc)
+        assert np.array_equal(red.cpu().numpy(), r2)
+    # scatter: reduced[v] for the (distinct) frontier vertices, everything else untouched
+    uniq = np.unique(frontier[~holes]).astype(np.int32)
+    rs = torch.full((n,), 5.0, dtype=torch.float32, device="cuda")
+    ctx.neighborhood_reduce(g, torch.from_numpy(uniq).cuda(), torch.from_numpy(vals).cuda(), rs, identity=-7.0,
+                            op=mb.OP_PLUS, scatter=True)
+    ref_u, asum_u = oracle.neighborhood_reduce(o, uniq, vals.astype(np.float64), "plus", identity=-7.0)
+    got = rs.cpu().numpy()
+    _check_reduce(got[uniq], ref_u, asum_u)
+    mask = np.ones(n, bool)
+    mask[uniq] = False
+    assert np.all(got[mask] == 5.0)
+
+
+def test_dense_to_sparse_ragged_sizes(ctx):
+    """word-wise bitmap -> list: sizes that are not multiples of 32 / of the tile, empty and full bitmaps."""
+    rng = np.random.default_rng(5)
+    for n in (1, 31, 32, 33, 1000, 32768, 32769, 200003):
+        for density in (0.0, 0.02, 0.5, 1.0):
+            bits = rng.random(n) < density if 0.0 < density < 1.0 else np.full(n, density == 1.0)
+            words = np.zeros((n + 31) // 32, np.uint32)
+            idx = np.nonzero(bits)[0]
+            np.bitwise_or.at(words, idx >> 5, (np.uint32(1) << (idx & 31).astype(np.uint32)))
+            bm = torch.from_numpy(words.view(np.int32)).cuda()
+            out = torch.full((n,), -5, dtype=torch.int32, device="cuda")
+            k = ctx.dense_to_sparse(n, bm, out)
+            assert k == len(idx)
+            assert np.array_equal(out.cpu().numpy()[:k], idx.astype(np.int32))
 
 
 def test_neighborhood_reduce_nonfinite_values_read_as_zero(ctx):
