@@ -87,9 +87,17 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+WORK_CREATE = False   # --advance workcreate: the advance launch also produces the next level's scan
+
+
 def push_level_bytes(level, offset_bytes=4):
-    """Algorithmic bytes of one push level: |F|(4+2*O) + m_F*(4+4) + |F_next|*(4+4)."""
-    return level["frontier_len"] * (4 + 2 * offset_bytes) + level["arcs"] * 8 + level["discovered"] * 8
+    """Algorithmic bytes of one push level: |F|(4+2*O) + m_F*(4+4) + |F_next|*(4+4); the work-creating
+    advance additionally reads two offsets and writes row bounds + scan position per emitted vertex (the scan
+    kernel's bytes, moved into this launch)."""
+    b = level["frontier_len"] * (4 + 2 * offset_bytes) + level["arcs"] * 8 + level["discovered"] * 8
+    if WORK_CREATE:
+        b += level["discovered"] * (2 * offset_bytes + 8 + 4)
+    return b
 
 
 def sssp_level_bytes(level, offset_bytes=4):
@@ -244,7 +252,9 @@ def run_single_gpu(args):
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
     ctx = mb.Context(dev)
-    ctx.set_advance_impl(mb.ADVANCE_LBS if args.advance == "lbs" else mb.ADVANCE_QUAD)
+    global WORK_CREATE
+    WORK_CREATE = args.advance == "workcreate"
+    ctx.set_advance_impl({"lbs": mb.ADVANCE_LBS, "workcreate": mb.ADVANCE_QUAD_WORKCREATE}.get(args.advance, mb.ADVANCE_QUAD))
     ctx.set_level_loop(mb.LOOP_HOST if args.loop == "host" else mb.LOOP_GRAPH)
     g = ctx.prepare_graph(ctx.rmat_graph(scale, 16, 1))   # graph build + one-time derived data: outside the timed region
     mode = {"push": mb.BFS_PUSH, "beamer": mb.BFS_BEAMER}[args.mode]
@@ -291,7 +301,7 @@ def run_single_gpu(args):
         except Exception:
             traffic = None
     roofline = {
-        "bound": "hbm", "kernel": ("quad_advance_kernel<BfsPushQ,COMPACT>" if args.advance == "quad" else "lbs_advance_kernel<BfsPushOp,COMPACT>") + " (heaviest BFS level)",
+        "bound": "hbm", "kernel": ("quad_advance_kernel<BfsPushQ,COMPACT>" if args.advance != "lbs" else "lbs_advance_kernel<BfsPushOp,COMPACT>") + " (heaviest BFS level)",
         "achieved": top_gbs, "peak": peak, "unit": "GB/s", "frac": top_gbs / peak, "traffic": traffic,
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": push_level_bytes(lv[top]), "launch_ms": lv_ms[top],
@@ -379,8 +389,9 @@ def main():
     ap.add_argument("--scale", type=int, default=0)
     ap.add_argument("--mode", default="push", choices=["push", "beamer"])
     ap.add_argument("--cpu-runs", type=int, default=3)
-    ap.add_argument("--advance", default="quad", choices=["quad", "lbs"],
-                    help="push-advance kernel: quad_advance.cuh (default) or the first-generation advance.cuh")
+    ap.add_argument("--advance", default="quad", choices=["quad", "workcreate", "lbs"],
+                    help="push-advance kernel: quad_advance.cuh (default), the same creating the next level's scan, "
+                         "or the first-generation advance.cuh")
     ap.add_argument("--loop", default="graph", choices=["graph", "host"],
                     help="N=1 BFS level loop: one CUDA graph with device-side decisions, or host-driven")
     ap.add_argument("--extras", default="sssp,reduce",

@@ -9,6 +9,7 @@
 // it; NULL means "use the by-value arguments" (the host-driven loop and the operator API).
 #pragma once
 #include <stdint.h>
+#include <cuda_runtime.h>
 
 namespace b200 {
 
@@ -20,6 +21,12 @@ struct LoopDyn {
     int next_label;      // level + 1
     uint32_t bsel;       // pull levels: which of the two frontier bitmaps is current
     uint32_t run;        // LOOP_RUN_* bits: which kernels of the loop body have work (the others return at once)
+    // work-creating advance (NULL when the loop re-scans every level): this level's / the next level's quad scan and
+    // row bounds, swapped by the decide step like in / out
+    uint32_t *scanned_in;
+    uint2 *rows_in;
+    uint32_t *scanned_out;
+    uint2 *rows_out;
     unsigned long long *trace;   // debug aid (B200_LOOP_TRACE=1): trace[0] = entries used, then (globaltimer ns << 8 | kernel id)
     uint32_t trace_cap;
 };
@@ -40,6 +47,7 @@ __device__ __forceinline__ void loop_trace(const LoopDyn *dyn, unsigned id) {
 // IF / SWITCH conditional nodes cost ~7 / ~4 us each on a B200 (profiles/microbench/graph_cond.cu) against
 // ~1.1 us for a kernel that returns immediately, so the loop body is a flat kernel sequence and every
 // kernel checks its bit.
-enum : uint32_t { LOOP_RUN_PUSH = 1u, LOOP_RUN_PULL = 2u, LOOP_RUN_TO_PULL = 4u, LOOP_RUN_TO_PUSH = 8u };
+enum : uint32_t { LOOP_RUN_PUSH = 1u, LOOP_RUN_PULL = 2u, LOOP_RUN_TO_PULL = 4u, LOOP_RUN_TO_PUSH = 8u,
+                  LOOP_RUN_SCAN = 16u };   // the push level's frontier has no scan yet (first level, after a hand-over)
 
 }  // namespace b200

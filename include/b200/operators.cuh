@@ -185,6 +185,8 @@ inline QuadArgs make_quad_args(const b200_workspace *ws, const int *d_frontier, 
     a.min_chunk = QUAD_MIN_CHUNK;
     a.row_shift = row_shift;
     a.dyn = nullptr;
+    a.scanned_next = nullptr;
+    a.rows_next = nullptr;
     return a;
 }
 

@@ -52,6 +52,10 @@ struct QuadArgs {
     uint32_t min_chunk;                // lower bound on the work items per warp
     uint32_t row_shift;                // cyclic 1D partition: row of v is v >> row_shift
     const LoopDyn *dyn;                // graph-driven level loop: frontier / num_segments / out come from here (else NULL)
+    // work creation (OUT_COMPACT only, else NULL): the flush also writes the NEXT level's row bounds and quad scan;
+    // counters[B200_CNT_OUT] then holds (vertices emitted << 32) | quads created
+    uint32_t *scanned_next;
+    uint2 *rows_next;
 };
 
 // quads(v): number of aligned 16-byte quads of col_indices that row v touches.  Also leaves
@@ -113,6 +117,12 @@ quad_advance_kernel(QuadArgs a, Op op, int *__restrict__ out, unsigned long long
         a.frontier = a.dyn->in;
         a.num_segments = a.dyn->len;
         out = a.dyn->out;
+        if (a.dyn->scanned_in) {
+            a.scanned = a.dyn->scanned_in;
+            a.rows = a.dyn->rows_in;
+            a.scanned_next = a.dyn->scanned_out;
+            a.rows_next = a.dyn->rows_out;
+        }
         if constexpr (OUT_MODE == OUT_ROUTED) {
 #pragma unroll
             for (int p = 0; p < MAX_DEST; ++p)
@@ -178,6 +188,48 @@ quad_advance_kernel(QuadArgs a, Op op, int *__restrict__ out, unsigned long long
                     deg_sum += __ldg(a.offsets + r + 1) - __ldg(a.offsets + r);
                 }
             }
+        } else if (a.scanned_next) {
+            // work creation: one packed atomic reserves wcnt frontier slots AND the quads of their rows, so slot
+            // order and scan order agree (the next level's merge-path search needs a sorted scan)
+            uint32_t myq = 0;
+            for (uint32_t k = lane; k < wcnt; k += 32) {
+                const uint32_t r = (uint32_t)stage[k] >> a.row_shift;
+                const uint32_t b = __ldg(a.offsets + r), e = __ldg(a.offsets + r + 1);
+                myq += e > b ? ((e - 1) >> 2) - (b >> 2) + 1u : 0u;
+                if (DEG_SUM) deg_sum += e - b;
+            }
+            const uint32_t wq = warp_sum(myq);
+            unsigned long long g64 = 0;
+            if (lane == 0) g64 = atomicAdd(&counters[B200_CNT_OUT], ((unsigned long long)wcnt << 32) | wq);
+            g64 = __shfl_sync(FULL_MASK, g64, 0);
+            const unsigned long long g = g64 >> 32;
+            uint32_t run = (uint32_t)g64;
+            for (uint32_t k0 = 0; k0 < wcnt; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                const bool on = k < wcnt;
+                int u = 0;
+                uint32_t b = 0, e = 0;
+                if (on) {
+                    u = stage[k];
+                    const uint32_t r = (uint32_t)u >> a.row_shift;
+                    b = __ldg(a.offsets + r);          // second read of the pair: L1 hit
+                    e = __ldg(a.offsets + r + 1);
+                }
+                const uint32_t q = e > b ? ((e - 1) >> 2) - (b >> 2) + 1u : 0u;
+                uint32_t incl = q;
+#pragma unroll
+                for (int s = 1; s < 32; s <<= 1) {
+                    const uint32_t t = __shfl_up_sync(FULL_MASK, incl, s);
+                    if (lane >= (unsigned)s) incl += t;
+                }
+                if (on && g + k < out_capacity) {
+                    out[g + k] = u;
+                    a.rows_next[g + k] = make_uint2(b, e);
+                    a.scanned_next[g + k] = run + incl - q;
+                }
+                run += __shfl_sync(FULL_MASK, incl, 31);
+            }
+            if (lane == 0 && g + wcnt > out_capacity) counters[B200_CNT_OVERFLOW] = 1ull;
         } else {
             unsigned long long g = 0;
             if (lane == 0) g = atomicAdd(&counters[B200_CNT_OUT], (unsigned long long)wcnt);
@@ -222,7 +274,14 @@ quad_advance_kernel(QuadArgs a, Op op, int *__restrict__ out, unsigned long long
                 if (on[r]) u = op.finish(tok[r], c[r]);
                 if (STAGED) {
                     const unsigned mask = __ballot_sync(FULL_MASK, u >= 0);
-                    if (u >= 0) stage[wcnt + __popc(mask & lt_mask)] = u;
+                    if (u >= 0) {
+                        stage[wcnt + __popc(mask & lt_mask)] = u;
+#ifndef B200_QUAD_NO_PREFETCH
+                        // work creation / degree sum: the flush will read this vertex's row bounds -- start the fetch now
+                        if (OUT_MODE == OUT_COMPACT && (DEG_SUM || a.scanned_next))
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.offsets + ((uint32_t)u >> a.row_shift)));
+#endif
+                    }
                     wcnt += __popc(mask);
                 }
             }

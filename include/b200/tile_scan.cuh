@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(NT) scan_sizes_dyn_kernel(SizeFn fn, const Loo
     __shared__ uint32_t s_tile, s_bcast;
     loop_trace(dyn, 2);
     if (!(dyn->run & run_bit)) return;
+    if (dyn->scanned_in) out = dyn->scanned_in;   // work-creating loop: this level's scan buffer is chosen on the device
     const uint32_t count = dyn->len;
     LookbackState st;
     st.status = status;

@@ -37,6 +37,8 @@ typedef struct b200_workspace {
     int64_t launches;                   /* kernels launched through this workspace (bench `gpu_launches`) */
     void *d_rows;                       /* uint2[scanned_capacity]: (row begin, row end) of every frontier
                                            vertex, written by the quad scan beside d_scanned */
+    uint32_t *d_scanned2;               /* second (scan, rows) pair: the work-creating advance writes the NEXT level's */
+    void *d_rows2;                      /* scan and row bounds while it reads this level's (quad_advance.cuh) */
 } b200_workspace;
 
 #ifdef __cplusplus

@@ -164,11 +164,15 @@ int b200_ctx_reserve(b200_ctx *ctx, int64_t max_items) {
         B200_CUDA(cudaStreamSynchronize((cudaStream_t)ws.stream));
         if (ws.d_scanned) cudaFree(ws.d_scanned);
         if (ws.d_rows) cudaFree(ws.d_rows);
-        ws.d_scanned = nullptr;
-        ws.d_rows = nullptr;
+        if (ws.d_scanned2) cudaFree(ws.d_scanned2);
+        if (ws.d_rows2) cudaFree(ws.d_rows2);
+        ws.d_scanned = ws.d_scanned2 = nullptr;
+        ws.d_rows = ws.d_rows2 = nullptr;
         ws.scanned_capacity = 0;
         B200_CUDA(cudaMalloc(&ws.d_scanned, sizeof(uint32_t) * (size_t)(max_items + 1)));
         B200_CUDA(cudaMalloc(&ws.d_rows, 2 * sizeof(uint32_t) * (size_t)(max_items + 1)));
+        B200_CUDA(cudaMalloc(&ws.d_scanned2, sizeof(uint32_t) * (size_t)(max_items + 1)));
+        B200_CUDA(cudaMalloc(&ws.d_rows2, 2 * sizeof(uint32_t) * (size_t)(max_items + 1)));
         ws.scanned_capacity = max_items;
     }
     return B200_OK;
@@ -187,7 +191,7 @@ int b200_ctx_num_sms(b200_ctx *ctx, int *num_sms) {
 }
 
 int b200_ctx_set_advance_impl(b200_ctx *ctx, int impl) {
-    if (!ctx || (impl != B200_ADVANCE_QUAD && impl != B200_ADVANCE_LBS)) return B200_ERR_INVALID;
+    if (!ctx || (impl != B200_ADVANCE_QUAD && impl != B200_ADVANCE_LBS && impl != B200_ADVANCE_QUAD_WORKCREATE)) return B200_ERR_INVALID;
     ctx->adv_impl = impl;
     return B200_OK;
 }
@@ -263,6 +267,8 @@ int b200_ctx_destroy(b200_ctx *ctx) {
     if (ctx->ws.d_status) cudaFree(ctx->ws.d_status);
     if (ctx->ws.d_scanned) cudaFree(ctx->ws.d_scanned);
     if (ctx->ws.d_rows) cudaFree(ctx->ws.d_rows);
+    if (ctx->ws.d_scanned2) cudaFree(ctx->ws.d_scanned2);
+    if (ctx->ws.d_rows2) cudaFree(ctx->ws.d_rows2);
     if (ctx->ws.d_counters) cudaFree(ctx->ws.d_counters);
     if (ctx->ws.h_counters) cudaFreeHost(ctx->ws.h_counters);
     if (ctx->ws.d_tile_counter) cudaFree(ctx->ws.d_tile_counter);

@@ -19,6 +19,7 @@ __global__ void bfs_init_kernel(int32_t *labels, uint32_t *visited, int32_t *fro
     visited[src >> 5] |= 1u << (src & 31);
     frontier[0] = src;
 }
+__global__ void set_counter_kernel(unsigned long long *p, unsigned long long v) { *p = v; }
 __global__ void sssp_init_kernel(float *dist, int32_t *preds, int32_t *stamp, unsigned long long n) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -209,7 +210,7 @@ int b200_advance_forward(b200_ctx *ctx, const b200_graph *g, const b200_problem 
     B200_CUDA(cudaSetDevice(ws->device));
     B200_CUDA(reset_counters(ws));
     const unsigned long long cap = (unsigned long long)out_capacity;
-    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && !raw && quad_aligned(g->col_indices) &&
+    const bool quad = ctx->adv_impl != B200_ADVANCE_LBS && !raw && quad_aligned(g->col_indices) &&
                       (p->kind != B200_PROBLEM_SSSP || quad_aligned(p->weights));
     cudaError_t e = cudaErrorInvalidValue;
     if (quad) {
@@ -375,7 +376,7 @@ int b200_neighborhood_reduce_f32(b200_ctx *ctx, const b200_graph *g, const int32
     const float neutral = op == B200_OP_PLUS ? PlusF32::neutral() : (op == B200_OP_MIN ? MinF32::neutral() : MaxF32::neutral());
     FiniteValueFn vf{d_values};
     cudaError_t e;
-    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(idx);
+    const bool quad = ctx->adv_impl != B200_ADVANCE_LBS && quad_aligned(idx);
     if (quad) {
         B200_CUDA(launch_neighborhood_quad_scan<float>(ws, d_in, (uint32_t)in_len, off, d_reduced, identity, neutral, scatter));
         const QuadArgs a = make_quad_args(ws, d_in, (uint32_t)in_len, off, idx, nullptr);
@@ -410,7 +411,7 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
     cudaStream_t st = ws_stream(ws);
     const size_t words = (size_t)((n + 31) / 32);
     const bool timing = stats && stats->collect_timing;
-    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(g->col_indices);
+    const bool quad = ctx->adv_impl != B200_ADVANCE_LBS && quad_aligned(g->col_indices);
     if (alpha <= 0.f) alpha = 15.f;
     if (beta <= 0.f) beta = 18.f;
     if (quad && !timing && ctx->loop_impl == B200_LOOP_GRAPH) {
@@ -437,7 +438,10 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
     ws->launches++;
     B200_CUDA(cudaGetLastError());
 
-    int sel = 0, bsel = 0, level = 0;
+    int sel = 0, bsel = 0, level = 0, wsel = 0;
+    const bool work_create = quad && ctx->adv_impl == B200_ADVANCE_QUAD_WORKCREATE;   // (else: scan before every level)
+    bool have_scan = false;
+    int64_t next_quads = 0;
     int64_t flen = 1, unvisited = n - 1, reached = 1, total_arcs = 0;
     int64_t m_unexplored = g->m;
     bool pull = false;
@@ -452,8 +456,22 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
             const bool deg = mode == B200_BFS_BEAMER;
             int32_t *next = ctx->frontier[sel ^ 1];
             if (quad) {
-                B200_CUDA(launch_quad_scan(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets));
-                const QuadArgs a = make_quad_args(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets, g->col_indices, nullptr);
+                if (!have_scan) {
+                    B200_CUDA(launch_quad_scan(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets));   // into pair 0
+                    wsel = 0;
+                } else {   // the previous advance created this level's scan and row bounds (pair wsel)
+                    set_counter_kernel<<<1, 1, 0, st>>>(ws->d_counters + B200_CNT_TOTAL, (unsigned long long)next_quads);
+                    ws->launches++;
+                }
+                QuadArgs a = make_quad_args(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets, g->col_indices, nullptr);
+                if (work_create) {
+                    uint32_t *sc[2] = {ws->d_scanned, ws->d_scanned2};
+                    uint2 *rw[2] = {reinterpret_cast<uint2 *>(ws->d_rows), reinterpret_cast<uint2 *>(ws->d_rows2)};
+                    a.scanned = sc[wsel];
+                    a.rows = rw[wsel];
+                    a.scanned_next = sc[wsel ^ 1];
+                    a.rows_next = rw[wsel ^ 1];
+                }
                 BfsPushQ op{ctx->bm_visited, d_labels, level + 1};
                 if (tl) B200_CUDA(cudaEventRecord(ev[3 * level + 1], st));
                 if (deg) B200_CUDA((launch_quad_advance<OUT_COMPACT, true>(ws, a, op, next, (unsigned long long)n)));
@@ -470,9 +488,16 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
             B200_CUDA(read_counters(ws));
             if (ws->h_counters[B200_CNT_OVERFLOW]) return B200_ERR_OVERFLOW;
             found = (int64_t)ws->h_counters[B200_CNT_OUT];
+            if (work_create) {   // (vertices emitted << 32) | quads created
+                next_quads = found & 0xffffffffll;
+                found = (int64_t)((unsigned long long)found >> 32);
+                have_scan = true;
+                wsel ^= 1;
+            }
             arcs = (int64_t)ws->h_counters[quad ? B200_CNT_ARCS : B200_CNT_TOTAL];
             next_deg = (int64_t)ws->h_counters[B200_CNT_AUX];
         } else {
+            have_scan = false;   // the list that follows a pull phase comes from the bitmap: it needs a scan
             if (tl) B200_CUDA(cudaEventRecord(ev[3 * level + 1], st));
             bfs_pull_kernel<256><<<ws->num_sms * 8, 256, 0, st>>>((uint32_t)n, pull_off, pull_idx, ctx->bm_frontier[bsel],
                                                                   ctx->bm_frontier[bsel ^ 1], ctx->bm_visited, d_labels,
@@ -552,8 +577,11 @@ int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist
     cudaEvent_t *ev = timing ? level_events(ctx) : nullptr;
     const int64_t launches0 = ws->launches;
 
-    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(g->col_indices) && quad_aligned(g->col_values);
-    bool graph_done = false;
+    const bool quad = ctx->adv_impl != B200_ADVANCE_LBS && quad_aligned(g->col_indices) && quad_aligned(g->col_values);
+    const bool work_create = quad && ctx->adv_impl == B200_ADVANCE_QUAD_WORKCREATE;
+    bool graph_done = false, have_scan = false;
+    int64_t next_quads = 0;
+    int wsel = 0;
     int sel = 0, it = 0;
     int64_t flen = 1, total_arcs = 0;
     if (quad && !timing && ctx->loop_impl == B200_LOOP_GRAPH) {
@@ -585,8 +613,22 @@ int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist
         if (tl && it == 0) B200_CUDA(cudaEventRecord(ev[0], st));
         B200_CUDA(reset_counters(ws));
         if (quad) {
-            B200_CUDA(launch_quad_scan(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets));
-            const QuadArgs a = make_quad_args(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets, g->col_indices, g->col_values);
+            if (!have_scan) {
+                B200_CUDA(launch_quad_scan(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets));
+                wsel = 0;
+            } else {
+                set_counter_kernel<<<1, 1, 0, st>>>(ws->d_counters + B200_CNT_TOTAL, (unsigned long long)next_quads);
+                ws->launches++;
+            }
+            QuadArgs a = make_quad_args(ws, ctx->frontier[sel], (uint32_t)flen, g->row_offsets, g->col_indices, g->col_values);
+            if (work_create) {
+                uint32_t *sc[2] = {ws->d_scanned, ws->d_scanned2};
+                uint2 *rw[2] = {reinterpret_cast<uint2 *>(ws->d_rows), reinterpret_cast<uint2 *>(ws->d_rows2)};
+                a.scanned = sc[wsel];
+                a.rows = rw[wsel];
+                a.scanned_next = sc[wsel ^ 1];
+                a.rows_next = rw[wsel ^ 1];
+            }
             SsspRelaxQ op{d_dist, nullptr, ctx->stamp, it};   // preds: one exact pass at the end
             if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 1], st));
             B200_CUDA((launch_quad_advance<OUT_COMPACT, false>(ws, a, op, ctx->frontier[sel ^ 1], (unsigned long long)n)));
@@ -600,7 +642,13 @@ int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist
         if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 2], st));
         B200_CUDA(read_counters(ws));
         if (ws->h_counters[B200_CNT_OVERFLOW]) return B200_ERR_OVERFLOW;
-        const int64_t found = (int64_t)ws->h_counters[B200_CNT_OUT];
+        int64_t found = (int64_t)ws->h_counters[B200_CNT_OUT];
+        if (work_create) {
+            next_quads = found & 0xffffffffll;
+            found = (int64_t)((unsigned long long)found >> 32);
+            have_scan = true;
+            wsel ^= 1;
+        }
         const int64_t arcs = (int64_t)ws->h_counters[quad ? B200_CNT_ARCS : B200_CNT_TOTAL];
         if (ls) {
             ls->direction = 0;
@@ -667,7 +715,7 @@ int b200_pr_run(b200_ctx *ctx, const b200_graph *g, int max_iter, int scatter, f
     B200_CUDA(cudaGetLastError());
     int sel = 0, it = 0;
     int64_t flen = n, total_arcs = 0;
-    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(idx);
+    const bool quad = ctx->adv_impl != B200_ADVANCE_LBS && quad_aligned(idx);
     while (flen > 0 && it < max_iter) {
         b200_level_stat *ls = (stats && it < B200_MAX_LEVELS) ? &stats->level[it] : nullptr;
         const bool tl = timing && it < B200_MAX_LEVELS;

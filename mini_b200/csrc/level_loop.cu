@@ -66,6 +66,7 @@ struct LevelLoop {
         const void *k_offsets, *k_indices, *k_labels, *k_scratch, *k_iso, *k_first, *k_weights;
         int64_t k_n;
         int k_mode;
+        bool k_wc;
     } slot[2];
     int failed;          // status of the last failed build (the caller falls back to the host loop)
 };
@@ -88,9 +89,14 @@ struct FrontierQuadsDyn {   // FrontierQuads over the device-selected frontier l
             b = __ldg(offsets + v);
             e = __ldg(offsets + v + 1);
         }
-        rows[i] = make_uint2(b, e);
+        (dyn->rows_in ? dyn->rows_in : rows)[i] = make_uint2(b, e);
         return e > b ? ((e - 1) >> 2) - (b >> 2) + 1u : 0u;
     }
+};
+
+struct ScanPairs {   // the two (scan, row bounds) buffer pairs of the workspace; all NULL = re-scan every level
+    uint32_t *sc0, *sc1;
+    uint2 *rw0, *rw1;
 };
 
 __global__ void sssp_loop_fill_kernel(float *dist, int32_t *stamp, unsigned long long n) {
@@ -105,7 +111,8 @@ __global__ void sssp_loop_fill_kernel(float *dist, int32_t *stamp, unsigned long
 // SSSP: labels holds float distances (sssp_problem.hxx:44-46: source 0.0f)
 template <bool SSSP>
 __global__ void loop_init_kernel(const LoopParams *p, LoopState *s, int32_t *labels, uint32_t *visited, int32_t *f0,
-                                 int32_t *f1, long long n, unsigned long long *counters, unsigned int *tile_counters) {
+                                 int32_t *f1, long long n, unsigned long long *counters, unsigned int *tile_counters,
+                                 ScanPairs sp) {
     const int src = p->src;
     labels[src] = 0;                         // depth 0 / +0.0f
     if (!SSSP) visited[src >> 5] |= 1u << (src & 31);
@@ -116,7 +123,11 @@ __global__ void loop_init_kernel(const LoopParams *p, LoopState *s, int32_t *lab
     s->dyn.epoch = p->epoch0 & 0x3FFFFFFFu;
     s->dyn.next_label = 1;
     s->dyn.bsel = 0u;
-    s->dyn.run = LOOP_RUN_PUSH;
+    s->dyn.run = LOOP_RUN_PUSH | LOOP_RUN_SCAN;
+    s->dyn.scanned_in = sp.sc0;
+    s->dyn.rows_in = sp.rw0;
+    s->dyn.scanned_out = sp.sc1;
+    s->dyn.rows_out = sp.rw1;
     s->dyn.trace = nullptr;
     s->dyn.trace_cap = 0u;
     s->level = 0;
@@ -139,10 +150,18 @@ __global__ void loop_init_kernel(const LoopParams *p, LoopState *s, int32_t *lab
 // The host loop's per-level bookkeeping (engine.cu b200_bfs_run), on the device.
 __global__ void loop_decide_kernel(LoopState *s, unsigned long long *counters, unsigned int *tile_counters, LoopResult *res,
                                    cudaGraphConditionalHandle h_while) {
-    const long long found = (long long)counters[B200_CNT_OUT], arcs = (long long)counters[B200_CNT_ARCS];
+    const bool was_pull = s->pull != 0;
+    const bool work_create = s->dyn.scanned_in != nullptr;
+    long long found = (long long)counters[B200_CNT_OUT];
+    unsigned long long next_quads = 0ull;
+    if (work_create && !was_pull) {   // the advance packed (vertices emitted << 32) | quads created
+        next_quads = (unsigned long long)found & 0xffffffffull;
+        found = (long long)((unsigned long long)found >> 32);
+    }
+    const long long arcs = (long long)counters[B200_CNT_ARCS];
     const long long next_deg = (long long)counters[B200_CNT_AUX];
     const bool overflow = counters[B200_CNT_OVERFLOW] != 0ull;
-    const bool was_pull = s->pull != 0;
+    bool need_scan = !work_create;
     bool pull = was_pull;
     int level = s->level;
     if (level < B200_MAX_LEVELS) {
@@ -173,6 +192,14 @@ __global__ void loop_decide_kernel(LoopState *s, unsigned long long *counters, u
             const int *t = s->dyn.in;
             s->dyn.in = s->dyn.out;
             s->dyn.out = const_cast<int *>(t);
+            if (work_create) {   // the scan and row bounds the advance created become this level's
+                uint32_t *ts = s->dyn.scanned_in;
+                s->dyn.scanned_in = s->dyn.scanned_out;
+                s->dyn.scanned_out = ts;
+                uint2 *tr = s->dyn.rows_in;
+                s->dyn.rows_in = s->dyn.rows_out;
+                s->dyn.rows_out = tr;
+            }
             if (s->mode == B200_BFS_REF_ALPHA) {
                 if ((float)s->unvisited < (float)found * s->alpha) pull = true;   // bfs_enactor.hxx:68
             } else if (s->mode == B200_BFS_BEAMER) {
@@ -189,12 +216,14 @@ __global__ void loop_decide_kernel(LoopState *s, unsigned long long *counters, u
             s->dyn.bsel = 0u;
         } else if (!pull && was_pull) {
             trans = LOOP_RUN_TO_PUSH;   // bitmap -> list for the push levels that finish the traversal
+            need_scan = true;           // ... a list nobody has scanned
         }
     }
     s->pull = pull ? 1 : 0;
     s->dyn.next_label = level + 1;
     s->dyn.epoch = (s->dyn.epoch + 2u) & 0x3FFFFFFFu;
     for (int i = 0; i < B200_NUM_COUNTERS; ++i) counters[i] = 0ull;
+    if (!need_scan) counters[B200_CNT_TOTAL] = next_quads;   // what the scan kernel would have left there
     tile_counters[0] = 0u;
     tile_counters[1] = 0u;
     if (done) {
@@ -205,7 +234,7 @@ __global__ void loop_decide_kernel(LoopState *s, unsigned long long *counters, u
         res->launches = s->launches;
         __threadfence_system();
     }
-    s->dyn.run = done ? 0u : ((pull ? LOOP_RUN_PULL : LOOP_RUN_PUSH) | trans);
+    s->dyn.run = done ? 0u : ((pull ? LOOP_RUN_PULL : LOOP_RUN_PUSH | (need_scan ? LOOP_RUN_SCAN : 0u)) | trans);
     cudaGraphSetConditional(h_while, done ? 0u : 1u);
 }
 
@@ -220,7 +249,7 @@ void drop_graph(LevelLoop *L) {
 }
 
 // mode: a B200_BFS_* mode (d_labels = int32 labels) or MODE_SSSP (d_labels = float distances, reinterpreted)
-int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode, const uint32_t *iso) {
+int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode, const uint32_t *iso, bool work_create) {
     LevelLoop *L = ctx->loop;
     LevelLoop::Slot *S = &L->slot[mode == MODE_SSSP ? SLOT_SSSP : SLOT_BFS];
     const bool sssp = mode == MODE_SSSP;
@@ -242,6 +271,9 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
     size_t ndeps = 0;
     cudaGraphNodeParams np_w = {};
     const LoopDyn *dyn = &L->d_state->dyn;
+    ScanPairs sp = {nullptr, nullptr, nullptr, nullptr};
+    if (work_create)
+        sp = ScanPairs{ws->d_scanned, ws->d_scanned2, reinterpret_cast<uint2 *>(ws->d_rows), reinterpret_cast<uint2 *>(ws->d_rows2)};
 
     drop_slot(S);
     ws->stream = (void *)cs;   // the launchers below record into the capture stream
@@ -256,7 +288,7 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
         sssp_loop_fill_kernel<<<ws->num_sms * 4, 256, 0, cs>>>(reinterpret_cast<float *>(d_labels), ctx->stamp, (unsigned long long)n);
         LL_CUDA(cudaGetLastError());
         loop_init_kernel<true><<<1, 1, 0, cs>>>(L->d_params, L->d_state, d_labels, nullptr, ctx->frontier[0], ctx->frontier[1],
-                                                (long long)n, ws->d_counters, ws->d_tile_counter);
+                                                (long long)n, ws->d_counters, ws->d_tile_counter, sp);
     } else {
         LL_CUDA(cudaMemsetAsync(d_labels, 0xFF, sizeof(int32_t) * (size_t)n, cs));
         if (mode == B200_BFS_PUSH) {
@@ -267,7 +299,7 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
             LL_CUDA(cudaMemsetAsync(ctx->bm_frontier[0], 0, sizeof(uint32_t) * words, cs));
         }
         loop_init_kernel<false><<<1, 1, 0, cs>>>(L->d_params, L->d_state, d_labels, ctx->bm_visited, ctx->frontier[0],
-                                                 ctx->frontier[1], (long long)n, ws->d_counters, ws->d_tile_counter);
+                                                 ctx->frontier[1], (long long)n, ws->d_counters, ws->d_tile_counter, sp);
     }
     LL_CUDA(cudaGetLastError());
     capturing = false;
@@ -291,7 +323,7 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
         if (grid > max_tiles) grid = max_tiles;
         FrontierQuadsDyn fn{dyn, g->row_offsets, reinterpret_cast<uint2 *>(ws->d_rows)};
         scan_sizes_dyn_kernel<SCAN_NT, SCAN_VT><<<(unsigned)grid, SCAN_NT, 0, cs>>>(
-            fn, dyn, (uint32_t)LOOP_RUN_PUSH, ws->d_scanned, ws->d_status, ws->d_tile_counter, ws->d_counters + B200_CNT_TOTAL);
+            fn, dyn, (uint32_t)LOOP_RUN_SCAN, ws->d_scanned, ws->d_status, ws->d_tile_counter, ws->d_counters + B200_CNT_TOTAL);
         LL_CUDA(cudaGetLastError());
         QuadArgs a = make_quad_args(ws, ctx->frontier[0], 0u, g->row_offsets, g->col_indices, sssp ? g->col_values : nullptr);
         a.dyn = dyn;
@@ -342,6 +374,7 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
     S->k_first = g->first_in_neighbor;
     S->k_n = n;
     S->k_mode = mode;
+    S->k_wc = work_create;
     ws->stream = user_stream;
     ws->launches = launches0;
     return B200_OK;
@@ -405,11 +438,12 @@ static int run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, 
     cudaStream_t st = ws_stream(ws);
     if (L->failed) return B200_ERR_UNSUPPORTED;
     const uint32_t *iso = (mode != B200_BFS_PUSH && mode != MODE_SSSP) ? g->no_in_arc_bitmap : nullptr;
+    const bool work_create = ctx->adv_impl == B200_ADVANCE_QUAD_WORKCREATE;   // (else: scan before every level)
     if (!S->exec || S->k_offsets != g->row_offsets || S->k_indices != g->col_indices || S->k_labels != d_labels ||
         S->k_scratch != ctx->frontier[0] || S->k_n != g->n || S->k_mode != mode || S->k_iso != iso ||
-        S->k_first != g->first_in_neighbor || S->k_weights != g->col_values) {
+        S->k_first != g->first_in_neighbor || S->k_weights != g->col_values || S->k_wc != work_create) {
         B200_CUDA(cudaStreamSynchronize(st));   // a replay of the old graph may still be running
-        const int bs = build_graph(ctx, g, d_labels, mode, iso);
+        const int bs = build_graph(ctx, g, d_labels, mode, iso, work_create);
         if (bs != B200_OK) {
             L->failed = bs;
             return B200_ERR_UNSUPPORTED;

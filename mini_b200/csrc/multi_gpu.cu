@@ -115,7 +115,7 @@ int b200_mg_bfs_push(b200_ctx *ctx, const b200_graph *g, const b200_mg_bfs_state
             r.box[p] = p == s->rank ? d_next_frontier : d_send_boxes[p];
             r.capacity[p] = p == s->rank ? (unsigned long long)s->n_local : (unsigned long long)box_capacity;
         }
-        quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(g->col_indices);
+        quad = ctx->adv_impl != B200_ADVANCE_LBS && quad_aligned(g->col_indices);
         if (quad) {
             B200_CUDA(launch_quad_scan(ws, d_frontier, (uint32_t)frontier_len, g->row_offsets, part.log_p));
             const QuadArgs a = make_quad_args(ws, d_frontier, (uint32_t)frontier_len, g->row_offsets, g->col_indices, nullptr, part.log_p);

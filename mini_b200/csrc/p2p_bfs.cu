@@ -326,6 +326,10 @@ __global__ void p2p_loop_init_kernel(const P2PLoopParams *p, P2PLoopState *s, in
     s->dyn.next_label = 1;
     s->dyn.bsel = 0u;
     s->dyn.run = LOOP_RUN_PUSH;
+    s->dyn.scanned_in = nullptr;   // the routed flush does not create work: scan before every push level
+    s->dyn.rows_in = nullptr;
+    s->dyn.scanned_out = nullptr;
+    s->dyn.rows_out = nullptr;
     s->dyn.trace = p->trace;
     s->dyn.trace_cap = p->trace_cap;
     if (p->trace) p->trace[0] = 0ull;
@@ -1021,7 +1025,7 @@ int b200_p2p_bfs_prepare(b200_p2p_bfs *s, const b200_graph *g, int mode, int32_t
     if (s->P > 1 && !s->connected) return B200_ERR_INVALID;
     b200_ctx *ctx = s->ctx;
     B200_CUDA(cudaSetDevice(ctx->ws.device));
-    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(g->col_indices);
+    const bool quad = ctx->adv_impl != B200_ADVANCE_LBS && quad_aligned(g->col_indices);
     if (!quad || ctx->loop_impl != B200_LOOP_GRAPH) return B200_OK;   // host-driven loop: nothing to build
     const int st = p2p_ensure_graph(s, g, d_labels, mode);
     return st == B200_ERR_UNSUPPORTED ? B200_OK : st;                 // run() then takes the host-driven loop
@@ -1047,7 +1051,7 @@ int b200_p2p_bfs_run(b200_p2p_bfs *s, const b200_graph *g, int64_t m_global, int
     const int64_t launches0 = ws->launches;
     const uint32_t *pull_off = g->col_offsets ? g->col_offsets : g->row_offsets;
     const int32_t *pull_idx = g->row_indices ? g->row_indices : g->col_indices;
-    const bool quad = ctx->adv_impl == B200_ADVANCE_QUAD && quad_aligned(g->col_indices);
+    const bool quad = ctx->adv_impl != B200_ADVANCE_LBS && quad_aligned(g->col_indices);
     Ctrl *my_ctrl = reinterpret_cast<Ctrl *>(s->heap);
     int *my_inbox = reinterpret_cast<int *>(s->heap + s->off_inbox);
     if (alpha <= 0.f) alpha = 15.f;
