@@ -87,7 +87,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-WORK_CREATE = False   # --advance workcreate: the advance launch also produces the next level's scan
+WORK_CREATE = True    # --advance quad (default): the advance launch also produces the next level's scan
 
 
 def push_level_bytes(level, offset_bytes=4):
@@ -253,8 +253,8 @@ def run_single_gpu(args):
     torch.cuda.set_device(dev)
     ctx = mb.Context(dev)
     global WORK_CREATE
-    WORK_CREATE = args.advance == "workcreate"
-    ctx.set_advance_impl({"lbs": mb.ADVANCE_LBS, "workcreate": mb.ADVANCE_QUAD_WORKCREATE}.get(args.advance, mb.ADVANCE_QUAD))
+    WORK_CREATE = args.advance == "quad"
+    ctx.set_advance_impl({"lbs": mb.ADVANCE_LBS, "rescan": mb.ADVANCE_QUAD_RESCAN}.get(args.advance, mb.ADVANCE_QUAD))
     ctx.set_level_loop(mb.LOOP_HOST if args.loop == "host" else mb.LOOP_GRAPH)
     g = ctx.prepare_graph(ctx.rmat_graph(scale, 16, 1))   # graph build + one-time derived data: outside the timed region
     mode = {"push": mb.BFS_PUSH, "beamer": mb.BFS_BEAMER}[args.mode]
@@ -365,6 +365,9 @@ def run_single_gpu(args):
         "dtype": "int32", "data": "synthetic",
         "config": {"workload": f"BFS from vertex 0, RMAT scale-{scale} ef16 symmetrised (n={gn}, m={gm}), "
                                f"{args.mode} (LB advance + fused uniquify filter)",
+                   "advance": args.advance + (" (work-creating: the flush writes the next level's row bounds and scan "
+                                               "positions; their 20 B per emitted vertex are counted in the roofline's "
+                                               "algorithmic bytes)" if args.advance == "quad" else ""),
                    "teps_numerator": "sum of deg(v) over reached v", "reached_arcs": reached_arcs,
                    "l2": "inputs larger than L2 (col_indices alone is %d MiB vs 126 MB L2)" % (gm * 4 >> 20),
                    "level_loop": loop_used + (" (one CUDA graph per BFS: WHILE/IF/SWITCH conditional nodes set by a "
@@ -389,9 +392,9 @@ def main():
     ap.add_argument("--scale", type=int, default=0)
     ap.add_argument("--mode", default="push", choices=["push", "beamer"])
     ap.add_argument("--cpu-runs", type=int, default=3)
-    ap.add_argument("--advance", default="quad", choices=["quad", "workcreate", "lbs"],
-                    help="push-advance kernel: quad_advance.cuh (default), the same creating the next level's scan, "
-                         "or the first-generation advance.cuh")
+    ap.add_argument("--advance", default="quad", choices=["quad", "rescan", "lbs"],
+                    help="push-advance kernel: quad_advance.cuh creating the next level's scan in its flush (default), "
+                         "the same with a scan kernel before every level, or the first-generation advance.cuh")
     ap.add_argument("--loop", default="graph", choices=["graph", "host"],
                     help="N=1 BFS level loop: one CUDA graph with device-side decisions, or host-driven")
     ap.add_argument("--extras", default="sssp,reduce",

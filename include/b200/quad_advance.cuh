@@ -191,12 +191,25 @@ quad_advance_kernel(QuadArgs a, Op op, int *__restrict__ out, unsigned long long
         } else if (a.scanned_next) {
             // work creation: one packed atomic reserves wcnt frontier slots AND the quads of their rows, so slot
             // order and scan order agree (the next level's merge-path search needs a sorted scan)
+            // (one pass: the row bounds of the <= WSTAGE / 32 entries a lane owns stay in registers, all loads in flight)
+            constexpr int E = WSTAGE / 32;
+            uint32_t rb_[E], re_[E];
             uint32_t myq = 0;
-            for (uint32_t k = lane; k < wcnt; k += 32) {
-                const uint32_t r = (uint32_t)stage[k] >> a.row_shift;
-                const uint32_t b = __ldg(a.offsets + r), e = __ldg(a.offsets + r + 1);
-                myq += e > b ? ((e - 1) >> 2) - (b >> 2) + 1u : 0u;
-                if (DEG_SUM) deg_sum += e - b;
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                const uint32_t k = lane + 32u * i;
+                rb_[i] = 0u;
+                re_[i] = 0u;
+                if (k < wcnt) {
+                    const uint32_t r = (uint32_t)stage[k] >> a.row_shift;
+                    rb_[i] = __ldg(a.offsets + r);
+                    re_[i] = __ldg(a.offsets + r + 1);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                myq += re_[i] > rb_[i] ? ((re_[i] - 1) >> 2) - (rb_[i] >> 2) + 1u : 0u;
+                if (DEG_SUM) deg_sum += re_[i] - rb_[i];
             }
             const uint32_t wq = warp_sum(myq);
             unsigned long long g64 = 0;
@@ -204,18 +217,12 @@ quad_advance_kernel(QuadArgs a, Op op, int *__restrict__ out, unsigned long long
             g64 = __shfl_sync(FULL_MASK, g64, 0);
             const unsigned long long g = g64 >> 32;
             uint32_t run = (uint32_t)g64;
-            for (uint32_t k0 = 0; k0 < wcnt; k0 += 32) {
-                const uint32_t k = k0 + lane;
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                const uint32_t k = lane + 32u * i;
+                if (32u * i >= wcnt) break;                      // warp-uniform
                 const bool on = k < wcnt;
-                int u = 0;
-                uint32_t b = 0, e = 0;
-                if (on) {
-                    u = stage[k];
-                    const uint32_t r = (uint32_t)u >> a.row_shift;
-                    b = __ldg(a.offsets + r);          // second read of the pair: L1 hit
-                    e = __ldg(a.offsets + r + 1);
-                }
-                const uint32_t q = e > b ? ((e - 1) >> 2) - (b >> 2) + 1u : 0u;
+                const uint32_t q = re_[i] > rb_[i] ? ((re_[i] - 1) >> 2) - (rb_[i] >> 2) + 1u : 0u;
                 uint32_t incl = q;
 #pragma unroll
                 for (int s = 1; s < 32; s <<= 1) {
@@ -223,8 +230,8 @@ quad_advance_kernel(QuadArgs a, Op op, int *__restrict__ out, unsigned long long
                     if (lane >= (unsigned)s) incl += t;
                 }
                 if (on && g + k < out_capacity) {
-                    out[g + k] = u;
-                    a.rows_next[g + k] = make_uint2(b, e);
+                    out[g + k] = stage[k];
+                    a.rows_next[g + k] = make_uint2(rb_[i], re_[i]);
                     a.scanned_next[g + k] = run + incl - q;
                 }
                 run += __shfl_sync(FULL_MASK, incl, 31);
@@ -274,14 +281,7 @@ quad_advance_kernel(QuadArgs a, Op op, int *__restrict__ out, unsigned long long
                 if (on[r]) u = op.finish(tok[r], c[r]);
                 if (STAGED) {
                     const unsigned mask = __ballot_sync(FULL_MASK, u >= 0);
-                    if (u >= 0) {
-                        stage[wcnt + __popc(mask & lt_mask)] = u;
-#ifndef B200_QUAD_NO_PREFETCH
-                        // work creation / degree sum: the flush will read this vertex's row bounds -- start the fetch now
-                        if (OUT_MODE == OUT_COMPACT && (DEG_SUM || a.scanned_next))
-                            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.offsets + ((uint32_t)u >> a.row_shift)));
-#endif
-                    }
+                    if (u >= 0) stage[wcnt + __popc(mask & lt_mask)] = u;
                     wcnt += __popc(mask);
                 }
             }

@@ -141,18 +141,17 @@ int b200_ctx_l2_pin(b200_ctx *ctx, const void *d_ptr, int64_t bytes);
  * behind the operators and primitives below.  Both give identical results.
  *   B200_ADVANCE_QUAD (default): LBS over aligned 16-byte quads of col_indices, warp-private
  *     chunks, probe / compact / dense-commit stages, L1-resident bitmap (include/b200/quad_advance.cuh);
- *     A degree scan runs before every level (transform_scan + transform_lbs as the reference orders them,
- *     advance.hxx:30-44);
- *   B200_ADVANCE_QUAD_WORKCREATE: the same kernel, WORK-CREATING inside b200_bfs_run / b200_sssp_run (the README's
- *     "dynamic group workload mapping", README.md:12; nearest in-tree relative: mgpu expt::lbs_workcreate,
- *     kernel_workcreate.hxx:15-268): the flush that appends a discovered vertex to the next frontier also appends
- *     its row bounds and its position in the next level's quad scan -- slots and scan positions come from ONE
- *     packed 64-bit atomic, so the scan stays sorted -- and the next level starts without a scan kernel.
- *     Measured (scale-22 push BFS): 0.541 -> 0.520 ms per traversal, but the heaviest advance launch grows
- *     0.226 -> 0.253 ms because its flush now reads 2 M row-bound pairs; not the default (profiles/README.md);
+ *     Inside b200_bfs_run / b200_sssp_run it is WORK-CREATING (the README's "dynamic group workload mapping",
+ *     README.md:12; nearest in-tree relative: mgpu expt::lbs_workcreate, kernel_workcreate.hxx:15-268): the flush
+ *     that appends a discovered vertex to the next frontier also appends its row bounds and its position in the
+ *     next level's quad scan -- slots and scan positions come from ONE packed 64-bit atomic, so the scan stays
+ *     sorted -- and the next level starts without a scan kernel (scale-22 push BFS 0.571 -> 0.526 ms; the heaviest
+ *     launch takes 0.2446 instead of 0.2314 ms for 5.5 % more bytes, profiles/README.md);
+ *   B200_ADVANCE_QUAD_RESCAN: the same kernel with a degree scan before every level (transform_scan + transform_lbs
+ *     as the reference orders them, advance.hxx:30-44);
  *   B200_ADVANCE_LBS: LBS over arcs, CTA-cooperative windows (include/b200/advance.cuh); also
  *     taken automatically for B200_ADV_RAW_OUTPUT and for arrays that are not 16-byte aligned. */
-enum { B200_ADVANCE_QUAD = 0, B200_ADVANCE_LBS = 1, B200_ADVANCE_QUAD_WORKCREATE = 2 };
+enum { B200_ADVANCE_QUAD = 0, B200_ADVANCE_LBS = 1, B200_ADVANCE_QUAD_RESCAN = 2 };
 int b200_ctx_set_advance_impl(b200_ctx *ctx, int impl);
 
 /* Who drives the level loop of b200_bfs_run (the role of the host loop in bfs_enactor_t::enact_pushpull,

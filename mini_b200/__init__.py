@@ -9,7 +9,7 @@ There is no CPU fallback: importing the compute API without the built library ra
 from .lib import (  # noqa: F401
     B200Error, Context, Graph, Stats, load_library, library_path,
     BFS_PUSH, BFS_REF_ALPHA, BFS_BEAMER, ADV_IDEMPOTENT, ADV_NO_OUTPUT, ADV_RAW_OUTPUT,
-    OP_PLUS, OP_MIN, OP_MAX, ADVANCE_QUAD, ADVANCE_LBS, ADVANCE_QUAD_WORKCREATE, LOOP_GRAPH, LOOP_HOST,
+    OP_PLUS, OP_MIN, OP_MAX, ADVANCE_QUAD, ADVANCE_LBS, ADVANCE_QUAD_RESCAN, LOOP_GRAPH, LOOP_HOST,
 )
 
 __all__ = ["B200Error", "Context", "Graph", "Stats", "load_library", "library_path"]

@@ -191,7 +191,7 @@ int b200_ctx_num_sms(b200_ctx *ctx, int *num_sms) {
 }
 
 int b200_ctx_set_advance_impl(b200_ctx *ctx, int impl) {
-    if (!ctx || (impl != B200_ADVANCE_QUAD && impl != B200_ADVANCE_LBS && impl != B200_ADVANCE_QUAD_WORKCREATE)) return B200_ERR_INVALID;
+    if (!ctx || (impl != B200_ADVANCE_QUAD && impl != B200_ADVANCE_LBS && impl != B200_ADVANCE_QUAD_RESCAN)) return B200_ERR_INVALID;
     ctx->adv_impl = impl;
     return B200_OK;
 }

@@ -13,7 +13,7 @@ ADV_IDEMPOTENT, ADV_NO_OUTPUT, ADV_RAW_OUTPUT = 1, 2, 4
 OP_PLUS, OP_MIN, OP_MAX = 0, 1, 2
 PROBLEM_BFS, PROBLEM_SSSP, PROBLEM_PR = 1, 2, 3
 MAX_LEVELS = 512
-ADVANCE_QUAD, ADVANCE_LBS, ADVANCE_QUAD_WORKCREATE = 0, 1, 2
+ADVANCE_QUAD, ADVANCE_LBS, ADVANCE_QUAD_RESCAN = 0, 1, 2
 LOOP_GRAPH, LOOP_HOST = 0, 1
 
 
@@ -231,8 +231,8 @@ class Context:
         _check(self._L.b200_ctx_sync(self._h), "b200_ctx_sync")
 
     def set_advance_impl(self, impl: int):
-        """ADVANCE_QUAD (default), ADVANCE_QUAD_WORKCREATE (the advance also creates the next level's scan) or
-        ADVANCE_LBS: which kernel runs the push advance (same results)."""
+        """ADVANCE_QUAD (default; inside bfs / sssp the advance also creates the next level's scan), ADVANCE_QUAD_RESCAN
+        (a scan kernel before every level) or ADVANCE_LBS: which kernel runs the push advance (same results)."""
         _check(self._L.b200_ctx_set_advance_impl(self._h, impl), "b200_ctx_set_advance_impl")
 
     def set_level_loop(self, impl: int):

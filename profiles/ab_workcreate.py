@@ -1,9 +1,9 @@
 import sys, torch
 sys.path.insert(0, ".")
 import mini_b200 as mb
-for a in ("workcreate", "quad"):
+for a in ("quad", "rescan"):
     ctx = mb.Context(0)
-    ctx.set_advance_impl(mb.ADVANCE_QUAD if a == "quad" else mb.ADVANCE_QUAD_WORKCREATE)
+    ctx.set_advance_impl(mb.ADVANCE_QUAD if a == "quad" else mb.ADVANCE_QUAD_RESCAN)
     g = ctx.prepare_graph(ctx.rmat_graph(22, 16, 1))
     gw = ctx.rmat_graph(22, 16, 1, weighted=True)
     lab = torch.empty(g.n, dtype=torch.int32, device="cuda")

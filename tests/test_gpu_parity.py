@@ -17,7 +17,7 @@ FIXTURES = ["ref_fixture_bfs.json", "ref_fixture_sssp_directed.json",
 FLT_MAX = np.finfo(np.float32).max
 
 
-@pytest.fixture(scope="module", params=["quad", "lbs", "quad-hostloop", "quad-workcreate", "quad-workcreate-hostloop"])
+@pytest.fixture(scope="module", params=["quad", "lbs", "quad-hostloop", "quad-rescan", "quad-rescan-hostloop"])
 def ctx(request):
     """Every parity test runs against both push-advance kernels (quad_advance.cuh / advance.cuh) and, for the
     quad kernel, against both level loops (one CUDA graph per traversal / host-driven) and both ways of getting a
@@ -25,7 +25,7 @@ def ctx(request):
     import mini_b200
     c = mini_b200.Context(0)
     c.set_advance_impl(mini_b200.ADVANCE_LBS if request.param == "lbs" else
-                       mini_b200.ADVANCE_QUAD_WORKCREATE if "workcreate" in request.param else mini_b200.ADVANCE_QUAD)
+                       mini_b200.ADVANCE_QUAD_RESCAN if "rescan" in request.param else mini_b200.ADVANCE_QUAD)
     c.set_level_loop(mini_b200.LOOP_HOST if "hostloop" in request.param else mini_b200.LOOP_GRAPH)
     c.variant = request.param
     yield c
