@@ -253,7 +253,7 @@ def run_single_gpu(args):
     torch.cuda.set_device(dev)
     ctx = mb.Context(dev)
     global WORK_CREATE
-    WORK_CREATE = args.advance == "quad"
+    WORK_CREATE = args.advance == "quad" and (args.scale or 22) <= 23   # engine.cuh WORK_CREATE_MAX_N
     ctx.set_advance_impl({"lbs": mb.ADVANCE_LBS, "rescan": mb.ADVANCE_QUAD_RESCAN}.get(args.advance, mb.ADVANCE_QUAD))
     ctx.set_level_loop(mb.LOOP_HOST if args.loop == "host" else mb.LOOP_GRAPH)
     g = ctx.prepare_graph(ctx.rmat_graph(scale, 16, 1))   # graph build + one-time derived data: outside the timed region

@@ -146,7 +146,9 @@ int b200_ctx_l2_pin(b200_ctx *ctx, const void *d_ptr, int64_t bytes);
  *     that appends a discovered vertex to the next frontier also appends its row bounds and its position in the
  *     next level's quad scan -- slots and scan positions come from ONE packed 64-bit atomic, so the scan stays
  *     sorted -- and the next level starts without a scan kernel (scale-22 push BFS 0.571 -> 0.526 ms; the heaviest
- *     launch takes 0.2446 instead of 0.2314 ms for 5.5 % more bytes, profiles/README.md);
+ *     launch takes 0.2411 instead of 0.2297 ms for 5.5 % more bytes, profiles/README.md).  Graphs with more than
+ *     2^23 vertices keep the scan: their offsets no longer fit in L2 and the flush's reads become DRAM round trips
+ *     (scale 26: 10 % slower than the streaming scan kernel);
  *   B200_ADVANCE_QUAD_RESCAN: the same kernel with a degree scan before every level (transform_scan + transform_lbs
  *     as the reference orders them, advance.hxx:30-44);
  *   B200_ADVANCE_LBS: LBS over arcs, CTA-cooperative windows (include/b200/advance.cuh); also

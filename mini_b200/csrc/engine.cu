@@ -439,7 +439,7 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
     B200_CUDA(cudaGetLastError());
 
     int sel = 0, bsel = 0, level = 0, wsel = 0;
-    const bool work_create = quad && ctx->adv_impl == B200_ADVANCE_QUAD;   // (B200_ADVANCE_QUAD_RESCAN: scan before every level)
+    const bool work_create = quad && ctx->adv_impl == B200_ADVANCE_QUAD && n <= WORK_CREATE_MAX_N;   // (else: scan before every level)
     bool have_scan = false;
     int64_t next_quads = 0;
     int64_t flen = 1, unvisited = n - 1, reached = 1, total_arcs = 0;
@@ -578,7 +578,7 @@ int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist
     const int64_t launches0 = ws->launches;
 
     const bool quad = ctx->adv_impl != B200_ADVANCE_LBS && quad_aligned(g->col_indices) && quad_aligned(g->col_values);
-    const bool work_create = quad && ctx->adv_impl == B200_ADVANCE_QUAD;
+    const bool work_create = quad && ctx->adv_impl == B200_ADVANCE_QUAD && n <= WORK_CREATE_MAX_N;
     bool graph_done = false, have_scan = false;
     int64_t next_quads = 0;
     int wsel = 0;

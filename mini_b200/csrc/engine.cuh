@@ -63,6 +63,12 @@ inline int cuda_status(cudaError_t e) {
     } while (0)
 
 int ensure_traversal_scratch(b200_ctx *ctx, int64_t n);
+
+// The work-creating advance reads the row bounds of every vertex it emits inside its flush.  While the offsets
+// array is L2-resident (scale 22: 16 MB) that is cheaper than a scan kernel between the levels (push BFS 237.6 ->
+// 258 GTEPS); at scale 26 (268 MB of offsets, every read a DRAM round trip in the middle of a flush) it was 10 %
+// slower than the streaming scan kernel (8.33 -> 9.13 ms), so large graphs keep the scan.
+constexpr int64_t WORK_CREATE_MAX_N = 1ll << 23;
 // Pull levels walk every unvisited vertex; on RMAT half of them have no arc at all (scale 26: 34 M of 67 M) and
 // were re-inspected at every pull level.  The visited bitmap of a direction-optimising traversal therefore STARTS
 // as "vertex has no in-arc" instead of all-zero: such a vertex cannot be anybody's child, so no result changes

@@ -438,7 +438,7 @@ static int run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, 
     cudaStream_t st = ws_stream(ws);
     if (L->failed) return B200_ERR_UNSUPPORTED;
     const uint32_t *iso = (mode != B200_BFS_PUSH && mode != MODE_SSSP) ? g->no_in_arc_bitmap : nullptr;
-    const bool work_create = ctx->adv_impl == B200_ADVANCE_QUAD;   // (B200_ADVANCE_QUAD_RESCAN: scan before every level)
+    const bool work_create = ctx->adv_impl == B200_ADVANCE_QUAD && g->n <= WORK_CREATE_MAX_N;   // (else: scan before every level)
     if (!S->exec || S->k_offsets != g->row_offsets || S->k_indices != g->col_indices || S->k_labels != d_labels ||
         S->k_scratch != ctx->frontier[0] || S->k_n != g->n || S->k_mode != mode || S->k_iso != iso ||
         S->k_first != g->first_in_neighbor || S->k_weights != g->col_values || S->k_wc != work_create) {
