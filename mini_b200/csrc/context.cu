@@ -11,6 +11,7 @@ thread_local int g_last_cuda_error = 0;
 
 static void free_traversal_scratch(b200_ctx *ctx) {
     level_loop_invalidate(ctx);
+    ctx->scratch_gen++;
     for (int i = 0; i < 2; ++i) {
         if (ctx->frontier[i]) cudaFree(ctx->frontier[i]);
         if (ctx->bm_frontier[i]) cudaFree(ctx->bm_frontier[i]);
@@ -149,7 +150,10 @@ int b200_ctx_reserve(b200_ctx *ctx, int64_t max_items) {
     B200_CUDA(cudaSetDevice(ws.device));
     // smallest tile any scan-type kernel uses is 1024 items
     const int64_t tiles = (max_items + 1023) / 1024 + 1;
-    if (tiles > ws.status_tiles || max_items > ws.scanned_capacity) level_loop_invalidate(ctx);
+    if (tiles > ws.status_tiles || max_items > ws.scanned_capacity) {
+        level_loop_invalidate(ctx);
+        ctx->scratch_gen++;
+    }
     if (tiles > ws.status_tiles) {
         B200_CUDA(cudaStreamSynchronize((cudaStream_t)ws.stream));
         if (ws.d_status) cudaFree(ws.d_status);

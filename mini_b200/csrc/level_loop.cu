@@ -65,6 +65,7 @@ struct LevelLoop {
         cudaGraphExec_t exec;
         const void *k_offsets, *k_indices, *k_labels, *k_scratch, *k_iso, *k_first, *k_weights;
         int64_t k_n;
+        uint64_t k_gen;
         int k_mode;
         bool k_wc;
     } slot[2];
@@ -373,6 +374,7 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
     S->k_iso = iso;
     S->k_first = g->first_in_neighbor;
     S->k_n = n;
+    S->k_gen = ctx->scratch_gen;
     S->k_mode = mode;
     S->k_wc = work_create;
     ws->stream = user_stream;
@@ -441,7 +443,8 @@ static int run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, 
     const bool work_create = ctx->adv_impl == B200_ADVANCE_QUAD && g->n <= WORK_CREATE_MAX_N;   // (else: scan before every level)
     if (!S->exec || S->k_offsets != g->row_offsets || S->k_indices != g->col_indices || S->k_labels != d_labels ||
         S->k_scratch != ctx->frontier[0] || S->k_n != g->n || S->k_mode != mode || S->k_iso != iso ||
-        S->k_first != g->first_in_neighbor || S->k_weights != g->col_values || S->k_wc != work_create) {
+        S->k_first != g->first_in_neighbor || S->k_weights != g->col_values || S->k_wc != work_create ||
+        S->k_gen != ctx->scratch_gen) {
         B200_CUDA(cudaStreamSynchronize(st));   // a replay of the old graph may still be running
         const int bs = build_graph(ctx, g, d_labels, mode, iso, work_create);
         if (bs != B200_OK) {

@@ -623,6 +623,7 @@ struct b200_p2p_bfs {
     cudaGraphExec_t exec;
     unsigned long long *d_trace;
     const void *k_offsets, *k_indices, *k_labels, *k_scratch, *k_iso, *k_first;
+    uint64_t k_gen;            // b200_ctx::scratch_gen the graph was built against
     int k_mode;
     int graph_failed;
 };
@@ -776,6 +777,7 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
     s->k_scratch = ctx->frontier[0];
     s->k_iso = g->no_in_arc_bitmap;
     s->k_first = g->first_in_neighbor;
+    s->k_gen = ctx->scratch_gen;
     s->k_mode = mode;
     ws->stream = user_stream;
     ws->launches = launches0;
@@ -808,7 +810,7 @@ int p2p_ensure_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, in
     }
     if (!s->exec || s->k_offsets != g->row_offsets || s->k_indices != g->col_indices || s->k_labels != d_labels ||
         s->k_scratch != ctx->frontier[0] || s->k_mode != mode || s->k_iso != g->no_in_arc_bitmap ||
-        s->k_first != g->first_in_neighbor) {
+        s->k_first != g->first_in_neighbor || s->k_gen != ctx->scratch_gen) {
         B200_CUDA(cudaStreamSynchronize(st));
         const int bs = p2p_build_graph(s, g, d_labels, mode);
         if (bs != B200_OK) {

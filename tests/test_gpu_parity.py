@@ -176,6 +176,15 @@ def test_graph_level_loop_is_used_and_matches_host_loop(mode):
                 key = lambda st: [(l["direction"], l["frontier_len"], l["arcs"], l["discovered"]) for l in st.levels]
                 assert key(sa) == key(sb)
                 assert sa.launches > 0
+        # a larger graph reallocates the ctx scratch the cached traversal graph points into: it must be rebuilt
+        small = graphs[1]
+        ref_small, _ = _bfs(c, small, 3, mode)
+        ref_small = ref_small.clone()
+        big = c.rmat_graph(16, 16, 1)
+        c.set_level_loop(mb.LOOP_GRAPH)
+        _bfs(c, big, 0, mode)
+        again, st_again = _bfs(c, small, 3, mode)
+        assert st_again.level_loop == "graph" and torch.equal(again, ref_small)
         # SSSP: the Bellman-Ford frontier iterations replay as a graph too (bit-identical distances)
         gw = c.rmat_graph(13, 16, 1, weighted=True)
         c.set_level_loop(mb.LOOP_GRAPH)
