@@ -218,7 +218,10 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     import oracle
-    scale = args.scale or 22
+    # N = 1: the arm's own workload (scale 22).  N > 1: the arm runs scale 26, whose CSR (2^31 arcs) the reference's
+    # int32 CPU path cannot hold and whose host-side build alone takes minutes: the bounded sample is the same
+    # generator at scale 24 (a quarter of the vertices and arcs; GTEPS is a rate)
+    scale = args.scale or (22 if args.gpus <= 1 else 24)
     t0 = time.time()
     g = oracle.rmat_csr(scale, 16, 1)
     gen_s = time.time() - t0
@@ -232,7 +235,8 @@ def run_reference_arm(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": f"BFS from vertex 0, RMAT scale-{scale} ef16 symmetrised (n={g.n}, m={g.m}), "
-                               "reference CPU validation BFS bfs_problem.hxx:52-72",
+                               "reference CPU validation BFS bfs_problem.hxx:52-72"
+                               + ("" if args.gpus <= 1 or args.scale else " -- bounded sample of the N>1 arm's scale-26 workload"),
                    "graph_build_s": round(gen_s, 2)},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind,
                          "sample": f"{len(times)} full BFS runs from vertex 0 on the whole scale-{scale} graph",
