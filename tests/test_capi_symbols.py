@@ -63,3 +63,46 @@ def test_product_never_imports_oracle():
         for f in files:
             txt = open(os.path.join(d, f)).read()
             assert "#include \"oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_header_is_plain_c_and_ctypes_layouts_match(tmp_path):
+    """include/b200_frontier.h must compile as C99 (it is the FFI boundary) and the ctypes mirrors in
+    mini_b200/lib.py must have exactly the C layouts (sizes and a few offsets) -- ABI drift shows up here, on the CPU."""
+    import subprocess
+    from mini_b200 import lib as L
+    src = tmp_path / "layout.c"
+    src.write_text(r'''
+#include <stddef.h>
+#include <stdio.h>
+#include "b200_frontier.h"
+#include "b200/workspace.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(b200_graph), offsetof(b200_graph, no_in_arc_bitmap),
+           offsetof(b200_graph, first_in_neighbor), sizeof(b200_problem), sizeof(b200_level_stat), sizeof(b200_stats),
+           offsetof(b200_stats, level_loop), offsetof(b200_stats, level), offsetof(b200_workspace, launches),
+           (size_t)B200_ABI_VERSION);
+    return 0;
+}
+''')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True, capture_output=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = [C.sizeof(L.CGraph), L.CGraph.no_in_arc_bitmap.offset, L.CGraph.first_in_neighbor.offset, C.sizeof(L.CProblem),
+            C.sizeof(L.CLevelStat), C.sizeof(L.CStats), L.CStats.level_loop.offset, L.CStats.level.offset]
+    assert got[:8] == want, (got, want)
+    assert got[9] == 2
+    # dist_bench.py reads b200_workspace::launches through a prefix mirror of the struct
+    import re
+    txt = open(os.path.join(ROOT, "mini_b200", "dist_bench.py")).read()
+    assert '("launches", C.c_int64)' in txt
+    fields = re.findall(r'\("(\w+)", C\.(c_\w+)\)', txt[txt.index("class _WS"):txt.index("ws = C.cast")])
+    sizes = {"c_void_p": 8, "c_int32": 4, "c_int64": 8, "c_uint": 4}
+    off = 0
+    for name, ty in fields:
+        sz = sizes[ty]
+        off = (off + sz - 1) // sz * sz
+        if name == "launches":
+            break
+        off += sz
+    assert off == got[8], (off, got[8])
