@@ -21,17 +21,16 @@ namespace gunrock {
 namespace bfs {
 
 struct bfs_enactor_t : enactor_t {
+    using problem_ptr = std::shared_ptr<bfs_problem_t>;
+    using P = bfs_problem_t;
+    using F = bfs_functor_t;
+
     bfs_enactor_t(standard_context_t &context, int num_nodes, int num_edges) : enactor_t(context, num_nodes, num_edges) {}
-    bfs_enactor_t(const bfs_enactor_t &) = delete;
-    bfs_enactor_t &operator=(const bfs_enactor_t &) = delete;
 
-    void init_frontier(std::shared_ptr<bfs_problem_t> bfs_problem) {
-        buffers[0]->load(std::vector<int>(1, bfs_problem->src));
-    }
+    // the frontier of level 0 is the source alone
+    void init_frontier(problem_ptr bfs_problem) { buffers[0]->load(std::vector<int>(1, bfs_problem->src)); }
 
-    void enact_pushpull(std::shared_ptr<bfs_problem_t> bfs_problem, float threshold, standard_context_t &context) {
-        typedef bfs_problem_t P;
-        typedef bfs_functor_t F;
+    void enact_pushpull(problem_ptr bfs_problem, float threshold, standard_context_t &context) {
         init_frontier(bfs_problem);
         const int num_nodes = bfs_problem->gslice->num_nodes;
         int remaining = num_nodes - 1;   // vertices without a label
@@ -70,8 +69,8 @@ struct bfs_enactor_t : enactor_t {
 
     // Whole traversal inside the engine; labels land in bfs_problem->d_labels.
     // mode: B200_BFS_PUSH / B200_BFS_REF_ALPHA (threshold = alpha) / B200_BFS_BEAMER.
-    int enact_builtin(std::shared_ptr<bfs_problem_t> bfs_problem, int mode, float alpha, float beta,
-                      standard_context_t &context, b200_stats *stats = nullptr) {
+    int enact_builtin(problem_ptr bfs_problem, int mode, float alpha, float beta, standard_context_t &context,
+                      b200_stats *stats = nullptr) {
         const b200_graph g = bfs_problem->gslice->view();
         return b200_bfs_run(context.engine(), &g, bfs_problem->src, mode, alpha, beta, bfs_problem->d_labels.data(), stats);
     }

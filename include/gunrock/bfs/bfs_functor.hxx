@@ -10,12 +10,12 @@ struct bfs_functor_t {
     typedef bfs_problem_t::data_slice_t slice_t;
 
     // filter: drop the -1 holes an un-compacted advance leaves
-    static __device__ __forceinline__ bool cond_filter(int idx, slice_t *data, int iteration) { return idx != -1; }
+    GUNROCK_FN bool cond_filter(GUNROCK_VERTEX_ARGS(slice_t)) { return idx != -1; }
 
     // uniquify: label a vertex the first time it is seen.  Valid for every source and for
     // vertex 0 (the reference's version only accepts idx > 0 and labels > 0);
     // exactness comes from the visited-bit test-and-set that precedes this call.
-    static __device__ __forceinline__ bool cond_uniq(int idx, slice_t *data, int iteration) {
+    GUNROCK_FN bool cond_uniq(GUNROCK_VERTEX_ARGS(slice_t)) {
         if (idx < 0) return false;
         const int seen = data->d_labels[idx];
         if (seen >= 0 && seen <= iteration) return false;
@@ -24,26 +24,24 @@ struct bfs_functor_t {
     }
 
     // advance: visit dst if nobody has yet; the compare-and-swap decides the winner
-    static __device__ __forceinline__ bool cond_advance(int src, int dst, int edge_id, int rank, int output_idx,
-                                                        slice_t *data, int iteration) {
+    GUNROCK_FN bool cond_advance(GUNROCK_ARC_ARGS(slice_t)) {
         return data->d_labels[dst] == -1;
     }
-    static __device__ __forceinline__ bool apply_advance(int src, int dst, int edge_id, int rank, int output_idx,
-                                                         slice_t *data, int iteration) {
+    GUNROCK_FN bool apply_advance(GUNROCK_ARC_ARGS(slice_t)) {
         return atomicCAS(data->d_labels + dst, -1, iteration + 1) == -1;
     }
 
     // push -> pull hand-over
-    static __device__ __forceinline__ bool cond_sparse_to_dense(int idx, slice_t *data, int iteration) {
+    GUNROCK_FN bool cond_sparse_to_dense(GUNROCK_VERTEX_ARGS(slice_t)) {
         return data->d_labels[idx] == iteration;
     }
-    static __device__ __forceinline__ bool cond_gen_unvisited(int idx, slice_t *data, int iteration) {
+    GUNROCK_FN bool cond_gen_unvisited(GUNROCK_VERTEX_ARGS(slice_t)) {
         return data->d_labels[idx] == -1;
     }
 
     // neighborhood-reduce hooks (unused by BFS itself)
-    static __device__ __forceinline__ int get_value_to_reduce(int idx, slice_t *data, int iteration) { return iteration; }
-    static __device__ __forceinline__ void write_reduced_value(int item, int val, slice_t *data, int iteration) {}
+    GUNROCK_FN int get_value_to_reduce(GUNROCK_VERTEX_ARGS(slice_t)) { return iteration; }
+    GUNROCK_FN void write_reduced_value(int item, int val, slice_t *data, int iteration) {}
 };
 
 }  // namespace bfs

@@ -8,37 +8,37 @@ namespace gunrock {
 namespace bfs {
 
 struct bfs_problem_t : problem_t {
-    mem_t<int> d_labels;
-    mem_t<int> d_preds;
-    std::vector<int> labels;
-    std::vector<int> preds;
-    int src = 0;
-
+    // what bfs_functor_t reads and writes, as raw device pointers
     struct data_slice_t {
-        int *d_labels;
-        int *d_preds;
-        void init(mem_t<int> &_labels, mem_t<int> &_preds) {
-            d_labels = _labels.data();
-            d_preds = _preds.data();
-        }
+        int *d_labels, *d_preds;
     };
+
+    int src = 0;
+    std::vector<int> labels, preds;        // host copies (extract() refreshes labels)
+    mem_t<int> d_labels, d_preds;
     mem_t<data_slice_t> d_data_slice;
-    std::vector<data_slice_t> data_slice;
 
-    bfs_problem_t() {}
-    bfs_problem_t(const bfs_problem_t &) = delete;
-    bfs_problem_t &operator=(const bfs_problem_t &) = delete;
+    bfs_problem_t() = default;
 
-    bfs_problem_t(std::shared_ptr<graph_device_t> rhs, size_t src, standard_context_t &context)
-        : problem_t(rhs), labels(rhs->num_nodes, -1), preds(rhs->num_nodes, -1), src((int)src), data_slice(1) {
-        labels[src] = 0;
+    bfs_problem_t(std::shared_ptr<graph_device_t> graph, size_t source, standard_context_t &context)
+        : problem_t(graph), src((int)source), labels(graph->num_nodes, -1), preds(graph->num_nodes, -1) {
+        labels[source] = 0;                // the source is at depth 0, everything else unvisited
         d_labels = to_mem(labels, context);
         d_preds = to_mem(preds, context);
-        data_slice[0].init(d_labels, d_preds);
-        d_data_slice = to_mem(data_slice, context);
+        d_data_slice = publish_slice(data_slice_t{d_labels.data(), d_preds.data()}, context);
     }
 
     void extract() { mgpu::dtoh(labels, d_labels.data(), gslice->num_nodes); }
+
+    // The same data as the engine's POD (b200_frontier.h), for calling the C ABI operators on this problem.
+    b200_problem engine_view(uint32_t *d_visited_bitmap = nullptr) {
+        b200_problem p = {};
+        p.kind = B200_PROBLEM_BFS;
+        p.labels = d_labels.data();
+        p.preds = d_preds.data();
+        p.visited_bitmap = d_visited_bitmap;
+        return p;
+    }
 
     // Host validation: level-synchronous BFS over a FIFO, same result as the reference's
     // queue BFS (bfs_problem.hxx:52-72).  validation_labels must come in as all -1.

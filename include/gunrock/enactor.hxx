@@ -10,10 +10,10 @@ using namespace mgpu;
 namespace gunrock {
 
 struct enactor_t {
-    std::vector<std::shared_ptr<frontier_t<int>>> buffers;
-    std::shared_ptr<frontier_t<int>> indices;
-    std::shared_ptr<frontier_t<int>> filtered_indices;
-    std::vector<std::shared_ptr<frontier_t<int>>> unvisited;
+    using frontier_ptr = std::shared_ptr<frontier_t<int>>;
+    std::vector<frontier_ptr> buffers;      // ping-pong frontiers
+    frontier_ptr indices, filtered_indices; // iota(n) and its filtered twin ...
+    std::vector<frontier_ptr> unvisited;    // ... as the ping-pong pair the pull phase walks
 
     enactor_t(standard_context_t &context, int num_nodes, int num_edges, float queue_sizing = 1.0f) {
         init(context, num_nodes, num_edges, queue_sizing);
@@ -25,14 +25,14 @@ struct enactor_t {
         // capacity as in the reference (num_edges * queue_sizing) so RAW-layout advances fit;
         // never below num_nodes because the pull phase stores per-vertex flags in these buffers
         const size_t cap = std::max((size_t)((double)num_edges * queue_sizing), (size_t)num_nodes);
-        for (int k = 0; k < 2; ++k) buffers.push_back(std::make_shared<frontier_t<int>>(context, cap));
-        indices = std::make_shared<frontier_t<int>>(context, num_nodes);
-        filtered_indices = std::make_shared<frontier_t<int>>(context, num_nodes);
+        auto make = [&](size_t capacity) { return std::make_shared<frontier_t<int>>(context, capacity); };
+        buffers = {make(cap), make(cap)};
+        indices = make(num_nodes);
+        filtered_indices = make(num_nodes);
         mem_t<int> iota = fill_function<int>([] __device__(int i) { return i; }, num_nodes, context);
         indices->load(iota);
         filtered_indices->load(iota);
-        unvisited.push_back(indices);
-        unvisited.push_back(filtered_indices);
+        unvisited = {indices, filtered_indices};
         b200_ctx_reserve(context.engine(), (int64_t)cap);
     }
 };

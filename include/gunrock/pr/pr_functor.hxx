@@ -13,7 +13,7 @@ struct pr_functor_t {
     typedef pr_problem_t::data_slice_t slice_t;
 
     // rank update + convergence test: keep the vertex while its rank still moves by > 0.1 %
-    static __device__ __forceinline__ bool cond_filter(int idx, slice_t *data, int iteration) {
+    GUNROCK_FN bool cond_filter(GUNROCK_VERTEX_ARGS(slice_t)) {
         const float before = data->d_current_ranks[idx];
         const float deg = data->d_degrees[idx];
         float after = 0.15f;
@@ -23,18 +23,16 @@ struct pr_functor_t {
         return fabs(after - before) > (0.001f * before);
     }
 
-    static __device__ __forceinline__ bool cond_advance(int src, int dst, int edge_id, int rank, int output_idx,
-                                                        slice_t *data, int iteration) { return true; }
-    static __device__ __forceinline__ bool apply_advance(int src, int dst, int edge_id, int rank, int output_idx,
-                                                         slice_t *data, int iteration) { return true; }
+    GUNROCK_FN bool cond_advance(GUNROCK_ARC_ARGS(slice_t)) { return true; }
+    GUNROCK_FN bool apply_advance(GUNROCK_ARC_ARGS(slice_t)) { return true; }
 
     // a neighbour contributes its current rank (non-finite ranks count as 0)
-    static __device__ __forceinline__ float get_value_to_reduce(int idx, slice_t *data, int iteration) {
+    GUNROCK_FN float get_value_to_reduce(GUNROCK_VERTEX_ARGS(slice_t)) {
         const float r = data->d_current_ranks[idx];
         return isfinite(r) ? r : 0.0f;
     }
     // scatter hook for neighborhood_kernel<..., write_back = true>
-    static __device__ __forceinline__ void write_reduced_value(int item, float val, slice_t *data, int iteration) {
+    GUNROCK_FN void write_reduced_value(int item, float val, slice_t *data, int iteration) {
         data->d_reduced_ranks[item] = val;
     }
 };

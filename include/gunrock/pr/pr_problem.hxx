@@ -7,39 +7,29 @@ namespace gunrock {
 namespace pr {
 
 struct pr_problem_t : problem_t {
-    mem_t<float> d_current_ranks;
-    mem_t<float> d_reduced_ranks;
-    mem_t<float> d_degrees;
-    int max_iter = 0;
-
+    // what pr_functor_t reads and writes, as raw device pointers
     struct data_slice_t {
-        float *d_current_ranks;
-        float *d_reduced_ranks;
-        float *d_degrees;
-        void init(mem_t<float> &_current_ranks, mem_t<float> &_reduced_ranks, mem_t<float> &_degrees) {
-            d_current_ranks = _current_ranks.data();
-            d_reduced_ranks = _reduced_ranks.data();
-            d_degrees = _degrees.data();
-        }
+        float *d_current_ranks, *d_reduced_ranks, *d_degrees;
     };
+
+    static constexpr float kInitialRank = 0.15f;   // pr_problem.hxx:38
+    int max_iter = 0;
+    mem_t<float> d_current_ranks, d_reduced_ranks, d_degrees;
     mem_t<data_slice_t> d_data_slice;
-    std::vector<data_slice_t> data_slice;
 
-    pr_problem_t() {}
-    pr_problem_t(const pr_problem_t &) = delete;
-    pr_problem_t &operator=(const pr_problem_t &) = delete;
+    pr_problem_t() = default;
 
-    pr_problem_t(std::shared_ptr<graph_device_t> rhs, int max_iter, standard_context_t &context)
-        : problem_t(rhs), max_iter(max_iter), data_slice(1) {
-        d_current_ranks = mgpu::fill(0.15f, rhs->num_nodes, context);
-        d_reduced_ranks = mgpu::fill(0.0f, rhs->num_nodes, context);
-        d_degrees = mgpu::fill(0.0f, rhs->num_nodes, context);
+    pr_problem_t(std::shared_ptr<graph_device_t> graph, int iterations, standard_context_t &context)
+        : problem_t(graph), max_iter(iterations) {
+        const int n = graph->num_nodes;
+        d_current_ranks = mgpu::fill(kInitialRank, n, context);
+        d_reduced_ranks = mgpu::fill(0.0f, n, context);
+        d_degrees = mgpu::fill(0.0f, n, context);
         GetDegrees(d_degrees, context);
-        data_slice[0].init(d_current_ranks, d_reduced_ranks, d_degrees);
-        d_data_slice = to_mem(data_slice, context);
+        d_data_slice = publish_slice(data_slice_t{d_current_ranks.data(), d_reduced_ranks.data(), d_degrees.data()}, context);
     }
 
-    void extract() {}
+    void extract() {}   // (the reference's is empty too: test_pr.cu never reads the ranks back)
 };
 
 }  // namespace pr

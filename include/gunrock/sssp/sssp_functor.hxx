@@ -15,21 +15,19 @@ struct sssp_functor_t {
 
     // keep a vertex once per iteration: the stamp test-and-set is one atomic exchange here
     // (the reference reads then writes d_visited non-atomically and may keep duplicates)
-    static __device__ __forceinline__ bool cond_filter(int idx, slice_t *data, int iteration) {
+    GUNROCK_FN bool cond_filter(GUNROCK_VERTEX_ARGS(slice_t)) {
         if (idx == -1) return false;
         return atomicExch(data->d_visited + idx, iteration) != iteration;
     }
 
     // relax src -> dst; true when this thread lowered dst's distance
-    static __device__ __forceinline__ bool cond_advance(int src, int dst, int edge_id, int rank, int output_idx,
-                                                        slice_t *data, int iteration) {
+    GUNROCK_FN bool cond_advance(GUNROCK_ARC_ARGS(slice_t)) {
         const float through_src = data->d_labels[src] + data->d_weights[edge_id];
         return through_src < atomicMin(data->d_labels + dst, through_src);
     }
 
     // record the tail as predecessor (last writer wins, as in the reference)
-    static __device__ __forceinline__ bool apply_advance(int src, int dst, int edge_id, int rank, int output_idx,
-                                                         slice_t *data, int iteration) {
+    GUNROCK_FN bool apply_advance(GUNROCK_ARC_ARGS(slice_t)) {
         data->d_preds[dst] = src;
         return true;
     }

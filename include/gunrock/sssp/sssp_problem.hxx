@@ -11,41 +11,33 @@ namespace gunrock {
 namespace sssp {
 
 struct sssp_problem_t : problem_t {
-    mem_t<float> d_labels;
-    mem_t<int> d_preds;
-    mem_t<int> d_visited;
-    std::vector<float> labels;
-    std::vector<int> preds;
-    int src = 0;
-
+    // what sssp_functor_t reads and writes, as raw device pointers (member ORDER as in the reference: labels, preds,
+    // weights, visited)
     struct data_slice_t {
         float *d_labels;
         int *d_preds;
         float *d_weights;
         int *d_visited;
-        void init(mem_t<float> &_labels, mem_t<int> &_preds, mem_t<float> &_weights, mem_t<int> &_visited) {
-            d_labels = _labels.data();
-            d_preds = _preds.data();
-            d_weights = _weights.data();
-            d_visited = _visited.data();
-        }
     };
+
+    int src = 0;
+    std::vector<float> labels;             // host copies, refreshed by extract()
+    std::vector<int> preds;
+    mem_t<float> d_labels;
+    mem_t<int> d_preds, d_visited;
     mem_t<data_slice_t> d_data_slice;
-    std::vector<data_slice_t> data_slice;
 
-    sssp_problem_t() {}
-    sssp_problem_t(const sssp_problem_t &) = delete;
-    sssp_problem_t &operator=(const sssp_problem_t &) = delete;
+    sssp_problem_t() = default;
 
-    sssp_problem_t(std::shared_ptr<graph_device_t> rhs, size_t src, standard_context_t &context)
-        : problem_t(rhs), labels(rhs->num_nodes, std::numeric_limits<float>::max()), preds(rhs->num_nodes, -1),
-          src((int)src), data_slice(1) {
-        labels[src] = 0;
+    sssp_problem_t(std::shared_ptr<graph_device_t> graph, size_t source, standard_context_t &context)
+        : problem_t(graph), src((int)source), labels(graph->num_nodes, std::numeric_limits<float>::max()),
+          preds(graph->num_nodes, -1) {
+        labels[source] = 0;                // unreached = FLT_MAX, the source is at distance 0
         d_labels = to_mem(labels, context);
         d_preds = to_mem(preds, context);
-        d_visited = mgpu::fill(-1, rhs->num_nodes, context);
-        data_slice[0].init(d_labels, d_preds, gslice->d_col_values, d_visited);
-        d_data_slice = to_mem(data_slice, context);
+        d_visited = mgpu::fill(-1, graph->num_nodes, context);   // per-iteration dedupe stamps
+        d_data_slice = publish_slice(
+            data_slice_t{d_labels.data(), d_preds.data(), gslice->d_col_values.data(), d_visited.data()}, context);
     }
 
     void extract() {
