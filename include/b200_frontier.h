@@ -45,7 +45,9 @@ enum {
     B200_ERR_OVERFLOW = 3,  /* an output frontier exceeded the capacity the caller gave */
     B200_ERR_NOMEM = 4,
     B200_ERR_UNSUPPORTED = 5,
-    B200_ERR_TIMEOUT = 6    /* a cross-GPU barrier of the peer-memory path waited too long for a peer */
+    B200_ERR_TIMEOUT = 6,   /* a cross-GPU barrier of the peer-memory path waited too long for a peer */
+    B200_ERR_IO = 7,        /* a file could not be opened, read or written */
+    B200_ERR_FORMAT = 8     /* a file is not what it should be (malformed .mtx, bad / truncated / corrupt CSR cache) */
 };
 
 typedef struct b200_ctx b200_ctx; /* replaces mgpu::standard_context_t (context.hxx:103-219) + per-call mem_t scratch */
@@ -354,6 +356,26 @@ int b200_p2p_bfs_run(b200_p2p_bfs *s, const b200_graph *g_local, int64_t m_globa
  * uses B200_LOOP_HOST.  b200_p2p_bfs_run builds lazily if this was not called. */
 int b200_p2p_bfs_prepare(b200_p2p_bfs *s, const b200_graph *g_local, int mode, int32_t *d_labels_local);
 int b200_p2p_bfs_destroy(b200_p2p_bfs *s);
+
+/* ---- graph ingest on the host (no GPU involved): the .mtx loader of the reference and a binary CSR cache ---- */
+/* Host CSR owned by the library (malloc; release with b200_host_csr_free). */
+typedef struct b200_host_csr {
+    int64_t n, m;
+    uint32_t *row_offsets; /* [n+1] */
+    int32_t *col_indices;  /* [m]   */
+    float *col_values;     /* [m] or NULL */
+} b200_host_csr;
+/* load_graph (graph.hxx:96-223) for hosts that cannot include the C++ headers: "%" comment lines, a "rows cols
+ * entries" line, then 1-based "i j [w]" entries; entry (i, j) is the arc (j-1) -> (i-1) with weight w (1.0 if absent);
+ * `undirected` appends every reverse; arcs ordered by (row, column) with a STABLE sort (the reference's comparator is
+ * not a strict weak order, :139-157), duplicates and self loops kept.  The result feeds b200_host_graph_upload.
+ * B200_ERR_IO: cannot open; B200_ERR_FORMAT: malformed (the reference prints and exit(0)s, :108-111,:121-124). */
+int b200_mtx_load(const char *path, int undirected, b200_host_csr *out);
+/* Binary cache of a host CSR: 32-byte header (magic "B200CSR1", n, m, flags), the three arrays, FNV-1a checksum.
+ * Reading verifies magic, sizes, checksum, offset monotonicity and index range (B200_ERR_FORMAT otherwise). */
+int b200_csr_cache_write(const char *path, const b200_host_csr *csr);
+int b200_csr_cache_read(const char *path, b200_host_csr *out);
+int b200_host_csr_free(b200_host_csr *csr);
 
 /* ---- host-buffer entry points (what test_bfs.cu times + extract: H2D, run, D2H) */
 typedef struct b200_host_graph b200_host_graph; /* graph_to_device result (graph.hxx:60-83) kept by the engine */

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb200_frontier.so")
-SOURCES = ["context.cu", "graph_build.cu", "engine.cu", "level_loop.cu", "multi_gpu.cu", "p2p_bfs.cu"]
+SOURCES = ["context.cu", "graph_build.cu", "engine.cu", "level_loop.cu", "multi_gpu.cu", "p2p_bfs.cu", "ingest.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",

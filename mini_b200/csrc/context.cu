@@ -96,6 +96,8 @@ const char *b200_status_string(int status) {
         case B200_ERR_NOMEM: return "out of device memory";
         case B200_ERR_UNSUPPORTED: return "unsupported";
         case B200_ERR_TIMEOUT: return "a peer GPU did not reach a barrier in time";
+        case B200_ERR_IO: return "file could not be opened, read or written";
+        case B200_ERR_FORMAT: return "malformed file";
         default: return "unknown status";
     }
 }

@@ -31,6 +31,11 @@ class CGraph(C.Structure):
                 ("row_values", C.c_void_p), ("no_in_arc_bitmap", C.c_void_p), ("first_in_neighbor", C.c_void_p)]
 
 
+class CHostCSR(C.Structure):
+    _fields_ = [("n", C.c_int64), ("m", C.c_int64), ("row_offsets", C.c_void_p), ("col_indices", C.c_void_p),
+                ("col_values", C.c_void_p)]
+
+
 class CProblem(C.Structure):
     _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("labels", C.c_void_p), ("preds", C.c_void_p),
                 ("dist", C.c_void_p), ("weights", C.c_void_p), ("visited", C.c_void_p),
@@ -122,6 +127,10 @@ def load_library():
         "b200_p2p_bfs_run": ([vp, pg, i64, i32, i32, f32, f32, vp, ps, pi64], i32),
         "b200_p2p_bfs_prepare": ([vp, pg, i32, vp], i32),
         "b200_p2p_bfs_destroy": ([vp], i32),
+        "b200_mtx_load": ([C.c_char_p, i32, C.POINTER(CHostCSR)], i32),
+        "b200_csr_cache_write": ([C.c_char_p, C.POINTER(CHostCSR)], i32),
+        "b200_csr_cache_read": ([C.c_char_p, C.POINTER(CHostCSR)], i32),
+        "b200_host_csr_free": ([C.POINTER(CHostCSR)], i32),
         "b200_host_graph_upload": ([vp, i64, i64, vp, vp, vp, C.POINTER(vp)], i32),
         "b200_host_graph_free": ([vp, vp], i32),
         "b200_host_graph_view": ([vp, pg], i32),
@@ -415,6 +424,48 @@ class Context:
         _check(self._L.b200_sssp_host(self._h, hg, src, dist_init_ptr, dist_out_ptr, preds_out_ptr, C.byref(cs)),
                "b200_sssp_host")
         return Stats(cs)
+
+
+def _copy_out(h: CHostCSR):
+    import numpy as np
+    n, m = h.n, h.m
+    off = np.ctypeslib.as_array(C.cast(h.row_offsets, C.POINTER(C.c_uint32)), (n + 1,)).copy()
+    idx = np.ctypeslib.as_array(C.cast(h.col_indices, C.POINTER(C.c_int32)), (max(m, 1),))[:m].copy()
+    w = None
+    if h.col_values:
+        w = np.ctypeslib.as_array(C.cast(h.col_values, C.POINTER(C.c_float)), (max(m, 1),))[:m].copy()
+    return n, off, idx, w
+
+
+def load_mtx(path: str, undirected: bool = False):
+    """b200_mtx_load (the reference's load_graph semantics) -> (n, offsets uint32 [n+1], indices int32 [m], weights f32 [m])."""
+    L = load_library()
+    h = CHostCSR()
+    _check(L.b200_mtx_load(os.fsencode(path), int(undirected), C.byref(h)), "b200_mtx_load")
+    try:
+        return _copy_out(h)
+    finally:
+        L.b200_host_csr_free(C.byref(h))
+
+
+def write_csr_cache(path: str, offsets_u32, indices_i32, weights_f32=None):
+    import numpy as np
+    L = load_library()
+    off = np.ascontiguousarray(offsets_u32, dtype=np.uint32)
+    idx = np.ascontiguousarray(indices_i32, dtype=np.int32)
+    w = None if weights_f32 is None else np.ascontiguousarray(weights_f32, dtype=np.float32)
+    h = CHostCSR(len(off) - 1, len(idx), off.ctypes.data, idx.ctypes.data, None if w is None else w.ctypes.data)
+    _check(L.b200_csr_cache_write(os.fsencode(path), C.byref(h)), "b200_csr_cache_write")
+
+
+def read_csr_cache(path: str):
+    L = load_library()
+    h = CHostCSR()
+    _check(L.b200_csr_cache_read(os.fsencode(path), C.byref(h)), "b200_csr_cache_read")
+    try:
+        return _copy_out(h)
+    finally:
+        L.b200_host_csr_free(C.byref(h))
 
 
 def bfs_problem(labels, visited_bitmap, preds=None) -> CProblem:
