@@ -144,3 +144,29 @@ def test_empty_graph_cache(tmp_path):
     L.write_csr_cache(p, np.zeros(5, np.uint32), np.zeros(0, np.int32))
     n, off, idx, w = L.read_csr_cache(p)
     assert n == 4 and off.tolist() == [0] * 5 and len(idx) == 0 and w is None
+
+
+def test_plain_c_host_uses_the_abi(tmp_path, golden):
+    """examples/ingest_host.c: a C99 program (gcc, no CUDA / C++ headers) drives the C ABI -- .mtx ingest, CSR cache
+    round trip, and (only with a GPU) upload + BFS.  Without a GPU it must say so instead of computing on the CPU."""
+    import subprocess
+    exe = tmp_path / "ingest_host"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-D_POSIX_C_SOURCE=200809L", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "ingest_host.c"), "-L", os.path.join(ROOT, "mini_b200"), "-lb200_frontier",
+                    "-Wl,-rpath," + os.path.join(ROOT, "mini_b200"), "-o", str(exe)], check=True, capture_output=True)
+    rec = golden("ref_fixture_bfs.json")
+    p = tmp_path / "g.mtx"
+    with open(p, "w") as f:
+        f.write(" ".join(str(x) for x in rec["mtx_header"]) + "\n")
+        for e in rec["mtx_edges"]:
+            f.write(" ".join(str(int(x)) if k < 2 else repr(x) for k, x in enumerate(e)) + "\n")
+    r = subprocess.run([str(exe), str(p), "--undirected", "--bfs", str(rec["src"])], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ref = oracle.load_mtx(str(p), True)
+    assert f"n={ref.n} m={ref.m} " in r.stdout and "cache_round_trip=ok" in r.stdout
+    import torch
+    if torch.cuda.is_available():
+        depths = oracle.bfs(ref, rec["src"])
+        assert f"reached={int((depths >= 0).sum())} depth={int(depths.max())}" in r.stdout, r.stdout
+    else:
+        assert "bfs skipped: no CUDA device" in r.stdout
