@@ -309,6 +309,11 @@ class Context:
         w = None if weights is None else torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float32)).to(self.torch_device)
         return Graph(len(offsets) - 1, int(offsets[-1]), off, idx, w)
 
+    def graph_from_mtx(self, path: str, undirected: bool = False) -> Graph:
+        """MatrixMarket file -> device Graph, with the reference's load_graph semantics (b200_mtx_load)."""
+        _n, off, idx, w = load_mtx(path, undirected)
+        return self.graph_from_host(off, idx, w)
+
     # ------------------------------------------------------------------ primitives
     def bfs(self, g: Graph, src: int = 0, mode: int = BFS_PUSH, alpha: float = 0.0, beta: float = 0.0,
             labels=None, timing: bool = False):
