@@ -23,7 +23,12 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "bfs_gteps_rmat"
+# Distinct metric names per workload: the N=1 line is BASELINE.json configs[1] (scale-22 push BFS), the N>1 lines are
+# configs[3] (scale-26 direction-optimising BFS) -- a scaling curve v_N / (N * v_1) across the two would divide two
+# different workloads.  The same-workload 1 -> N curve is carried inside the lines themselves: `scale26` on the N=1
+# line, `single_gpu_same_graph` / `speedup_vs_1gpu_same_graph` / `scaling_efficiency_same_workload` on every N>1 line.
+METRIC = "bfs_gteps_rmat22_push"
+METRIC_MG = "bfs_gteps_rmat26_do"
 UNIT = "GTEPS"
 
 
@@ -91,13 +96,14 @@ WORK_CREATE = True    # --advance quad (default): the advance launch also produc
 
 
 def push_level_bytes(level, offset_bytes=4):
-    """Algorithmic bytes of one push level: |F|(4+2*O) + m_F*(4+4) + |F_next|*(4+4); the work-creating
-    advance additionally reads two offsets and writes row bounds + scan position per emitted vertex (the scan
-    kernel's bytes, moved into this launch)."""
-    b = level["frontier_len"] * (4 + 2 * offset_bytes) + level["arcs"] * 8 + level["discovered"] * 8
-    if WORK_CREATE:
-        b += level["discovered"] * (2 * offset_bytes + 8 + 4)
-    return b
+    """Algorithmic bytes of one push level, SURVEY.md 8d verbatim: |F|(4+2*O) + m_F*(4+4) + |F_next|*(4+4)."""
+    return level["frontier_len"] * (4 + 2 * offset_bytes) + level["arcs"] * 8 + level["discovered"] * 8
+
+
+def work_creation_bytes(level, offset_bytes=4):
+    """What the work-creating advance moves ON TOP of the 8d model (reported separately, never inside `frac`): two
+    offsets read, row bounds + scan position written per emitted vertex -- the scan kernel's bytes, moved into this launch."""
+    return level["discovered"] * (2 * offset_bytes + 8 + 4) if WORK_CREATE else 0
 
 
 def sssp_level_bytes(level, offset_bytes=4):
@@ -151,11 +157,32 @@ def run_sssp_leg(ctx, mb, args, peak):
     reached_arcs = int((off[1:] - off[:-1])[dist < 3.0e38].sum().item())
     roof = _per_level(lambda: ctx.sssp(g, 0, dist=dist, timing=True)[1], 5, sssp_level_bytes, peak)
     roof["kernel"] = "quad_advance_kernel<SsspRelaxQ,COMPACT> (heaviest iteration)"
-    return {"workload": f"SSSP from vertex 0, RMAT scale-{scale} ef16 symmetrised, uniform integer weights [1,64] "
-                        "as fp32, idempotent LB advance (Bellman-Ford frontier iterations)",
-            "value": reached_arcs / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "steps": steps,
-            "iterations": st.num_levels, "relaxed_arcs": st.total_arcs, "reached_arcs": reached_arcs,
-            "gpu_launches": launches, "roofline": roof}
+    out = {"workload": f"SSSP from vertex 0, RMAT scale-{scale} ef16 symmetrised, uniform integer weights [1,64] "
+                       "as fp32, LB advance with the per-iteration de-duplicating stamp (Bellman-Ford frontier iterations)",
+           "value": reached_arcs / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "steps": steps,
+           "iterations": st.num_levels, "relaxed_arcs": st.total_arcs, "reached_arcs": reached_arcs,
+           "gpu_launches": launches, "roofline": roof}
+    if args.parity:
+        # full-size parity: distances memcmp-equal to the CPU oracle (Dijkstra under sssp_functor.hxx:20-29) on the
+        # device-built CSR; and, when it was built, to the reference's own GPU enactor
+        import numpy as np
+        import oracle
+        ctx.sssp(g, 0, dist=dist)
+        t0 = time.time()
+        o = oracle.CSR(g.n, g.offsets_host(), g.col_indices.cpu().numpy(), g.col_values.cpu().numpy())
+        ref = oracle.sssp_dist(o, 0)
+        d = dist.cpu().numpy()
+        out["parity"] = {"sssp_dist_bit_exact_vs_cpu": bool(d.tobytes() == ref.tobytes()), "oracle_s": round(time.time() - t0, 1)}
+        if args.ref_gpu and oracle.have_ref_gpu():
+            try:
+                rg, secs = oracle.ref_gpu("sssp", o, src=0, runs=2, queue_sizing=2.0, timeout=300)
+                out["reference_gpu"] = {"impl": "sssp_enactor_t::enact, unmodified reference compiled for sm_100, wall clock as test_sssp.cu:39-42",
+                                        "ms_per_step": 1e3 * min(secs), "value": reached_arcs / min(secs) / 1e9, "unit": UNIT,
+                                        "dist_equal_to_ours": bool(rg["labels"].tobytes() == d.tobytes())}
+            except Exception as e:   # noqa: BLE001 (the reference exit()s on frontier overflow)
+                out["reference_gpu"] = {"unavailable": repr(e)[:300]}
+        del o
+    return out
 
 
 def run_reduce_leg(ctx, mb, args, peak):
@@ -186,11 +213,40 @@ def run_reduce_leg(ctx, mb, args, peak):
             roof["traffic"] = json.load(open(tp)).get("scale24_reduce_top_launch_dram_bytes")
         except Exception:
             pass
-    return {"workload": f"PageRank-style neighborhood_reduce fp32 pull-sum, RMAT scale-{scale} ef16 symmetrised "
-                        f"(n={g.n}, m={g.m}), 10 iterations over the filter's dynamic frontiers",
-            "value": st.total_arcs / (ms * 1e-3) / 1e9, "unit": "G arcs reduced/s", "ms_per_step": ms, "steps": steps,
-            "iterations": st.num_levels, "frontier_lens": lens, "reduced_arcs": st.total_arcs,
-            "gpu_launches": launches, "roofline": roof}
+    out = {"workload": f"PageRank-style neighborhood_reduce fp32 pull-sum, RMAT scale-{scale} ef16 symmetrised "
+                       f"(n={g.n}, m={g.m}), 10 iterations over the filter's dynamic frontiers",
+           "value": st.total_arcs / (ms * 1e-3) / 1e9, "unit": "G arcs reduced/s", "ms_per_step": ms, "steps": steps,
+           "iterations": st.num_levels, "frontier_lens": lens, "reduced_arcs": st.total_arcs,
+           "gpu_launches": launches, "roofline": roof}
+    if args.parity:
+        # full-size parity of the reduce itself: frontier = all vertices, NON-uniform values, every slot against the
+        # fp64 CPU oracle (neighborhood.hxx:47-58) within 1e-5 * sum|terms| + 1e-6
+        import numpy as np
+        import oracle
+        t0 = time.time()
+        v = torch.arange(g.n, dtype=torch.int64, device=ctx.torch_device)
+        vals = (0.15 + ((v * 2654435761) % 1000).to(torch.float64) / 1000.0).to(torch.float32)
+        frontier = torch.arange(g.n, dtype=torch.int32, device=ctx.torch_device)
+        red = torch.empty(g.n, dtype=torch.float32, device=ctx.torch_device)
+        ctx.neighborhood_reduce(g, frontier, vals, red, 0.0)
+        o = oracle.CSR(g.n, g.offsets_host(), g.col_indices.cpu().numpy())
+        ref, asum = oracle.neighborhood_reduce(o, np.arange(g.n, dtype=np.int32), vals.cpu().numpy().astype(np.float64))
+        err = np.abs(red.cpu().numpy().astype(np.float64) - ref)
+        tol = 1e-5 * asum + 1e-6
+        out["parity"] = {"reduce_sums_within_tolerance_vs_cpu_f64": bool((err <= tol).all()),
+                         "tolerance": "1e-5 * sum|terms| + 1e-6 per slot", "max_err_over_tol": float((err / tol).max()),
+                         "slots_checked": int(g.n), "oracle_s": round(time.time() - t0, 1)}
+        if args.ref_gpu and args.ref_gpu_pr and oracle.have_ref_gpu():
+            try:
+                rg, secs = oracle.ref_gpu("pr", o, max_iter=10, runs=2, timeout=600)
+                cur = ctx.pr(g, 10, False)[0].cpu().numpy()
+                out["reference_gpu"] = {"impl": "pr_enactor_t::enact, unmodified reference compiled for sm_100, wall clock as test_pr.cu:36-40",
+                                        "ms_per_step": 1e3 * min(secs), "speedup_ours": 1e3 * min(secs) / ms,
+                                        "ranks_within_rel_1e-4_of_ours": bool(np.allclose(rg["current"], cur, rtol=1e-4, atol=1e-6))}
+            except Exception as e:   # noqa: BLE001
+                out["reference_gpu"] = {"unavailable": repr(e)[:300]}
+        del o
+    return out
 
 
 def cpu_bfs_baseline(off64, idx, runs):
@@ -231,7 +287,7 @@ def run_reference_arm(args):
     total = sum(times)
     val = reached * len(times) / total / 1e9
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC if args.gpus <= 1 else METRIC_MG, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": f"BFS from vertex 0, RMAT scale-{scale} ef16 symmetrised (n={g.n}, m={g.m}), "
@@ -272,16 +328,36 @@ def run_single_gpu(args):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
+    step_ms = []
     e0.record()
     for _ in range(args.steps):
         _, st = ctx.bfs(g, 0, mode, 15.0, 18.0, labels=labels)
         launches += st.launches
+        step_ms.append(st.device_ms)      # the library's own CUDA-event pair around each traversal
     e1.record()
     torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
     loop_used = st.level_loop
     reached_arcs = g.degrees_sum_reached(labels)
     value = reached_arcs * args.steps / (ms_total * 1e-3) / 1e9
+    step_ms.sort()
+    median_ms = step_ms[len(step_ms) // 2]
+
+    # ---- seeds 2 and 3 beside seed 1 (own graphs, median of >= 10 runs after 2 warm-ups)
+    seeds = {"1": {"gteps_median": reached_arcs / (median_ms * 1e-3) / 1e9, "ms_median": median_ms, "reached_arcs": reached_arcs}}
+    for sd in (2, 3) if args.seeds else ():
+        gs = ctx.prepare_graph(ctx.rmat_graph(scale, 16, sd))
+        ls = torch.empty(gs.n, dtype=torch.int32, device=ctx.torch_device)
+        t = []
+        for i in range(12):
+            _, s2 = ctx.bfs(gs, 0, mode, 15.0, 18.0, labels=ls)
+            if i >= 2:
+                t.append(s2.device_ms)
+        t.sort()
+        ra = gs.degrees_sum_reached(ls)
+        seeds[str(sd)] = {"gteps_median": ra / (t[len(t) // 2] * 1e-3) / 1e9, "ms_median": t[len(t) // 2], "reached_arcs": ra}
+        del gs, ls
+    torch.cuda.empty_cache()
 
     # ---- roofline of the dominant kernel (lbs_advance_kernel<BfsPushOp>): per-launch CUDA-event times
     peak, peak_src = _peaks()
@@ -310,6 +386,8 @@ def run_single_gpu(args):
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": push_level_bytes(lv[top]), "launch_ms": lv_ms[top],
         "arcs_per_launch": lv[top]["arcs"],
+        "bytes_model": "SURVEY.md 8d verbatim: |F|*12 + m_F*8 + |F_next|*8 (uint32 offsets)",
+        "work_creation_bytes_per_launch_not_in_frac": work_creation_bytes(lv[top]),
         "all_levels": {"achieved": tot_bytes / (tot_ms * 1e-3) / 1e9, "frac": tot_bytes / (tot_ms * 1e-3) / 1e9 / peak,
                        "advance_ms_sum": tot_ms,
                        "levels": [dict(frontier=l["frontier_len"], arcs=l["arcs"], discovered=l["discovered"],
@@ -351,11 +429,53 @@ def run_single_gpu(args):
     else:
         parity, cpu = None, None
 
+    # ---- third column: the reference's GPU path, unmodified, compiled for sm_100 -- enact_pushpull on the
+    # same CSR, wall clock around enact() exactly as tests/bfs/test_bfs.cu:38-42 times it (child process)
+    ref_gpu = None
+    if args.ref_gpu:
+        import oracle
+        if oracle.have_ref_gpu():
+            try:
+                o = oracle.CSR(g.n, off_h.astype(np.int64), idx_h)
+                rg, secs = oracle.ref_gpu("bfs", o, src=0, runs=3, timeout=300)
+                ref_gpu = {"impl": "bfs_enactor_t::enact_pushpull (alpha = 1/n as test_bfs.cu:30), unmodified reference compiled for sm_100",
+                           "ms_per_step": 1e3 * min(secs), "value": reached_arcs / min(secs) / 1e9, "unit": UNIT,
+                           "runs_s": [round(x, 5) for x in secs], "labels_equal_to_ours": bool(np.array_equal(rg["labels"], h_out.numpy())),
+                           "speedup_ours_device": (1e3 * min(secs)) / (ms_total / args.steps),
+                           "speedup_ours_e2e": (1e3 * min(secs)) / (1e3 * e2e_s / args.steps)}
+                del o
+            except Exception as e:   # noqa: BLE001
+                ref_gpu = {"unavailable": repr(e)[:300]}
+        else:
+            ref_gpu = {"unavailable": "oracle/_ref/ref_gpu_bfs not built (needs /root/reference at build time)"}
+
     # ---- the other single-GPU configurations of BASELINE.json (own graphs; the BFS graph is released first)
     gn, gm = g.n, g.m
     del g, labels
     torch.cuda.empty_cache()
     extras = {}
+    if "scale26" in args.extras:
+        # v_1 of the 1 -> N curve of BASELINE.json configs[3]: the N>1 workload (scale-26, both modes) on ONE GPU
+        try:
+            g26 = ctx.prepare_graph(ctx.rmat_graph(26, 16, 1))
+            l26 = torch.empty(g26.n, dtype=torch.int32, device=ctx.torch_device)
+            leg = {"workload": f"BFS from vertex 0, RMAT scale-26 ef16 symmetrised (n={g26.n}, m={g26.m}) on 1 GPU: the v_1 of "
+                               "the N>1 lines' metric " + METRIC_MG}
+            for md, flag in (("do", mb.BFS_BEAMER), ("push", mb.BFS_PUSH)):
+                t = []
+                for i in range(3 + 10):
+                    _, s26 = ctx.bfs(g26, 0, flag, 15.0, 18.0, labels=l26)
+                    if i >= 3:
+                        t.append(s26.device_ms)
+                t.sort()
+                ra = g26.degrees_sum_reached(l26)
+                leg[md] = {"ms_median": t[len(t) // 2], "ms_mean": sum(t) / len(t), "value": ra / (sum(t) / len(t) * 1e-3) / 1e9,
+                           "unit": UNIT, "levels": s26.num_levels, "reached_arcs": ra}
+            extras["scale26"] = leg
+            del g26, l26
+        except Exception as e:   # noqa: BLE001
+            extras["scale26"] = {"unavailable": repr(e)[:200]}
+        torch.cuda.empty_cache()
     if "sssp" in args.extras:
         extras["sssp"] = run_sssp_leg(ctx, mb, args, peak)
         torch.cuda.empty_cache()
@@ -370,21 +490,29 @@ def run_single_gpu(args):
         "config": {"workload": f"BFS from vertex 0, RMAT scale-{scale} ef16 symmetrised (n={gn}, m={gm}), "
                                f"{args.mode} (LB advance + fused uniquify filter)",
                    "advance": args.advance + (" (work-creating: the flush writes the next level's row bounds and scan "
-                                               "positions; their 20 B per emitted vertex are counted in the roofline's "
-                                               "algorithmic bytes)" if args.advance == "quad" else ""),
+                                               "positions; those 20 B per emitted vertex are NOT in roofline.frac, see "
+                                               "roofline.work_creation_bytes_per_launch_not_in_frac)" if args.advance == "quad" else ""),
                    "teps_numerator": "sum of deg(v) over reached v", "reached_arcs": reached_arcs,
                    "l2": "inputs larger than L2 (col_indices alone is %d MiB vs 126 MB L2)" % (gm * 4 >> 20),
-                   "level_loop": loop_used + (" (one CUDA graph per BFS: WHILE/IF/SWITCH conditional nodes set by a "
-                                                  "device-side decide kernel; one host sync per BFS)"
+                   "level_loop": loop_used + (" (one CUDA graph per BFS: a WHILE conditional node over a flat self-guarded body, "
+                                                  "steered by a device-side decide kernel; one host sync per BFS)"
                                                   if loop_used == "graph" else " (one counter read-back per level)"),
                    "parallelism": "1 GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "reference_gpu": ref_gpu,
+        "value_median_of_steps": reached_arcs / (median_ms * 1e-3) / 1e9,
+        "gteps_graph500_convention": {"value": value / 2.0, "note": "Graph500 counts undirected input edges: m_reached / 2 over the same time"},
+        "seeds": seeds,
         "parity": {"bfs_labels_bit_exact_vs_cpu": parity},
     }
     line.update(extras)
+    for k in ("sssp", "neighborhood_reduce"):
+        if k in extras and "parity" in extras[k]:
+            line["parity"].update(extras[k]["parity"])
     print(json.dumps(line))
     ctx.close()
-    return 0 if parity in (True, None) else 1
+    bad = [k for k, v in line["parity"].items() if v is False]
+    return 1 if bad else 0
 
 
 def main():
@@ -401,15 +529,22 @@ def main():
                          "the same with a scan kernel before every level, or the first-generation advance.cuh")
     ap.add_argument("--loop", default="graph", choices=["graph", "host"],
                     help="N=1 BFS level loop: one CUDA graph with device-side decisions, or host-driven")
-    ap.add_argument("--extras", default="sssp,reduce",
-                    help="N=1: extra legs after the BFS line: sssp (configs[2]) and/or reduce (configs[4]); '' = none")
+    ap.add_argument("--extras", default="sssp,reduce,scale26",
+                    help="N=1: extra legs after the BFS line: sssp (configs[2]), reduce (configs[4]), scale26 (the N>1 "
+                         "workload on one GPU); '' = none")
+    ap.add_argument("--no-parity", dest="parity", action="store_false", help="skip the full-size CPU-oracle checks of the extra legs")
+    ap.add_argument("--no-ref-gpu", dest="ref_gpu", action="store_false", help="skip the reference-GPU baseline column")
+    ap.add_argument("--no-ref-gpu-pr", dest="ref_gpu_pr", action="store_false", help="skip the reference GPU PR run (scale-24: ~1 min)")
+    ap.add_argument("--no-seeds", dest="seeds", action="store_false", help="skip the seed-2 / seed-3 graphs")
     ap.add_argument("--reduce-scale", dest="reduce_scale", type=int, default=24)
     ap.add_argument("--mg-mode", dest="mg_mode", default="beamer", choices=["push", "beamer"])
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1 frontier exchange: fused into the kernels over NVLink peer memory, or NCCL collectives")
     ap.add_argument("--no-mg-other", dest="mg_other", action="store_false", help="N>1: skip the other traversal mode")
     ap.add_argument("--no-mg-single", dest="mg_single", action="store_false",
-                    help="N>1: skip the same-graph single-GPU run on rank 0")
+                    help="N>1: skip the same-graph single-GPU run on rank 0 (and the label comparison against it)")
+    ap.add_argument("--no-mg-oracle", dest="mg_oracle", action="store_false",
+                    help="N>1: skip the 64-bit CPU-oracle BFS of the scale-26 graph on rank 0 (~20 s)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

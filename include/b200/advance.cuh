@@ -536,9 +536,25 @@ __global__ void __launch_bounds__(NT, B200_PULL_MINB) bfs_pull_dyn_kernel(uint32
                       counters, part, first_nbr);
 }
 
-// frontier list -> bitmap (dynamic list and length; bitmap pre-cleared)
-static __global__ void sparse_to_bitmap_dyn_kernel(const LoopDyn *dyn, uint32_t *bitmap) {
+// push -> pull switch of the graph-driven loop: frontier list -> bitmap (dynamic list and length; bitmap pre-cleared),
+// and visited |= "vertex has no in-arc" (iso: prebuilt bitmap, else derived from the pull offsets; engine.cuh)
+static __global__ void sparse_to_bitmap_dyn_kernel(const LoopDyn *dyn, uint32_t *bitmap, const uint32_t *__restrict__ pull_offsets,
+                                                   uint32_t n, const uint32_t *__restrict__ iso, uint32_t *visited) {
     if (!(dyn->run & LOOP_RUN_TO_PULL)) return;
+    {
+        const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5, num_words = (n + 31u) >> 5;
+        const unsigned lane = threadIdx.x & 31u;
+        for (uint32_t word = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; word < num_words; word += warps_total) {
+            unsigned mask;
+            if (iso) {
+                mask = iso[word];
+            } else {
+                const uint32_t v = (word << 5) + lane;
+                mask = __ballot_sync(0xffffffffu, v < n && pull_offsets[v + 1] == pull_offsets[v]);
+            }
+            if (lane == 0 && mask) visited[word] |= mask;
+        }
+    }
     const int *__restrict__ sparse = dyn->in;
     const uint32_t len = dyn->len;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {

@@ -619,8 +619,10 @@ struct SsspRelaxQDyn : SsspRelaxQ {
     }
 };
 
-// Deterministic predecessors once the distances are final: the smallest u with
-// dist[u] + w(u,v) == dist[v] (the reference's GPU preds are a race).
+// Deterministic predecessors once the distances are final: the smallest u != v with
+// dist[u] + w(u,v) == dist[v] (the reference's GPU preds are a race).  A zero-weight
+// arc between two vertices of equal distance counts only from the smaller id to the larger one, so
+// parent chains never close a cycle (a zero-weight self loop or u <-> v pair cannot make preds[v] = v).
 struct SsspPredQ {
     const float *dist;
     int *preds;
@@ -638,8 +640,11 @@ struct SsspPredQ {
     __device__ __forceinline__ bool probe_eval(Evidence dd, SrcVal ds, int, float w) const {
         return ds != 3.402823466e+38f && ds + w == dd;
     }
-    __device__ __forceinline__ Cand make_cand(SrcVal, int src, int dst, uint32_t, float) const {
-        return Cand{{(uint32_t)dst, (uint32_t)src}};
+    __device__ __forceinline__ Cand make_cand(SrcVal ds, int src, int dst, uint32_t, float w) const {
+        // (the tie rule needs src, which probe_eval does not see: an excluded pair becomes a no-op candidate)
+        const bool ok = src != dst && (w > 0.f || src < dst);
+        (void)ds;
+        return Cand{{(uint32_t)dst, ok ? (uint32_t)src : 0x7fffffffu}};
     }
     __device__ __forceinline__ Token claim(const Cand &c) const {
         atomicMin(preds + c.w[0], (int)c.w[1]);

@@ -54,7 +54,11 @@ typedef struct b200_ctx b200_ctx; /* replaces mgpu::standard_context_t (context.
 
 /* Device CSR / CSC view.  Mirrors gunrock::graph_device_t (graph.hxx:37-58);
  * col_offsets/row_indices/row_values may alias the CSR arrays exactly as
- * graph_to_device does for symmetric graphs (graph.hxx:75-80). */
+ * graph_to_device does for symmetric graphs (graph.hxx:75-80).
+ * Index / value arrays that are 16-byte aligned are read as aligned 128-bit quads: their allocation must be
+ * readable up to the next multiple of 4 elements (4 * ceil(m / 4)); the pad is never interpreted.  Every allocator
+ * in this library (b200_host_graph_upload, the Python Graph builders) pads; arrays that are not 16-byte aligned take
+ * the element-wise kernels.  Weights must be finite and >= 0 (distances are ordered through their bit patterns). */
 typedef struct b200_graph {
     int64_t n;                   /* num_nodes */
     int64_t m;                   /* num_edges (arcs), < 2^32 */
@@ -67,8 +71,8 @@ typedef struct b200_graph {
     const uint32_t *no_in_arc_bitmap; /* optional derived data, like graph_device_t::d_scanned_row_offsets
                                     (graph.hxx:52): [(n+31)/32] words, bit v set iff vertex v has no in-arc, built
                                     once per graph by b200_graph_no_in_arc_bitmap; the direction-optimising BFS
-                                    starts its visited set from it so pull levels skip vertices nobody can reach.
-                                    NULL => computed at the start of every such traversal (one pass over the offsets) */
+                                    ORs it into its visited set at the push -> pull switch so pull levels skip vertices
+                                    nobody can reach.  NULL => computed at that switch (one pass over the offsets) */
     const int32_t *first_in_neighbor; /* optional derived data: [n], the first in-neighbour of every vertex (row_indices[
                                     col_offsets[v]]) or -1, built once per graph by b200_graph_first_in_neighbor.  A pull
                                     level resolves most vertices at their first in-arc (scale-26 level 1: 28 M of 32 M);

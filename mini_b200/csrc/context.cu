@@ -36,6 +36,23 @@ static __global__ void isolated_bitmap_kernel(const uint32_t *__restrict__ offse
     }
 }
 
+// visited |= "vertex has no in-arc" (iso: the caller's prebuilt bitmap, else derived from the offsets)
+static __global__ void or_no_in_arc_kernel(const uint32_t *__restrict__ offsets, uint32_t n, uint32_t num_words,
+                                           const uint32_t *__restrict__ iso, uint32_t *visited) {
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    for (uint32_t word = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; word < num_words; word += warps_total) {
+        unsigned mask;
+        if (iso) {
+            mask = iso[word];
+        } else {
+            const uint32_t v = (word << 5) + lane;
+            mask = __ballot_sync(0xffffffffu, v < n && offsets[v + 1] == offsets[v]);
+        }
+        if (lane == 0 && mask) visited[word] |= mask;
+    }
+}
+
 static __global__ void first_in_neighbor_kernel(const uint32_t *__restrict__ offsets, const int32_t *__restrict__ indices,
                                                 unsigned long long n, int32_t *__restrict__ out) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -61,6 +78,13 @@ cudaError_t preload_no_in_arc_kernel() {
 cudaError_t launch_no_in_arc_bitmap(b200_workspace *ws, const uint32_t *pull_offsets, int64_t n, uint32_t *d_bitmap) {
     const int64_t words = (n + 31) / 32;
     isolated_bitmap_kernel<<<ws->num_sms * 8, 256, 0, (cudaStream_t)ws->stream>>>(pull_offsets, (uint32_t)n, (uint32_t)words, d_bitmap);
+    ws->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_or_no_in_arc(b200_workspace *ws, const uint32_t *pull_offsets, int64_t n, const uint32_t *iso, uint32_t *d_visited) {
+    const int64_t words = (n + 31) / 32;
+    or_no_in_arc_kernel<<<ws->num_sms * 8, 256, 0, (cudaStream_t)ws->stream>>>(pull_offsets, (uint32_t)n, (uint32_t)words, iso, d_visited);
     ws->launches++;
     return cudaGetLastError();
 }

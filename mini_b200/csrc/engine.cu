@@ -119,16 +119,17 @@ struct BitmapPred {
     }
 };
 
-// Deterministic predecessors once the distances are final: the smallest u with
-// dist[u] + w(u,v) == dist[v].  (The reference writes preds[dst] = src from every
-// relaxation attempt, sssp_functor.hxx:31-34, so its GPU preds are a race)
+// Deterministic predecessors once the distances are final: the smallest u != v with
+// dist[u] + w(u,v) == dist[v]; zero-weight arcs count only from the smaller id to the larger (no cycles,
+// see SsspPredQ).  (The reference writes preds[dst] = src from every relaxation attempt,
+// sssp_functor.hxx:31-34, so its GPU preds are a race)
 struct SsspPredOp {
     const float *dist;
     const float *weights;
     int *preds;
     __device__ __forceinline__ bool probe(int src, int dst, uint32_t eid) const {
-        const float ds = dist[src];
-        return ds != FLT_MAX && ds + ld_stream(weights + eid) == dist[dst];
+        const float ds = dist[src], w = ld_stream(weights + eid);
+        return ds != FLT_MAX && ds + w == dist[dst] && src != dst && (w > 0.f || src < dst);
     }
     __device__ __forceinline__ bool commit(int src, int dst, uint32_t, uint32_t, uint32_t) const {
         atomicMin(preds + dst, src);
@@ -427,13 +428,7 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
     B200_CUDA(cudaEventRecord(ctx->ev_run[0], st));
     // bfs_problem_t ctor (bfs_problem.hxx:38-42) + init_frontier (bfs_enactor.hxx:34-38)
     B200_CUDA(cudaMemsetAsync(d_labels, 0xFF, sizeof(int32_t) * (size_t)n, st));
-    if (mode == B200_BFS_PUSH) {
-        B200_CUDA(cudaMemsetAsync(ctx->bm_visited, 0, sizeof(uint32_t) * words, st));
-    } else if (g->no_in_arc_bitmap) {   // vertices without in-arcs start "visited": pull levels skip them (engine.cuh)
-        B200_CUDA(cudaMemcpyAsync(ctx->bm_visited, g->no_in_arc_bitmap, sizeof(uint32_t) * words, cudaMemcpyDeviceToDevice, st));
-    } else {
-        B200_CUDA(launch_no_in_arc_bitmap(ws, pull_off, n, ctx->bm_visited));
-    }
+    B200_CUDA(cudaMemsetAsync(ctx->bm_visited, 0, sizeof(uint32_t) * words, st));
     bfs_init_kernel<<<1, 1, 0, st>>>(d_labels, ctx->bm_visited, ctx->frontier[0], src);
     ws->launches++;
     B200_CUDA(cudaGetLastError());
@@ -539,6 +534,8 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
         }
         flen = found;
         if (pull && !was_pull) {
+            // vertices without in-arcs count as visited from here on: pull levels skip them (engine.cuh)
+            B200_CUDA(launch_or_no_in_arc(ws, pull_off, n, g->no_in_arc_bitmap, ctx->bm_visited));
             // frontier list -> bitmap (sparse_to_dense_kernel, advance.hxx:69-84)
             B200_CUDA(cudaMemsetAsync(ctx->bm_frontier[bsel], 0, sizeof(uint32_t) * words, st));
             sparse_to_bitmap_kernel<<<(unsigned)((flen + 255) / 256), 256, 0, st>>>(ctx->frontier[sel], (uint32_t)flen,
@@ -781,8 +778,8 @@ int b200_host_graph_upload(b200_ctx *ctx, int64_t n, int64_t m, const uint32_t *
     int s = B200_OK;
     do {
         if ((s = cuda_status(cudaMalloc(&hg->d_row_offsets, sizeof(uint32_t) * (size_t)(n + 1))))) break;
-        if ((s = cuda_status(cudaMalloc(&hg->d_col_indices, sizeof(int32_t) * (size_t)(m ? m : 1))))) break;
-        if (h_col_values && (s = cuda_status(cudaMalloc(&hg->d_col_values, sizeof(float) * (size_t)(m ? m : 1))))) break;
+        if ((s = cuda_status(cudaMalloc(&hg->d_col_indices, sizeof(int32_t) * (size_t)((m + 3) / 4 * 4 + 4))))) break;
+        if (h_col_values && (s = cuda_status(cudaMalloc(&hg->d_col_values, sizeof(float) * (size_t)((m + 3) / 4 * 4 + 4))))) break;
         if ((s = cuda_status(cudaMalloc(&hg->d_labels, sizeof(int32_t) * (size_t)n)))) break;
         if ((s = cuda_status(cudaMalloc(&hg->d_dist, sizeof(float) * (size_t)n)))) break;
         if ((s = cuda_status(cudaMalloc(&hg->d_preds, sizeof(int32_t) * (size_t)n)))) break;

@@ -72,11 +72,15 @@ int ensure_traversal_scratch(b200_ctx *ctx, int64_t n);
 // slower than the streaming scan kernel (8.33 -> 9.13 ms), so large graphs keep the scan.
 constexpr int64_t WORK_CREATE_MAX_N = 1ll << 23;
 // Pull levels walk every unvisited vertex; on RMAT half of them have no arc at all (scale 26: 34 M of 67 M) and
-// were re-inspected at every pull level.  The visited bitmap of a direction-optimising traversal therefore STARTS
-// as "vertex has no in-arc" instead of all-zero: such a vertex cannot be anybody's child, so no result changes
-// (labels stay -1), and whole words of them are skipped with one 4-byte read.  Source: b200_graph::no_in_arc_bitmap
-// if the caller built it once (b200_graph_no_in_arc_bitmap), else one pass over the offsets per traversal.
+// were re-inspected at every pull level.  At the push -> pull switch the visited bitmap of a direction-optimising
+// traversal is therefore OR-ed with "vertex has no in-arc" (by the pull arrays): the pull kernel can never label
+// such a vertex, so no result changes (labels stay -1), and whole words of them are skipped with one 4-byte read.
+// Source: b200_graph::no_in_arc_bitmap if the caller built it once (b200_graph_no_in_arc_bitmap), else one pass over
+// the pull offsets.  It is NOT applied before the switch: when the CSC arrays alias the CSR of a directed graph
+// (graph.hxx:75-80 does that for every input) "no in-arc" really means "no out-arc", and the push levels must still
+// label those sinks exactly as the reference does (bfs_enactor.hxx:54-66).
 cudaError_t launch_no_in_arc_bitmap(b200_workspace *ws, const uint32_t *pull_offsets, int64_t n, uint32_t *d_bitmap);
+cudaError_t launch_or_no_in_arc(b200_workspace *ws, const uint32_t *pull_offsets, int64_t n, const uint32_t *iso, uint32_t *d_visited);
 // b200_graph::first_in_neighbor: out[v] = first in-neighbour of v, or -1 (see the pull kernel, advance.cuh)
 cudaError_t launch_first_in_neighbor(b200_workspace *ws, const uint32_t *pull_offsets, const int32_t *pull_indices, int64_t n,
                                      int32_t *d_out);

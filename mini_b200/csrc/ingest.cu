@@ -85,25 +85,44 @@ int b200_host_csr_free(b200_host_csr *csr) {
     return B200_OK;
 }
 
+static int mtx_load_impl(const char *path, int undirected, b200_host_csr *out);
+
 int b200_mtx_load(const char *path, int undirected, b200_host_csr *out) {
     if (!path || !out) return B200_ERR_INVALID;
     std::memset(out, 0, sizeof *out);
-    FILE *f = std::fopen(path, "r");
+    try {   // nothing may unwind through the extern "C" boundary
+        return mtx_load_impl(path, undirected, out);
+    } catch (const std::bad_alloc &) {
+        b200_host_csr_free(out);
+        return B200_ERR_NOMEM;
+    } catch (...) {
+        b200_host_csr_free(out);
+        return B200_ERR_FORMAT;
+    }
+}
+
+static int mtx_load_impl(const char *path, int undirected, b200_host_csr *out) {
+    struct File {   // closed on every exit path, exceptions included
+        FILE *f;
+        ~File() { close(); }
+        void close() { if (f) std::fclose(f); f = nullptr; }
+    } fc{std::fopen(path, "r")};
+    FILE *f = fc.f;
     if (!f) return B200_ERR_IO;
     std::string line;
     bool have = false;
     while ((have = read_line(f, line)) && !line.empty() && line[0] == '%') {}
     long long rows = 0, cols = 0, entries = 0;
     if (!have || std::sscanf(line.c_str(), "%lld %lld %lld", &rows, &cols, &entries) != 3 || rows < 1 || entries < 0 ||
-        rows > (1ll << 31) || entries * (undirected ? 2 : 1) >= (1ll << 32)) {
-        std::fclose(f);
+        rows > (1ll << 31) || entries >= (1ll << 32) / (undirected ? 2 : 1)) {   // (compared before any multiply)
+        fc.close();
         return B200_ERR_FORMAT;
     }
     std::vector<Arc> arcs;
     try {
         arcs.resize((size_t)entries * (undirected ? 2 : 1));
     } catch (const std::bad_alloc &) {
-        std::fclose(f);
+        fc.close();
         return B200_ERR_NOMEM;
     }
     for (long long e = 0; e < entries; ++e) {
@@ -112,20 +131,20 @@ int b200_mtx_load(const char *path, int undirected, b200_host_csr *out) {
         int got = 0;
         do {   // (blank lines between entries are tolerated)
             if (!read_line(f, line)) {
-                std::fclose(f);
+                fc.close();
                 return B200_ERR_FORMAT;
             }
         } while (line.empty());
         got = std::sscanf(line.c_str(), "%lld %lld %f", &i, &j, &w);
         if (got < 2 || i < 1 || j < 1 || i > rows || j > rows) {
-            std::fclose(f);
+            fc.close();
             return B200_ERR_FORMAT;
         }
         if (got == 2) w = 1.0f;
         arcs[(size_t)e] = Arc{(int32_t)(j - 1), (int32_t)(i - 1), w};
         if (undirected) arcs[(size_t)(e + entries)] = Arc{(int32_t)(i - 1), (int32_t)(j - 1), w};
     }
-    std::fclose(f);
+    fc.close();
     std::stable_sort(arcs.begin(), arcs.end(),
                      [](const Arc &a, const Arc &b) { return a.row != b.row ? a.row < b.row : a.col < b.col; });
     const int64_t n = rows, m = (int64_t)arcs.size();

@@ -63,7 +63,7 @@ struct LevelLoop {
     struct Slot {
         cudaGraph_t graph;
         cudaGraphExec_t exec;
-        const void *k_offsets, *k_indices, *k_labels, *k_scratch, *k_iso, *k_first, *k_weights;
+        const void *k_offsets, *k_indices, *k_labels, *k_scratch, *k_iso, *k_first, *k_weights, *k_pull_offsets, *k_pull_indices;
         int64_t k_n;
         uint64_t k_gen;
         int k_mode;
@@ -292,13 +292,8 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
                                                 (long long)n, ws->d_counters, ws->d_tile_counter, sp);
     } else {
         LL_CUDA(cudaMemsetAsync(d_labels, 0xFF, sizeof(int32_t) * (size_t)n, cs));
-        if (mode == B200_BFS_PUSH) {
-            LL_CUDA(cudaMemsetAsync(ctx->bm_visited, 0, sizeof(uint32_t) * words, cs));
-        } else {   // vertices without in-arcs start "visited" (engine.cuh); frontier bitmap 0 starts clean
-            if (iso) LL_CUDA(cudaMemcpyAsync(ctx->bm_visited, iso, sizeof(uint32_t) * words, cudaMemcpyDeviceToDevice, cs));
-            else LL_CUDA(launch_no_in_arc_bitmap(ws, pull_off, n, ctx->bm_visited));
-            LL_CUDA(cudaMemsetAsync(ctx->bm_frontier[0], 0, sizeof(uint32_t) * words, cs));
-        }
+        LL_CUDA(cudaMemsetAsync(ctx->bm_visited, 0, sizeof(uint32_t) * words, cs));
+        if (mode != B200_BFS_PUSH) LL_CUDA(cudaMemsetAsync(ctx->bm_frontier[0], 0, sizeof(uint32_t) * words, cs));   // frontier bitmap 0 starts clean
         loop_init_kernel<false><<<1, 1, 0, cs>>>(L->d_params, L->d_state, d_labels, ctx->bm_visited, ctx->frontier[0],
                                                  ctx->frontier[1], (long long)n, ws->d_counters, ws->d_tile_counter, sp);
     }
@@ -349,7 +344,8 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
     LL_CUDA(cudaGetLastError());
     if (has_pull) {
         // transitions: list -> bitmap 0 (all-zero by invariant) | bitmap -> list (+ clears bitmap 0)
-        sparse_to_bitmap_dyn_kernel<<<ws->num_sms * 4, 256, 0, cs>>>(dyn, ctx->bm_frontier[0]);
+        // (+ vertices without in-arcs count as visited from the switch on, engine.cuh)
+        sparse_to_bitmap_dyn_kernel<<<ws->num_sms * 4, 256, 0, cs>>>(dyn, ctx->bm_frontier[0], pull_off, (uint32_t)n, iso, ctx->bm_visited);
         LL_CUDA(cudaGetLastError());
         const int64_t num_words = (n + 31) / 32;
         const int64_t max_tiles = (num_words + COMPACT_NT * BITLIST_VT - 1) / (COMPACT_NT * BITLIST_VT);
@@ -373,6 +369,8 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
     S->k_scratch = ctx->frontier[0];
     S->k_iso = iso;
     S->k_first = g->first_in_neighbor;
+    S->k_pull_offsets = pull_off;
+    S->k_pull_indices = pull_idx;
     S->k_n = n;
     S->k_gen = ctx->scratch_gen;
     S->k_mode = mode;
@@ -444,6 +442,8 @@ static int run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, 
     if (!S->exec || S->k_offsets != g->row_offsets || S->k_indices != g->col_indices || S->k_labels != d_labels ||
         S->k_scratch != ctx->frontier[0] || S->k_n != g->n || S->k_mode != mode || S->k_iso != iso ||
         S->k_first != g->first_in_neighbor || S->k_weights != g->col_values || S->k_wc != work_create ||
+        S->k_pull_offsets != (g->col_offsets ? g->col_offsets : g->row_offsets) ||
+        S->k_pull_indices != (g->row_indices ? g->row_indices : g->col_indices) ||
         S->k_gen != ctx->scratch_gen) {
         B200_CUDA(cudaStreamSynchronize(st));   // a replay of the old graph may still be running
         const int bs = build_graph(ctx, g, d_labels, mode, iso, work_create);

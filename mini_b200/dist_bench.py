@@ -22,6 +22,7 @@ def _level_rows(levels):
 
 def run(args) -> int:
     import torch
+    from bench import METRIC_MG
     import torch.distributed as dist
     import mini_b200 as mb
     from mini_b200 import dist as D
@@ -150,6 +151,8 @@ def run(args) -> int:
     # the same graph on ONE GPU (rank 0 builds the whole scale-26 CSR: 8 GiB + offsets), same modes: the
     # denominator of "scaling from 1 to N GPUs on scale-26" (north_star); the other ranks wait at the barrier
     single = None
+    lab1 = None
+    oracle_parity = None
     if args.mg_single and rank == 0:
         try:
             g1 = ctx.prepare_graph(ctx.rmat_graph(scale, ef, 1))
@@ -168,9 +171,43 @@ def run(args) -> int:
                 torch.cuda.synchronize()
                 ms1 = e0.elapsed_time(e1) / reps
                 single[md] = {"ms_per_step": ms1, "value": reached_arcs / (ms1 * 1e-3) / 1e9, "unit": "GTEPS"}
-            del g1, lab1
+            if getattr(args, "mg_oracle", True):
+                # full-size parity, part 1: the single-GPU labels against the 64-bit CPU oracle BFS (bfs_problem.hxx:52-72
+                # restated with int64 offsets -- the reference's int32 CSR cannot hold 2^31 arcs) on the device-built CSR
+                import numpy as np
+                import oracle
+                t0 = time.time()
+                o = oracle.CSR(g1.n, g1.offsets_host(), g1.col_indices.cpu().numpy())
+                ref = oracle.bfs(o, 0)
+                oracle_parity = {"single_gpu_labels_bit_exact_vs_cpu_oracle_int64": bool(np.array_equal(ref, lab1.cpu().numpy())),
+                                 "oracle_s": round(time.time() - t0, 1)}
+                del o, ref
+            del g1
         except Exception as e:   # noqa: BLE001  (e.g. not enough free HBM next to the partition)
             single = {"unavailable": repr(e)[:200]}
+            lab1 = None
+    dist.barrier()
+    # full-size parity, part 2: every rank's label slice against the single-GPU labels of the same graph, bit-exact
+    slices_equal = None
+    if args.mg_single:
+        have = torch.tensor([1 if (rank != 0 or lab1 is not None) else 0], device=ctx.torch_device)
+        dist.all_reduce(have, op=dist.ReduceOp.MIN)
+        if int(have.item()) == 1:
+            run_bfs(mode)
+            if lab1 is None:
+                lab1 = torch.empty(n, dtype=torch.int32, device=ctx.torch_device)
+            dist.broadcast(lab1, src=0)
+            from mini_b200 import partition as PT
+            log_p = PT.log2_ranks(world)
+            r = torch.arange(rk.n_local, dtype=torch.int64, device=ctx.torch_device)
+            sw = (((r * PT.GOLDEN) & 0xFFFFFFFF) >> (32 - log_p)) if log_p else torch.zeros_like(r)
+            gid = (r << log_p) | (rank ^ sw)
+            eq = torch.tensor([int(torch.equal(lab1[gid], rk.labels))], device=ctx.torch_device)
+            dist.all_reduce(eq, op=dist.ReduceOp.MIN)
+            slices_equal = bool(int(eq.item()) == 1)
+            del r, sw, gid
+    lab1 = None
+    torch.cuda.empty_cache()
     dist.barrier()
 
     if rank == 0:
@@ -179,7 +216,7 @@ def run(args) -> int:
                    "inbox; gather+OR of bitmap slices; flag barriers) -- no NCCL on the data path") if exchange == "p2p" else \
                   "NCCL alltoallv (push) / allgather of bitmap slices (pull)"
         line = {
-            "metric": "bfs_gteps_rmat", "value": value, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC_MG, "value": value, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": f"direction-optimising BFS from vertex 0, RMAT scale-{scale} ef16 symmetrised "
@@ -202,16 +239,21 @@ def run(args) -> int:
             "cpu_baseline": None,
             "other_mode": other_line,
             "single_gpu_same_graph": single,
-            "parity": {"bfs_properties_hold_at_full_scale": props_ok, "vertices_per_level": level_hist},
+            "parity": {"bfs_properties_hold_at_full_scale": props_ok, "vertices_per_level": level_hist,
+                       "every_rank_slice_bit_exact_vs_1gpu_labels": slices_equal},
         }
+        if oracle_parity:
+            line["parity"].update(oracle_parity)
         if single and mode in single:
             line["speedup_vs_1gpu_same_graph"] = single[mode]["ms_per_step"] / (ms_total / args.steps)
+            line["scaling_efficiency_same_workload"] = line["speedup_vs_1gpu_same_graph"] / world
             if other_line and other in single:
                 other_line["speedup_vs_1gpu_same_graph"] = single[other]["ms_per_step"] / other_line["ms_per_step"]
+                other_line["scaling_efficiency_same_workload"] = other_line["speedup_vs_1gpu_same_graph"] / world
         print(json.dumps(line))
     dist.barrier()
     if exchange == "p2p":
         rk.close()
     ctx.close()
     dist.destroy_process_group()
-    return 0 if props_ok else 1
+    return 0 if (props_ok and slices_equal is not False) else 1

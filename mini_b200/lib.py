@@ -199,6 +199,12 @@ class Graph:
         return int(deg[labels >= 0].sum().item())
 
 
+def _quad_padded(n_elems: int, dtype, device):
+    """Device array of n_elems whose allocation is readable up to the next multiple of 4 elements (b200_graph)."""
+    import torch
+    return torch.empty((max(n_elems, 1) + 3) // 4 * 4, dtype=dtype, device=device)[:n_elems]
+
+
 class Context:
     """b200_ctx bound to one CUDA device; uses torch's current stream on that device by default."""
 
@@ -261,8 +267,8 @@ class Context:
         import torch
         n, m = 1 << scale, (2 * edge_factor) << scale
         off = torch.empty(n + 1, dtype=torch.int32, device=self.torch_device)
-        idx = torch.empty(m, dtype=torch.int32, device=self.torch_device)
-        w = torch.empty(m, dtype=torch.float32, device=self.torch_device) if weighted else None
+        idx = _quad_padded(m, torch.int32, self.torch_device)
+        w = _quad_padded(m, torch.float32, self.torch_device) if weighted else None
         _check(self._L.b200_rmat_build_csr(self._h, scale, edge_factor, seed, off.data_ptr(), idx.data_ptr(),
                                            _ptr(w), weight_seed), "b200_rmat_build_csr")
         return Graph(n, m, off, idx, w)
@@ -281,8 +287,8 @@ class Context:
         k = src.numel()
         m = k * (2 if symmetrize else 1)
         off = torch.empty(n + 1, dtype=torch.int32, device=self.torch_device)
-        idx = torch.empty(max(m, 1), dtype=torch.int32, device=self.torch_device)
-        w = torch.empty(max(m, 1), dtype=torch.float32, device=self.torch_device) if weighted else None
+        idx = _quad_padded(max(m, 1), torch.int32, self.torch_device)
+        w = _quad_padded(max(m, 1), torch.float32, self.torch_device) if weighted else None
         _check(self._L.b200_build_csr_from_pairs(self._h, n, k, _ptr(src), _ptr(dst), int(symmetrize), off.data_ptr(),
                                                  idx.data_ptr(), _ptr(w), weight_seed), "b200_build_csr_from_pairs")
         return Graph(n, m, off, idx[:m], None if w is None else w[:m])
@@ -305,9 +311,14 @@ class Context:
         import numpy as np
         import torch
         off = torch.from_numpy(np.asarray(offsets).astype(np.uint32).view(np.int32).copy()).to(self.torch_device)
-        idx = torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int32)).to(self.torch_device)
-        w = None if weights is None else torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float32)).to(self.torch_device)
-        return Graph(len(offsets) - 1, int(offsets[-1]), off, idx, w)
+        m = int(offsets[-1])
+        idx = _quad_padded(m, torch.int32, self.torch_device)
+        idx.copy_(torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int32)[:m]))
+        w = None
+        if weights is not None:
+            w = _quad_padded(m, torch.float32, self.torch_device)
+            w.copy_(torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float32)[:m]))
+        return Graph(len(offsets) - 1, m, off, idx, w)
 
     def graph_from_mtx(self, path: str, undirected: bool = False) -> Graph:
         """MatrixMarket file -> device Graph, with the reference's load_graph semantics (b200_mtx_load)."""

@@ -28,9 +28,12 @@ def build(force: bool = False) -> None:
     """Compile liboracle.so (and _ref/libref_cpu.so when /root/reference exists)."""
     src = os.path.join(_HERE, "oracle.c")
     stale = (not os.path.exists(_LIB)) or os.path.getmtime(_LIB) < os.path.getmtime(src)
+    gpu_bin = os.path.join(_HERE, "_ref", "ref_gpu_pr")
     need_ref = os.path.isdir("/root/reference/gunrock/src") and (
         not os.path.exists(_REF)
-        or os.path.getmtime(_REF) < os.path.getmtime(os.path.join(_HERE, "ref_shim.cu")))
+        or os.path.getmtime(_REF) < os.path.getmtime(os.path.join(_HERE, "ref_shim.cu"))
+        or not os.path.exists(gpu_bin)
+        or os.path.getmtime(gpu_bin) < os.path.getmtime(os.path.join(_HERE, "ref_gpu_driver.cu")))
     if force or stale or need_ref:
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
 
@@ -58,7 +61,7 @@ def lib():
         L.orc_neighborhood_reduce_f64.argtypes = [C.c_int64, _i32p, _i64p, _i32p, _f64p, C.c_int,
                                                   C.c_double, _f64p, C.c_void_p]
         L.orc_neighborhood_reduce_f64.restype = None
-        L.orc_pr.argtypes = [C.c_int64, _i64p, _i32p, C.c_int, C.c_int, _f32p, _f32p, _i64p]
+        L.orc_pr.argtypes = [C.c_int64, _i64p, _i32p, C.c_int, C.c_int, _f32p, _f32p, _i64p, C.c_void_p]
         L.orc_pr.restype = C.c_int
         L.orc_bfs_push_level.argtypes = [_i64p, _i32p, _i32p, C.c_int64, C.c_int32, _i32p, _i32p]
         L.orc_bfs_push_level.restype = C.c_int64
@@ -90,6 +93,55 @@ def ref():
         R.ref_load_graph.restype = C.c_int
         _ref = R
     return _ref
+
+
+def have_ref_gpu() -> bool:
+    """The unmodified reference GPU primitives (oracle/_ref/ref_gpu_{bfs,sssp,pr}, ref_gpu_driver.cu)."""
+    build()
+    return all(os.path.exists(os.path.join(_HERE, "_ref", f"ref_gpu_{p}")) for p in ("bfs", "sssp", "pr"))
+
+
+def ref_gpu(prim: str, g: "CSR", src: int = 0, alpha: float | None = None, max_iter: int = 10, runs: int = 1,
+            queue_sizing: float = 1.0, values=None, timeout: float = 600.0):
+    """Runs the reference's own GPU enactor (bfs: enact_pushpull, sssp: enact, pr: enact) on the CSR in a child
+    process (the reference exit()s on frontier overflow and prints from its enactors).  Needs a GPU.
+    Returns (dict of output arrays, list of wall-clock seconds per run as the reference's tests time them)."""
+    import json
+    import tempfile
+    assert g.m < 2 ** 31 and g.n < 2 ** 31, "the reference's CSR is int32"
+    exe = os.path.join(_HERE, "_ref", f"ref_gpu_{prim}")
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.bin"), os.path.join(td, "out.bin")
+        with open(fin, "wb") as f:
+            f.write(np.array([g.n, g.m], np.int64).tobytes())
+            f.write(np.array([0 if g.weights is None else 1, 1], np.int32).tobytes())
+            f.write(g.offsets.astype(np.int32).tobytes())
+            f.write(g.indices.tobytes())
+            if g.weights is not None:
+                f.write(g.weights.tobytes())
+        cmd = [exe, prim, fin, fout, f"--src={src}", f"--max_iter={max_iter}", f"--runs={runs}",
+               f"--queue-sizing={queue_sizing}"]
+        if alpha is not None:
+            cmd.append(f"--alpha={alpha!r}")
+        if values is not None:
+            fv = os.path.join(td, "values.bin")
+            np.ascontiguousarray(values, np.float32).tofile(fv)
+            cmd.append(f"--values={fv}")
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not last:
+            raise RuntimeError(f"ref_gpu_{prim} failed rc={r.returncode}: {r.stdout[-400:]} {r.stderr[-400:]}")
+        info = json.loads(last[-1])
+        raw = np.fromfile(fout, np.uint8)
+    n = g.n
+    if prim == "bfs":
+        out = {"labels": raw[:4 * n].view(np.int32).copy()}
+    elif prim == "sssp":
+        out = {"labels": raw[:4 * n].view(np.float32).copy(), "preds": raw[4 * n:8 * n].view(np.int32).copy()}
+    else:
+        out = {"current": raw[:4 * n].view(np.float32).copy(), "reduced": raw[4 * n:8 * n].view(np.float32).copy()}
+    out["stdout"] = r.stdout
+    return out, info["elapsed_s"]
 
 
 # --------------------------------------------------------------------------- graphs
@@ -198,11 +250,13 @@ def neighborhood_reduce(g: CSR, frontier, values, op: str = "plus", identity: fl
     return red, asum
 
 
-def pr(g: CSR, max_iter: int = 10, scatter: bool = False):
+def pr(g: CSR, max_iter: int = 10, scatter: bool = False, init=None):
     cur = np.empty(g.n, np.float32)
     red = np.empty(g.n, np.float32)
     lens = np.zeros(max(max_iter, 1), np.int64)
-    it = lib().orc_pr(g.n, g.offsets, g.indices, max_iter, int(scatter), cur, red, lens)
+    init = None if init is None else np.ascontiguousarray(init, np.float32)
+    it = lib().orc_pr(g.n, g.offsets, g.indices, max_iter, int(scatter), cur, red, lens,
+                      None if init is None else init.ctypes.data)
     return cur, red, lens[:it]
 
 

@@ -293,12 +293,12 @@ ORC_API void orc_neighborhood_reduce_f64(int64_t n_front, const int32_t *frontie
  * number of iterations run. */
 ORC_API int orc_pr(int64_t n, const int64_t *offsets, const int32_t *indices, int max_iter,
                    int scatter, float *current /* n, out */, float *reduced /* n, out */,
-                   int64_t *frontier_lens) {
+                   int64_t *frontier_lens, const float *init /* nullable: initial ranks instead of 0.15f (pr_problem.hxx:38) */) {
     int32_t *fa = (int32_t *)malloc((size_t)n * sizeof(int32_t));
     int32_t *fb = (int32_t *)malloc((size_t)n * sizeof(int32_t));
     float *tmp = (float *)malloc((size_t)n * sizeof(float));
     int64_t len = n;
-    for (int64_t v = 0; v < n; ++v) { fa[v] = (int32_t)v; current[v] = 0.15f; reduced[v] = 0.0f; }
+    for (int64_t v = 0; v < n; ++v) { fa[v] = (int32_t)v; current[v] = init ? init[v] : 0.15f; reduced[v] = 0.0f; }
     int it = 0;
     while (len > 0 && it < max_iter) {
         /* neighborhood_kernel<..., plus_t<float>, has_output=false, push=false>; CSC == CSR (graph.hxx:75-80) */

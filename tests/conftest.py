@@ -34,6 +34,22 @@ def pytest_collection_modifyitems(config, items):
             it.add_marker(skip)
 
 
+def golden_f32(case, key):
+    """float32 array of a reference-GPU golden case: a JSON list, or base64 of float32 bytes (make_golden_gpu.py)."""
+    import base64
+    import numpy as np
+    if key in case:
+        return np.asarray(case[key], dtype=np.float32)
+    return np.frombuffer(base64.b64decode(case[key + "_f32_b64"]), dtype=np.float32).copy()
+
+
+def golden_custom_values(n):
+    """The non-uniform initial ranks make_golden_gpu.py fed the reference GPU PR (values_formula in the golden files)."""
+    import numpy as np
+    v = np.arange(n, dtype=np.uint64)
+    return (0.15 + ((v * np.uint64(2654435761)) % np.uint64(1000)).astype(np.float64) / 1000.0).astype(np.float32)
+
+
 @pytest.fixture(scope="session")
 def golden():
     import json

@@ -21,7 +21,7 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
-    assert d["impl"] == "reference" and d["metric"] == "bfs_gteps_rmat" and d["unit"] == "GTEPS"
+    assert d["impl"] == "reference" and d["metric"] == "bfs_gteps_rmat22_push" and d["unit"] == "GTEPS"
     for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
               "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
@@ -31,6 +31,15 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["value"] == d["value"] and cb["sample"]
     e = d["e2e"]
     assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_names_the_multi_gpu_metric_for_n_gt_1():
+    """N=1 (scale-22 push) and N>1 (scale-26 direction-optimising) are different workloads: the metric names differ so
+    that nobody divides one by the other."""
+    r = _run({"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"}, "--gpus", "2")
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+    assert d["metric"] == "bfs_gteps_rmat26_do" and d["n_gpus"] == 2
 
 
 def test_reference_arm_other_ranks_exit_quietly():

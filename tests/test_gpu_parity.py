@@ -106,6 +106,25 @@ def test_bfs_reference_fixtures(ctx, golden, name, mode):
         assert np.array_equal(labels.cpu().numpy(), oracle.bfs(o, src))
 
 
+@pytest.mark.parametrize("mode", ["ref_alpha", "beamer"])
+def test_bfs_directed_graph_without_switch(ctx, golden, mode):
+    """Directed input whose CSC aliases its CSR (what graph_to_device does, graph.hxx:75-80): as long as no pull level
+    runs (the reference's default alpha = 1/n never switches on small graphs, bfs_enactor.hxx:68) the direction-
+    optimising modes must label sinks exactly like the push BFS -- the "no in-arc" visited preset may only be applied
+    at the switch."""
+    import mini_b200 as mb
+    rec = golden("ref_fixture_sssp_directed.json")
+    o = oracle.CSR(rec["n"], rec["offsets"], rec["indices"], rec["weights"])
+    cases = [o, _rand_graph(3000, 9000, 11, symmetrize=False), _rand_graph(500, 400, 12, symmetrize=False)]
+    flag = mb.BFS_REF_ALPHA if mode == "ref_alpha" else mb.BFS_BEAMER
+    for c in cases:
+        g = _dev_graph(ctx, c)
+        for src in range(0, c.n, max(1, c.n // 7)):
+            # (alpha this small switches only once nothing is left to discover: unvisited == 0 / no unexplored arc)
+            labels, st = ctx.bfs(g, src, flag, alpha=1e-9, beta=18.0)
+            assert np.array_equal(labels.cpu().numpy(), oracle.bfs(c, src)), (c.n, src)
+
+
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", ["ref_rmat_s8.json", "ref_rmat_s10.json", "ref_rmat_s16.json", "ref_rmat_s12_seed3.json"])
 def test_bfs_rmat_golden(ctx, golden, name, mode):
@@ -271,6 +290,35 @@ def test_sssp_rmat_bit_exact(ctx, scale, ef, seed, src):
     dist, st = ctx.sssp(g, src)
     assert dist.cpu().numpy().tobytes() == oracle.sssp_dist(o, src).tobytes()
     assert st.num_levels >= 2
+
+
+def test_sssp_preds_acyclic_with_zero_weights(ctx):
+    """Zero-weight self loops and zero-weight u <-> v pairs (b200_mtx_load keeps both) must not make the
+    deterministic predecessor pass point a vertex at itself or close a 2-cycle: following preds always ends at -1."""
+    n = 64
+    rng = np.random.default_rng(4)
+    s = rng.integers(0, n, 300).astype(np.int32)
+    d = rng.integers(0, n, 300).astype(np.int32)
+    s = np.concatenate([s, np.arange(n, dtype=np.int32)])        # a self loop on every vertex
+    d = np.concatenate([d, np.arange(n, dtype=np.int32)])
+    o = oracle.build_csr(n, s, d, True, True)
+    w = o.weights.copy()
+    w[rng.random(w.shape[0]) < 0.5] = 0.0                        # half of the arcs (not pairwise consistent) weigh nothing
+    o = oracle.CSR(n, o.offsets, o.indices, w)
+    g = _dev_graph(ctx, o)
+    for src in (0, 7, 63):
+        preds = torch.empty(n, dtype=torch.int32, device="cuda")
+        dist, _ = ctx.sssp(g, src, preds=preds)
+        dd, p = dist.cpu().numpy(), preds.cpu().numpy()
+        assert dd.tobytes() == oracle.sssp_dist(o, src).tobytes()
+        assert p[src] == -1
+        for v in range(n):
+            u, hops = v, 0
+            while p[u] != -1:
+                assert p[u] != u and dd[p[u]] <= dd[u]
+                u = p[u]
+                hops += 1
+                assert hops <= n, "cycle in preds"
 
 
 def test_sssp_random_graphs(ctx):
@@ -526,6 +574,69 @@ def test_neighborhood_reduce_nonfinite_values_read_as_zero(ctx):
     red = torch.empty(o.n, dtype=torch.float32, device="cuda")
     ctx.neighborhood_reduce(g, torch.from_numpy(frontier).cuda(), torch.from_numpy(vals).cuda(), red)
     _check_reduce(red.cpu().numpy(), ref, asum)
+
+
+# ---- against the reference's own GPU code (tests/golden/ref_gpu_*.json, see tests/test_oracle.py for what they are)
+def _ref_gpu_pr_graph(golden, which):
+    if which == "fixture":
+        rec = golden("ref_fixture_pr.json")
+        return oracle.CSR(rec["n"], rec["offsets"], rec["indices"], rec["weights"])
+    return oracle.rmat_csr(12, 16, 1)
+
+
+@pytest.mark.parametrize("name,which", [("ref_gpu_pr_fixture.json", "fixture"), ("ref_gpu_pr_rmat_s12.json", "rmat12")])
+def test_neighborhood_reduce_vs_reference_gpu(ctx, golden, name, which):
+    """b200_neighborhood_reduce_f32 against the sums the reference's neighborhood_kernel<plus_t<float>> produced on a
+    B200 from non-uniform ranks (neighborhood.hxx:12-70): |ours - ref| <= 1e-5 * sum|terms| + 1e-6 per slot."""
+    from conftest import golden_custom_values, golden_f32
+    rec = golden(name)
+    o = _ref_gpu_pr_graph(golden, which)
+    g = _dev_graph(ctx, o)
+    case = [c for c in rec["cases"] if c["max_iter"] == 1 and c["custom_values"]][0]
+    vals = golden_custom_values(o.n)
+    frontier = torch.arange(o.n, dtype=torch.int32, device="cuda")
+    red = torch.empty(o.n, dtype=torch.float32, device="cuda")
+    arcs = ctx.neighborhood_reduce(g, frontier, torch.from_numpy(vals).cuda(), red, 0.0)
+    assert arcs == o.m
+    _, asum = oracle.neighborhood_reduce(o, np.arange(o.n, dtype=np.int32), vals.astype(np.float64))
+    ref = golden_f32(case, "reduced").astype(np.float64)
+    assert np.all(np.abs(red.cpu().numpy().astype(np.float64) - ref) <= 1e-5 * asum + 1e-6)
+
+
+@pytest.mark.parametrize("name,which", [("ref_gpu_pr_fixture.json", "fixture"), ("ref_gpu_pr_rmat_s12.json", "rmat12")])
+@pytest.mark.parametrize("iters", [1, 10])
+def test_pr_driver_vs_reference_gpu(ctx, golden, name, which, iters):
+    """b200_pr_run (slot-indexed, the reference's behaviour) against pr_enactor_t::enact run on a B200: the same
+    frontier length after every iteration, ranks and sums within rel 1e-4."""
+    from conftest import golden_f32
+    rec = golden(name)
+    o = _ref_gpu_pr_graph(golden, which)
+    g = _dev_graph(ctx, o)
+    case = [c for c in rec["cases"] if c["max_iter"] == iters and not c["custom_values"]][0]
+    cur, red, lens, st = ctx.pr(g, iters, False)
+    assert list(lens) == case["frontier_lens"]
+    assert np.allclose(cur.cpu().numpy(), golden_f32(case, "current"), rtol=1e-4, atol=1e-6)
+    assert np.allclose(red.cpu().numpy(), golden_f32(case, "reduced"), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,which", [("ref_gpu_traversal_fixture_bfs.json", "ref_fixture_bfs.json"),
+                                        ("ref_gpu_traversal_fixture_sssp.json", "ref_fixture_sssp_undirected.json"),
+                                        ("ref_gpu_traversal_rmat_s12.json", "rmat12")])
+def test_traversals_vs_reference_gpu(ctx, golden, name, which):
+    """BFS depths (all three modes) and SSSP distances bit-exact against the reference's GPU enactors' d_labels."""
+    rec = golden(name)
+    if which == "rmat12":
+        o = oracle.rmat_csr(12, 16, 1, weighted=True)
+    else:
+        r = golden(which)
+        o = oracle.CSR(r["n"], r["offsets"], r["indices"], r["weights"])
+    g = _dev_graph(ctx, o)
+    for c in rec["cases"]:
+        for mode in MODES:
+            lab, _ = _bfs(ctx, g, c["src"], mode)
+            assert hashlib.sha256(lab.cpu().numpy().tobytes()).hexdigest() == c["bfs_labels_sha256"]
+        dist, _ = ctx.sssp(g, c["src"])
+        assert hashlib.sha256(dist.cpu().numpy().tobytes()).hexdigest() == c["sssp_dist_sha256"]
 
 
 @pytest.mark.parametrize("scatter", [False, True])

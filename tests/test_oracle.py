@@ -141,6 +141,69 @@ def test_pr_driver_on_fixture(golden):
     assert len(lens) <= 50 and np.all(np.isfinite(cur))
 
 
+# ---------------------------------------------------------------- pinned by the reference's own GPU code
+# tests/golden/ref_gpu_*.json: outputs of the UNMODIFIED reference GPU primitives compiled for sm_100 and run on a
+# B200 (oracle/ref_gpu_driver.cu, tests/golden/make_golden_gpu.py).  They pin the parts of the oracle the
+# reference's tests never validate: neighbourhood sums, the PR driver (incl. its slot-indexed read)
+# and the SSSP distances.
+REF_GPU_PR = [("ref_gpu_pr_fixture.json", "fixture"), ("ref_gpu_pr_rmat_s12.json", "rmat12")]
+
+
+def _pr_graph(golden, which):
+    if which == "fixture":
+        return _csr_from(golden("ref_fixture_pr.json"))
+    return oracle.rmat_csr(12, 16, 1)
+
+
+@pytest.mark.parametrize("name,which", REF_GPU_PR)
+def test_neighborhood_reduce_matches_reference_gpu(golden, name, which):
+    """One enact() iteration from non-uniform ranks: d_reduced_ranks = the neighbourhood sums of neighborhood.hxx:47-58
+    computed by the reference's lbs_segreduce.  Tolerance: 1e-5 * sum|terms| + 1e-6 per slot."""
+    from conftest import golden_custom_values, golden_f32
+    rec = golden(name)
+    g = _pr_graph(golden, which)
+    case = [c for c in rec["cases"] if c["max_iter"] == 1 and c["custom_values"]][0]
+    vals = golden_custom_values(g.n)
+    red, asum = oracle.neighborhood_reduce(g, np.arange(g.n, dtype=np.int32), vals.astype(np.float64))
+    ref = golden_f32(case, "reduced").astype(np.float64)
+    assert np.all(np.abs(red - ref) <= 1e-5 * asum + 1e-6)
+    # and the filter's update of the ranks (pr_functor.hxx:11-17) from those sums
+    deg = np.diff(g.offsets).astype(np.float32)
+    new = np.where(deg > 0, np.float32(0.15) + np.float32(0.85) * ref.astype(np.float32) / np.maximum(deg, 1), np.float32(0.15))
+    assert np.allclose(golden_f32(case, "current"), new, rtol=1e-6, atol=0)
+    assert case["frontier_lens"] == [int((np.abs(new - vals) > np.float32(0.001) * vals).sum())]
+
+
+@pytest.mark.parametrize("name,which", REF_GPU_PR)
+def test_pr_driver_matches_reference_gpu(golden, name, which):
+    """pr_enactor_t::enact for 1 / 3 / 10 iterations, default and non-uniform initial ranks: identical frontier
+    length after every iteration, ranks and sums within rel 1e-4 of the reference GPU run."""
+    from conftest import golden_custom_values, golden_f32
+    rec = golden(name)
+    g = _pr_graph(golden, which)
+    for case in rec["cases"]:
+        init = golden_custom_values(g.n) if case["custom_values"] else None
+        cur, red, lens = oracle.pr(g, case["max_iter"], scatter=False, init=init)
+        assert lens.tolist() == case["frontier_lens"], (case["max_iter"], case["custom_values"])
+        assert np.allclose(cur, golden_f32(case, "current"), rtol=1e-4, atol=1e-6)
+        assert np.allclose(red, golden_f32(case, "reduced"), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,which", [("ref_gpu_traversal_fixture_bfs.json", "ref_fixture_bfs.json"),
+                                        ("ref_gpu_traversal_fixture_sssp.json", "ref_fixture_sssp_undirected.json"),
+                                        ("ref_gpu_traversal_rmat_s12.json", "rmat12")])
+def test_traversals_match_reference_gpu(golden, name, which):
+    """BFS depths (push-only and with the push -> pull switch forced) and SSSP DISTANCES (d_labels, which the
+    reference's own test never compares) of the reference GPU enactors, bit-exact."""
+    import hashlib
+    rec = golden(name)
+    g = oracle.rmat_csr(12, 16, 1, weighted=True) if which == "rmat12" else _csr_from(golden(which))
+    for c in rec["cases"]:
+        lab = oracle.bfs(g, c["src"])
+        assert hashlib.sha256(lab.tobytes()).hexdigest() == c["bfs_labels_sha256"] == c["bfs_pushpull_labels_sha256"]
+        assert hashlib.sha256(oracle.sssp_dist(g, c["src"]).tobytes()).hexdigest() == c["sssp_dist_sha256"]
+
+
 def test_push_level_restates_bfs():
     g = oracle.rmat_csr(10, 16, 1)
     labels = np.full(g.n, -1, np.int32)
