@@ -551,7 +551,7 @@ def main():
         return run_reference_arm(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 or world > 1:
-        from mini_b200 import dist_bench
+        import bench_multi as dist_bench
         return dist_bench.run(args)
     return run_single_gpu(args)
 

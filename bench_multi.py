@@ -1,4 +1,4 @@
-"""bench.py leg for N > 1 GPUs: direction-optimising BFS on RMAT scale-26 ef16 (BASELINE.json
+"""bench.py leg for N > 1 GPUs (bench code, not product: it may run the CPU oracle as the checker): direction-optimising BFS on RMAT scale-26 ef16 (BASELINE.json
 configs[3]), cyclic 1D vertex partition, one rank per GPU.  Strong scaling: the graph is fixed, each
 rank holds 1/N of the rows.
 

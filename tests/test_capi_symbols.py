@@ -92,9 +92,9 @@ int main(void) {
             C.sizeof(L.CLevelStat), C.sizeof(L.CStats), L.CStats.level_loop.offset, L.CStats.level.offset]
     assert got[:8] == want, (got, want)
     assert got[9] == 2
-    # dist_bench.py reads b200_workspace::launches through a prefix mirror of the struct
+    # bench_multi.py reads b200_workspace::launches through a prefix mirror of the struct
     import re
-    txt = open(os.path.join(ROOT, "mini_b200", "dist_bench.py")).read()
+    txt = open(os.path.join(ROOT, "bench_multi.py")).read()
     assert '("launches", C.c_int64)' in txt
     fields = re.findall(r'\("(\w+)", C\.(c_\w+)\)', txt[txt.index("class _WS"):txt.index("ws = C.cast")])
     sizes = {"c_void_p": 8, "c_int32": 4, "c_int64": 8, "c_uint": 4}
