@@ -238,11 +238,21 @@ def run_reduce_leg(ctx, mb, args, peak):
                          "slots_checked": int(g.n), "oracle_s": round(time.time() - t0, 1)}
         if args.ref_gpu and args.ref_gpu_pr and oracle.have_ref_gpu():
             try:
+                import re
                 rg, secs = oracle.ref_gpu("pr", o, max_iter=10, runs=2, timeout=600)
-                cur = ctx.pr(g, 10, False)[0].cpu().numpy()
+                cur, _, our_lens, _ = ctx.pr(g, 10, False)
+                cur = cur.cpu().numpy()
+                ref_lens = [int(x) for x in re.findall(r"finished iteration:\d+ output length: (\d+)", rg["stdout"])][-10:]
+                rel = np.abs(rg["current"] - cur) / np.maximum(np.abs(cur), 1e-6)
+                # (the reference reads its slot-indexed sums by vertex id, SURVEY quirk 8: once ONE vertex that sits within fp32
+                # rounding of the 0.001*old filter threshold is kept by one implementation and dropped by the other, every later
+                # slot shifts and the two runs stop being comparable vertex by vertex -- reported, not gated; the golden-vector
+                # tests pin the driver where no vertex sits on the threshold)
                 out["reference_gpu"] = {"impl": "pr_enactor_t::enact, unmodified reference compiled for sm_100, wall clock as test_pr.cu:36-40",
                                         "ms_per_step": 1e3 * min(secs), "speedup_ours": 1e3 * min(secs) / ms,
-                                        "ranks_within_rel_1e-4_of_ours": bool(np.allclose(rg["current"], cur, rtol=1e-4, atol=1e-6))}
+                                        "frontier_lens_reference": ref_lens, "frontier_lens_ours": [int(x) for x in our_lens],
+                                        "iterations_with_identical_frontier_length": int(sum(1 for a_, b_ in zip(ref_lens, our_lens) if a_ == b_)),
+                                        "fraction_of_ranks_within_rel_1e-4": float((rel <= 1e-4).mean())}
             except Exception as e:   # noqa: BLE001
                 out["reference_gpu"] = {"unavailable": repr(e)[:300]}
         del o

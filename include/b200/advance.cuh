@@ -338,7 +338,15 @@ static __global__ void bitmap_or_kernel(uint32_t *__restrict__ dst, const uint32
 // offsets of 4 vertices, then their first in-neighbours, then the 4 frontier-bitmap probes are in flight together.
 // Most vertices stop at their first in-arc (scale-26 level 1: 1.14 arcs inspected per discovered vertex); the
 // rest finish in a sequential early-exit loop.  Results and the inspected-arc count are the same as v1.
-template <int NT>
+// COHERENT = true: the bitmaps are read through L2 (ld.global.cg).  For a kernel that runs SEVERAL pull levels in one
+// launch (p2p_bfs.cu): the frontier / visited words are rewritten between its levels by other SMs, and neither L1 nor
+// the non-coherent path is invalidated inside a launch.  The graph arrays never change: they stay on __ldg.
+template <bool COHERENT>
+__device__ __forceinline__ uint32_t pull_ld_bm(const uint32_t *p) {
+    return COHERENT ? __ldcg(p) : __ldg(p);
+}
+
+template <int NT, bool COHERENT = false>
 __device__ __forceinline__ void bfs_pull_body(uint32_t n, const uint32_t *__restrict__ offsets,
                                               const int *__restrict__ indices,
                                               const uint32_t *__restrict__ frontier_bm,
@@ -370,7 +378,7 @@ __device__ __forceinline__ void bfs_pull_body(uint32_t n, const uint32_t *__rest
         uint32_t vis = 0xffffffffu, unv = 0u;
         const bool have_w = lane < (unsigned)CW && w < num_words;
         if (have_w) {
-            vis = visited_bm[w];
+            vis = COHERENT ? __ldcg(visited_bm + w) : visited_bm[w];
             unv = ~vis;
             const uint32_t rem = n - (w << 5);
             if (rem < 32u) unv &= (1u << rem) - 1u;      // bits past n in the last word
@@ -432,7 +440,7 @@ __device__ __forceinline__ void bfs_pull_body(uint32_t n, const uint32_t *__rest
                 hit[u] = 0u;
                 if (nb[u] >= 0) {
                     const uint32_t ub = part.bit((uint32_t)nb[u]);
-                    hit[u] = (__ldg(frontier_bm + (ub >> 5)) >> (ub & 31)) & 1u;
+                    hit[u] = (pull_ld_bm<COHERENT>(frontier_bm + (ub >> 5)) >> (ub & 31)) & 1u;
                 }
             }
             if (first_nbr) {   // only the vertices that go on need their row bounds
@@ -463,7 +471,7 @@ __device__ __forceinline__ void bfs_pull_body(uint32_t n, const uint32_t *__rest
                         for (uint32_t t = 0; t < B; ++t) {
                             if (d[t] >= 0) {
                                 const uint32_t ub = part.bit((uint32_t)d[t]);
-                                h |= ((__ldg(frontier_bm + (ub >> 5)) >> (ub & 31)) & 1u) << t;
+                                h |= ((pull_ld_bm<COHERENT>(frontier_bm + (ub >> 5)) >> (ub & 31)) & 1u) << t;
                             }
                         }
                         if (h) {
@@ -541,20 +549,7 @@ __global__ void __launch_bounds__(NT, B200_PULL_MINB) bfs_pull_dyn_kernel(uint32
 static __global__ void sparse_to_bitmap_dyn_kernel(const LoopDyn *dyn, uint32_t *bitmap, const uint32_t *__restrict__ pull_offsets,
                                                    uint32_t n, const uint32_t *__restrict__ iso, uint32_t *visited) {
     if (!(dyn->run & LOOP_RUN_TO_PULL)) return;
-    {
-        const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5, num_words = (n + 31u) >> 5;
-        const unsigned lane = threadIdx.x & 31u;
-        for (uint32_t word = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; word < num_words; word += warps_total) {
-            unsigned mask;
-            if (iso) {
-                mask = iso[word];
-            } else {
-                const uint32_t v = (word << 5) + lane;
-                mask = __ballot_sync(0xffffffffu, v < n && pull_offsets[v + 1] == pull_offsets[v]);
-            }
-            if (lane == 0 && mask) visited[word] |= mask;
-        }
-    }
+    or_no_in_arc_words(blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, pull_offsets, n, iso, visited);
     const int *__restrict__ sparse = dyn->in;
     const uint32_t len = dyn->len;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {

@@ -48,6 +48,7 @@ __device__ __forceinline__ void loop_trace(const LoopDyn *dyn, unsigned id) {
 // ~1.1 us for a kernel that returns immediately, so the loop body is a flat kernel sequence and every
 // kernel checks its bit.
 enum : uint32_t { LOOP_RUN_PUSH = 1u, LOOP_RUN_PULL = 2u, LOOP_RUN_TO_PULL = 4u, LOOP_RUN_TO_PUSH = 8u,
-                  LOOP_RUN_SCAN = 16u };   // the push level's frontier has no scan yet (first level, after a hand-over)
+                  LOOP_RUN_SCAN = 16u,     // the push level's frontier has no scan yet (first level, after a hand-over)
+                  LOOP_RUN_SMALL = 32u };  // multi-GPU: the next push levels are small -- one persistent kernel runs them (p2p_bfs.cu)
 
 }  // namespace b200

@@ -565,6 +565,37 @@ struct BfsPushPartQ {
     __device__ __forceinline__ bool route_is_local(int d) const { return d == (int)part.me; }
 };
 
+// Multi-GPU push level whose exchange is the `known` bitmap itself (p2p_bfs.cu, big levels): the advance only CLAIMS
+// the bit of every unvisited neighbour -- owner or not -- and emits nothing; after the level barrier each owner ORs
+// its slice of every rank's `known` and labels what is new.  The atomicOr result is unused, so it compiles to a
+// fire-and-forget RED.
+struct BfsClaimPartQ {
+    uint32_t *known;
+    Partition part;
+    static constexpr bool WEIGHTED = false;
+    using SrcVal = NoSrc;
+    using Token = NoSrc;
+    using Evidence = uint32_t;
+    using Cand = CandWords<1>;   // bit index in the rank-major map
+    __device__ __forceinline__ SrcVal load_src(int) const { return NoSrc(); }
+    __device__ __forceinline__ Evidence probe_load(bool on, SrcVal, int, int dst, uint32_t) const {
+        uint32_t word = 0xffffffffu;
+        if (on) word = known[part.bit((uint32_t)dst) >> 5];
+        return word;
+    }
+    __device__ __forceinline__ bool probe_eval(Evidence word, SrcVal, int dst, float) const {
+        return !((word >> (part.bit((uint32_t)dst) & 31)) & 1u);
+    }
+    __device__ __forceinline__ Cand make_cand(SrcVal, int, int dst, uint32_t, float) const {
+        return Cand{{part.bit((uint32_t)dst)}};
+    }
+    __device__ __forceinline__ Token claim(const Cand &c) const {
+        atomicOr(known + (c.w[0] >> 5), 1u << (c.w[0] & 31));
+        return NoSrc();
+    }
+    __device__ __forceinline__ int finish(Token, const Cand &) const { return -1; }
+};
+
 // BfsPushPartQ whose label comes from the device-resident level state (graph-driven loop).
 struct BfsPushPartQDyn : BfsPushPartQ {
     const LoopDyn *dyn;

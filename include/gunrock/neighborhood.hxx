@@ -78,7 +78,9 @@ void emit_raw(std::false_type, b200_workspace *, const b200::LbsArgs &, typename
               std::shared_ptr<frontier_t<int>> &) {}
 }  // namespace detail
 
-template <typename Problem, typename Functor, typename Value, typename reduce_op, bool has_output, bool push,
+// (push defaults to false = pull over the CSC: the reference's coloring / lspar call sites pass five template
+// arguments, coloring_enactor.hxx:60-76, one short of its own declaration)
+template <typename Problem, typename Functor, typename Value, typename reduce_op, bool has_output, bool push = false,
           bool write_back = false>
 int neighborhood_kernel(std::shared_ptr<Problem> problem, std::shared_ptr<frontier_t<int>> &input,
                         std::shared_ptr<frontier_t<int>> &output, Value *reduced, Value identity, int iteration,

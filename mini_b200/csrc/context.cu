@@ -5,6 +5,7 @@
 #include <cstring>
 #include <new>
 #include "engine.cuh"
+#include "b200/device_utils.cuh"
 
 namespace b200 {
 thread_local int g_last_cuda_error = 0;
@@ -37,20 +38,9 @@ static __global__ void isolated_bitmap_kernel(const uint32_t *__restrict__ offse
 }
 
 // visited |= "vertex has no in-arc" (iso: the caller's prebuilt bitmap, else derived from the offsets)
-static __global__ void or_no_in_arc_kernel(const uint32_t *__restrict__ offsets, uint32_t n, uint32_t num_words,
-                                           const uint32_t *__restrict__ iso, uint32_t *visited) {
-    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
-    const unsigned lane = threadIdx.x & 31u;
-    for (uint32_t word = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; word < num_words; word += warps_total) {
-        unsigned mask;
-        if (iso) {
-            mask = iso[word];
-        } else {
-            const uint32_t v = (word << 5) + lane;
-            mask = __ballot_sync(0xffffffffu, v < n && offsets[v + 1] == offsets[v]);
-        }
-        if (lane == 0 && mask) visited[word] |= mask;
-    }
+static __global__ void or_no_in_arc_kernel(const uint32_t *__restrict__ offsets, uint32_t n, const uint32_t *__restrict__ iso,
+                                           uint32_t *visited) {
+    or_no_in_arc_words(blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, offsets, n, iso, visited);
 }
 
 static __global__ void first_in_neighbor_kernel(const uint32_t *__restrict__ offsets, const int32_t *__restrict__ indices,
@@ -83,8 +73,7 @@ cudaError_t launch_no_in_arc_bitmap(b200_workspace *ws, const uint32_t *pull_off
 }
 
 cudaError_t launch_or_no_in_arc(b200_workspace *ws, const uint32_t *pull_offsets, int64_t n, const uint32_t *iso, uint32_t *d_visited) {
-    const int64_t words = (n + 31) / 32;
-    or_no_in_arc_kernel<<<ws->num_sms * 8, 256, 0, (cudaStream_t)ws->stream>>>(pull_offsets, (uint32_t)n, (uint32_t)words, iso, d_visited);
+    or_no_in_arc_kernel<<<ws->num_sms * 8, 256, 0, (cudaStream_t)ws->stream>>>(pull_offsets, (uint32_t)n, iso, d_visited);
     ws->launches++;
     return cudaGetLastError();
 }

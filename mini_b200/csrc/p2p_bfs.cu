@@ -77,6 +77,18 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
+// Spin loops poll the flag, not the clock: %globaltimer is read once every 256 polls (a read per poll made a flag
+// barrier 7-9 us and a 148-CTA grid barrier 7 us in the traces of rounds 1 / 2).  Returns true once `limit_ns` have passed.
+__device__ __forceinline__ bool spin_expired(uint32_t &polls, unsigned long long &t0, unsigned long long limit_ns) {
+    if ((++polls & 255u) != 0u) return false;
+    const unsigned long long now = globaltimer_ns();
+    if (t0 == 0ull) {
+        t0 = now;
+        return false;
+    }
+    return now - t0 > limit_ns;
+}
+
 // One warp: lane p signals rank p (release: everything this rank wrote before -- in this kernel
 // or in earlier kernels of the stream -- is visible to whoever acquires the flag) and waits for
 // rank p's signal.  Returns false on every lane if any wait timed out.
@@ -87,9 +99,10 @@ __device__ __forceinline__ bool p2p_signal_wait(const Peers &peers, int me, int 
     if (p < P && p != me) {
         st_release_sys(&reinterpret_cast<Ctrl *>(peers.base[p])->flags[me], epoch);
         const unsigned long long *mine = &reinterpret_cast<const Ctrl *>(peers.base[me])->flags[p];
-        const unsigned long long t0 = globaltimer_ns();
+        unsigned long long t0 = 0ull;
+        uint32_t polls = 0u;
         while (ld_acquire_sys(mine) < epoch) {
-            if (globaltimer_ns() - t0 > P2P_TIMEOUT_NS) {
+            if (spin_expired(polls, t0, P2P_TIMEOUT_NS)) {
                 ok = false;
                 break;
             }
@@ -267,10 +280,11 @@ struct P2PLoopParams {      // mapped pinned, read by the init kernel
     unsigned long long bar_epoch0;
     uint32_t lb_epoch0, stats_seq0;
     unsigned long long *trace;
-    uint32_t trace_cap, pad;
+    uint32_t trace_cap, small_on;
+    long long small_arcs, small_verts;   // a push level runs in the persistent small-level kernel while its frontier is this small
 };
 struct P2PLevelRec {
-    int32_t direction, pad;
+    int32_t direction, exchange;   // exchange: 0 = vertex ids through the inboxes, 1 = bitmap slices
     long long frontier_len, arcs, discovered, sent;
 };
 struct P2PLoopResult {      // mapped pinned, written by the decide step
@@ -287,6 +301,27 @@ struct P2PLoopState {       // device
     int32_t level, pull, mode, kernels_per_level;
     float alpha, beta;
     long long n, m_unexplored, flen, reached, total_arcs, launches;
+    long long small_arcs, small_verts;
+    uint32_t small_on, pad;
+};
+
+// ---- persistent small-level kernel: shared state -------------------------------------------
+constexpr int SMALL_NT = 512;
+constexpr int SMALL_SLOTS = 4;
+constexpr uint32_t SMALL_ROW = 512;   // rows up to this many arcs: one warp; longer rows: pieces of SMALL_ROW arcs over the whole grid
+constexpr unsigned long long SMALL_GRID_TIMEOUT_NS = 5ull * 1000ull * 1000ull * 1000ull;
+struct SmallCounters {      // one slot per level (level & 3): nobody has to wait for a reset
+    unsigned long long next_cnt, arcs, deg, big_cnt, overflow, pad;
+    unsigned long long send_cnt[P2P_MAX];
+};
+struct PullCounters {       // the pull-levels kernel's per-level counters (indexed by B200_CNT_*), one slot per level & 3
+    unsigned long long c[B200_NUM_COUNTERS];
+};
+struct SmallShared {        // device memory
+    SmallCounters slot[SMALL_SLOTS];
+    unsigned int bar_count, bar_gen;   // grid barrier of the small-level / pull-levels kernels
+    unsigned int abort;
+    unsigned int absorb_tile;          // dynamic tile claims of p2p_absorb_bits_kernel (re-armed by the decide kernel that follows it)
 };
 
 struct FrontierQuadsDynPart {   // FrontierQuads over the device-selected list, rows of a 1D partition
@@ -307,16 +342,23 @@ struct FrontierQuadsDynPart {   // FrontierQuads over the device-selected list, 
     }
 };
 
+__device__ __forceinline__ void small_zero_slot(SmallCounters *c) {
+    c->next_cnt = 0ull; c->arcs = 0ull; c->deg = 0ull; c->big_cnt = 0ull; c->overflow = 0ull;
+    for (int i = 0; i < P2P_MAX; ++i) c->send_cnt[i] = 0ull;
+}
 
-__global__ void p2p_loop_init_kernel(const P2PLoopParams *p, P2PLoopState *s, int32_t *labels, uint32_t *known, int32_t *f0,
-                                     int32_t *f1, long long n, Partition part, unsigned long long *counters,
-                                     unsigned int *tile_counters, unsigned long long *box_counts, int kernels_per_level) {
+__global__ void p2p_loop_init_kernel(const P2PLoopParams *p, P2PLoopState *s, int32_t *labels, uint32_t *known, uint32_t *done,
+                                     int32_t *f0, int32_t *f1, long long n, Partition part, unsigned long long *counters,
+                                     unsigned int *tile_counters, SmallShared *sh, PullCounters *pull_slots,
+                                     int kernels_per_level) {
     const int src = p->src;
     const uint32_t b = part.bit((uint32_t)src);
     known[b >> 5] |= 1u << (b & 31);
     const bool mine = part.owner((uint32_t)src) == part.me;
     if (mine) {
-        labels[part.row((uint32_t)src)] = 0;
+        const uint32_t r = part.row((uint32_t)src);
+        labels[r] = 0;
+        done[r >> 5] |= 1u << (r & 31);
         f0[0] = src;
     }
     s->dyn.in = f0;
@@ -325,8 +367,8 @@ __global__ void p2p_loop_init_kernel(const P2PLoopParams *p, P2PLoopState *s, in
     s->dyn.epoch = p->lb_epoch0 & 0x3FFFFFFFu;
     s->dyn.next_label = 1;
     s->dyn.bsel = 0u;
-    s->dyn.run = LOOP_RUN_PUSH;
-    s->dyn.scanned_in = nullptr;   // the routed flush does not create work: scan before every push level
+    s->dyn.run = p->small_on ? LOOP_RUN_SMALL : LOOP_RUN_PUSH;   // level 0 is one vertex
+    s->dyn.scanned_in = nullptr;   // big push levels scan their frontier (it comes out of a bitmap)
     s->dyn.rows_in = nullptr;
     s->dyn.scanned_out = nullptr;
     s->dyn.rows_out = nullptr;
@@ -348,67 +390,570 @@ __global__ void p2p_loop_init_kernel(const P2PLoopParams *p, P2PLoopState *s, in
     s->reached = 1;
     s->total_arcs = 0;
     s->launches = 1;
+    s->small_arcs = p->small_arcs;
+    s->small_verts = p->small_verts;
+    s->small_on = p->small_on;
     for (int i = 0; i < B200_NUM_COUNTERS; ++i) counters[i] = 0ull;
-    for (int i = 0; i < P2P_MAX; ++i) box_counts[i] = 0ull;
     tile_counters[0] = 0u;
     tile_counters[1] = 0u;
+    for (int i = 0; i < SMALL_SLOTS; ++i) {
+        small_zero_slot(&sh->slot[i]);
+        for (int k = 0; k < B200_NUM_COUNTERS; ++k) pull_slots[i].c[k] = 0ull;
+    }
+    sh->bar_count = 0u;
+    sh->abort = 0u;
+    sh->absorb_tile = 0u;
 }
 
-// the slice this level's discoveries are written to (slice[bsel ^ 1]) must start all-zero
-__global__ void p2p_clear_slice_dyn_kernel(const LoopDyn *dyn, uint4 *slice0, uint4 *slice1, uint32_t quads) {
-    loop_trace(dyn, 1);
-    if (!(dyn->run & LOOP_RUN_PUSH)) return;
-    uint4 *w = dyn->bsel ? slice0 : slice1;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += gridDim.x * blockDim.x) w[i] = make_uint4(0u, 0u, 0u, 0u);
+// ---------------------------------------------------------------------------------------------
+// The small levels of a traversal (level 0: one vertex; the tail after the pull phase; every level of a
+// small graph) cost a CUDA-graph iteration of ~10 kernel nodes and two flag barriers each in the flat body
+// -- 58 us per level at 8 GPUs for levels that move a few thousand vertices (round-1 trace).  This kernel
+// runs CONSECUTIVE small push levels inside one launch: per level two grid barriers and two cross-GPU flag
+// barriers, no kernel boundary.  One CTA per SM, all resident (the host sizes the grid from the occupancy).
+//   phase A  push over the local frontier: rows <= SMALL_ROW arcs one warp each, longer rows (the hub of
+//            level 0: 1.7 M arcs at scale 26) cut into SMALL_ROW-arc pieces dealt over every warp of the grid;
+//            a won vertex is labelled in place (owned) or stored into its owner's inbox over NVLink;
+//   barrier  grid, then flags to / from every peer (the counts travel with the flag);
+//   phase B  absorb the inbox segments: label-if-unvisited, append to the next frontier;
+//   barrier  grid, stats row to every peer, flags; every CTA sums the rows and takes the same decision.
+// The level state lives in registers (identically in every CTA); CTA 0 writes it back on exit for the
+// kernels that follow in the same graph iteration (pull or big push), so they run without another decide.
+// Every wait has a wall-clock timeout that raises the abort flag: a lost peer or a CTA that never became
+// resident ends the traversal with B200_ERR_TIMEOUT instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------------
+struct SmallArgs {
+    Peers peers;
+    int me, P;
+    Partition part;
+    const uint32_t *offsets;      // local CSR (global column ids)
+    const int *indices;
+    uint32_t *known, *done;
+    int *labels;
+    P2PLoopState *s;
+    SmallShared *sh;
+    uint32_t *big;                // frontier slots of the long rows of a level
+    size_t off_inbox, off_slice0, off_slice1;
+    uint32_t wl;                  // words per slice
+    const uint32_t *iso;          // no-in-arc bitmap of the local rows (nullable: derived from pull_offsets)
+    const uint32_t *pull_offsets;
+    P2PLoopResult *res;
+    cudaGraphConditionalHandle h_while;
+    PullCounters *pull_slots;     // re-armed on exit (the pull-levels kernel may run next; it re-arms this kernel's)
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_gpu_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
-__global__ void __launch_bounds__(32) p2p_publish_counts_dyn_kernel(Peers peers, int me, int P, P2PLoopState *s,
-                                                                    const unsigned long long *box_counts) {
-    loop_trace(&s->dyn, 4);
-    if (!(s->dyn.run & LOOP_RUN_PUSH)) return;
-    const int p = (int)lane_id();
-    const unsigned long long epoch = s->bar_epoch + 1ull;
-    __syncwarp();
-    if (p < P && p != me) st_relaxed_sys(&reinterpret_cast<Ctrl *>(peers.base[p])->counts[me], box_counts[p]);
-    const bool ok = p2p_signal_wait(peers, me, P, epoch);
-    if (p == 0) {
-        loop_trace(&s->dyn, 13);
-        s->bar_epoch = epoch;
-        if (!ok) s->timeout = 1u;
+// Whole grid.  s_gen: this CTA's copy of the barrier generation (shared memory).  Returns false once aborted.
+__device__ __forceinline__ bool small_grid_barrier(SmallShared *sh, unsigned *s_gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned g = *s_gen;
+        __threadfence();
+        if (atomicAdd(&sh->bar_count, 1u) == gridDim.x - 1u) {
+            sh->bar_count = 0u;
+            __threadfence();
+            atomicAdd(&sh->bar_gen, 1u);
+        } else {
+            unsigned long long t0 = 0ull;
+            uint32_t polls = 0u;
+            while (ld_acquire_gpu_u32(&sh->bar_gen) == g) {
+                if (spin_expired(polls, t0, SMALL_GRID_TIMEOUT_NS)) {
+                    atomicExch(&sh->abort, 1u);
+                    break;
+                }
+                if ((polls & 63u) == 0u && ld_relaxed_gpu_u32(&sh->abort)) break;
+            }
+        }
+        *s_gen = g + 1u;
+    }
+    __syncthreads();
+    return ld_relaxed_gpu_u32(&sh->abort) == 0u;
+}
+
+// Every CTA waits for the flags of all peers (they live in this rank's own heap: polling is local).
+__device__ __forceinline__ bool small_wait_peers(const SmallArgs &a, unsigned long long epoch) {
+    if (threadIdx.x < (unsigned)a.P && (int)threadIdx.x != a.me) {
+        const unsigned long long *mine = &reinterpret_cast<const Ctrl *>(a.peers.base[a.me])->flags[threadIdx.x];
+        unsigned long long t0 = 0ull;
+        uint32_t polls = 0u;
+        while (ld_acquire_sys(mine) < epoch) {
+            if (spin_expired(polls, t0, P2P_TIMEOUT_NS)) {
+                atomicExch(&a.sh->abort, 1u);
+                break;
+            }
+            if ((polls & 63u) == 0u && ld_relaxed_gpu_u32(&a.sh->abort)) break;
+        }
+    }
+    __syncthreads();
+    return ld_relaxed_gpu_u32(&a.sh->abort) == 0u;
+}
+
+__global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs a) {
+    constexpr int NW = SMALL_NT / 32, U = 4;
+    __shared__ unsigned s_gen;
+    __shared__ unsigned long long s_sum[8];
+    P2PLoopState *s = a.s;
+    loop_trace(&s->dyn, 20);
+    if (!(s->dyn.run & LOOP_RUN_SMALL)) return;
+    SmallShared *sh = a.sh;
+    if (ld_relaxed_gpu_u32(&sh->abort)) return;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5, lt_mask = lanemask_lt();
+    const uint32_t gwarp = blockIdx.x * NW + warp, total_warps = gridDim.x * NW;
+    const int me = a.me, P = a.P;
+    const Partition part = a.part;
+    Ctrl *my_ctrl = reinterpret_cast<Ctrl *>(a.peers.base[me]);
+    const int *my_inbox = reinterpret_cast<const int *>(a.peers.base[me] + a.off_inbox);
+    const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+    if (threadIdx.x == 0) s_gen = ld_relaxed_gpu_u32(&sh->bar_gen);
+
+    // the level state, identically in every CTA
+    int level = s->level;
+    const int mode = s->mode;
+    const float alpha = s->alpha;
+    long long m_unexplored = s->m_unexplored, flen = s->flen, reached = s->reached, total_arcs = s->total_arcs;
+    const long long small_arcs = s->small_arcs;
+    unsigned long long bar_epoch = s->bar_epoch;
+    uint32_t stats_seq = s->stats_seq, bsel = s->dyn.bsel;
+    const int *in = s->dyn.in;
+    int *out = s->dyn.out;
+    uint32_t len = s->dyn.len;
+    long long launches = s->launches;
+    int status = B200_OK;
+    uint32_t next_run = 0u;
+    bool finished = false;
+    __syncthreads();
+
+    for (;;) {
+        SmallCounters *c = &sh->slot[level & (SMALL_SLOTS - 1)];
+        if (lead) small_zero_slot(&sh->slot[(level + 1) & (SMALL_SLOTS - 1)]);   // last used three levels ago
+        const int next_label = level + 1;
+        unsigned long long arc_cnt = 0, deg_sum = 0;
+
+        // the per-arc step of a warp over arcs [b, e) of one row piece, 32 * U arcs at a time: all index loads, then all
+        // probes, then all claims are in flight together; the winners are counted per destination over the whole tile and
+        // every destination's slots are reserved with ONE atomic, the P atomics issued side by side by lanes 0 .. P-1
+        auto expand = [&](uint32_t b, uint32_t e) {
+            for (uint32_t e0 = b; e0 < e; e0 += 32u * U) {
+                int d[U], owner[U];
+                uint32_t kb[U], w[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t ee = e0 + 32u * u + lane;
+                    d[u] = ee < e ? __ldg(a.indices + ee) : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    kb[u] = 0u;
+                    w[u] = 0xffffffffu;
+                    if (d[u] >= 0) {
+                        kb[u] = part.bit((uint32_t)d[u]);
+                        w[u] = a.known[kb[u] >> 5];
+                    }
+                }
+                uint32_t old[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    old[u] = 0xffffffffu;
+                    if (!((w[u] >> (kb[u] & 31)) & 1u)) old[u] = atomicOr(a.known + (kb[u] >> 5), 1u << (kb[u] & 31));
+                }
+                bool any = false;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool won = !((old[u] >> (kb[u] & 31)) & 1u);
+                    owner[u] = won ? (int)part.owner((uint32_t)d[u]) : -1;
+                    any |= won;
+                    if (won && owner[u] == me) {
+                        const uint32_t r = part.row((uint32_t)d[u]);
+                        atomicOr(a.done + (r >> 5), 1u << (r & 31));
+                        a.labels[r] = next_label;
+                        deg_sum += __ldg(a.offsets + r + 1) - __ldg(a.offsets + r);
+                    }
+                }
+                if (!__any_sync(FULL_MASK, any)) continue;
+                uint32_t tot_mine = 0u;                  // lane p: winners of this tile that rank p owns
+                for (int p = 0; p < P; ++p) {
+                    uint32_t tot = 0u;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) tot += __popc(__ballot_sync(FULL_MASK, owner[u] == p));
+                    if ((int)lane == p) tot_mine = tot;
+                }
+                unsigned long long base_mine = 0ull;
+                if (tot_mine) base_mine = atomicAdd((int)lane == me ? &c->next_cnt : &c->send_cnt[lane], (unsigned long long)tot_mine);
+                for (int p = 0; p < P; ++p) {
+                    if (!__shfl_sync(FULL_MASK, tot_mine, p)) continue;
+                    unsigned long long run = __shfl_sync(FULL_MASK, base_mine, p);
+                    int *box = p == me ? out : reinterpret_cast<int *>(a.peers.base[p] + a.off_inbox) + (size_t)me * part.n_local;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const unsigned mask = __ballot_sync(FULL_MASK, owner[u] == p);
+                        if (owner[u] == p) {
+                            const unsigned long long pos = run + __popc(mask & lt_mask);
+                            if (pos < part.n_local) box[pos] = d[u];
+                            else c->overflow = 1ull;
+                        }
+                        run += __popc(mask);
+                    }
+                }
+            }
+            arc_cnt += e - b;   // (counted once per piece: same value on every lane)
+        };
+
+        // ---- phase A, pass 1: short rows, one warp each; long rows are queued
+        loop_trace(&s->dyn, 21);
+        for (uint32_t i = gwarp; i < len; i += total_warps) {
+            // (the frontier lists and the long-row queue are rewritten level after level inside this one launch: L1
+            // may hold a line of an earlier level, so they are read through L2)
+            const uint32_t r = (uint32_t)__ldcg(in + i) >> part.log_p;
+            const uint32_t b = __ldg(a.offsets + r), e = __ldg(a.offsets + r + 1);
+            if (e - b > SMALL_ROW) {
+                if (lane == 0) a.big[atomicAdd(&c->big_cnt, 1ull)] = r;
+                continue;
+            }
+            if (e > b) expand(b, e);
+        }
+        if (!small_grid_barrier(sh, &s_gen)) break;
+        // ---- pass 2: the pieces of the long rows, dealt round-robin over the warps of the grid
+        {
+            const uint32_t nbig = (uint32_t)ld_volatile_u64(&c->big_cnt);
+            uint32_t skew = 0;
+            for (uint32_t k = 0; k < nbig; ++k) {
+                const uint32_t r = __ldcg(a.big + k);
+                const uint32_t b = __ldg(a.offsets + r), e = __ldg(a.offsets + r + 1);
+                const uint32_t pieces = (e - b + SMALL_ROW - 1) / SMALL_ROW;
+                for (uint32_t p = (gwarp + total_warps - skew) % total_warps; p < pieces; p += total_warps) {
+                    const uint32_t pb = b + p * SMALL_ROW;
+                    expand(pb, e - pb > SMALL_ROW ? pb + SMALL_ROW : e);
+                }
+                skew = (skew + pieces) % total_warps;
+            }
+        }
+        __threadfence_system();          // this thread's stores into the peers' inboxes, before the flag
+        if (!small_grid_barrier(sh, &s_gen)) break;
+        // ---- everybody's sends are out: counts + flag to every peer, then wait for theirs
+        ++bar_epoch;
+        if (blockIdx.x == 0 && threadIdx.x < (unsigned)P && (int)threadIdx.x != me) {
+            Ctrl *pc = reinterpret_cast<Ctrl *>(a.peers.base[threadIdx.x]);
+            st_relaxed_sys(&pc->counts[me], ld_volatile_u64(&c->send_cnt[threadIdx.x]));
+            st_release_sys(&pc->flags[me], bar_epoch);
+        }
+        loop_trace(&s->dyn, 22);
+        if (!small_wait_peers(a, bar_epoch)) break;
+        loop_trace(&s->dyn, 23);
+        // ---- phase B: absorb what the peers left in the inbox segments
+        for (int q = 0; q < P; ++q) {
+            if (q == me) continue;
+            const unsigned long long cnt = ld_relaxed_sys(&my_ctrl->counts[q]);
+            const int *seg = my_inbox + (size_t)q * part.n_local;
+            for (unsigned long long base = (unsigned long long)gwarp * 32ull; base < cnt; base += (unsigned long long)total_warps * 32ull) {
+                const unsigned long long i = base + lane;
+                bool fresh = false;
+                int u = -1;
+                if (i < cnt) {
+                    u = __ldcg(seg + i);
+                    const uint32_t r = part.row((uint32_t)u), bit = 1u << (r & 31);
+                    fresh = !(a.done[r >> 5] & bit) && !(atomicOr(a.done + (r >> 5), bit) & bit);
+                    if (fresh) {
+                        a.labels[r] = next_label;
+                        atomicOr(a.known + (size_t)me * a.wl + (r >> 5), bit);
+                        deg_sum += __ldg(a.offsets + r + 1) - __ldg(a.offsets + r);
+                    }
+                }
+                const unsigned mask = __ballot_sync(FULL_MASK, fresh);
+                if (mask) {
+                    unsigned long long pos0 = 0;
+                    const unsigned leader = __ffs(mask) - 1;
+                    if (lane == leader) pos0 = atomicAdd(&c->next_cnt, (unsigned long long)__popc(mask));
+                    pos0 = __shfl_sync(FULL_MASK, pos0, leader);
+                    if (fresh) {
+                        const unsigned long long pos = pos0 + __popc(mask & lt_mask);
+                        if (pos < part.n_local) out[pos] = u;
+                        else c->overflow = 1ull;
+                    }
+                }
+            }
+        }
+        // level totals of this CTA -> the slot
+        if (threadIdx.x < 2) s_sum[threadIdx.x] = 0ull;
+        __syncthreads();
+#pragma unroll
+        for (int d2 = 16; d2 > 0; d2 >>= 1) deg_sum += __shfl_xor_sync(FULL_MASK, deg_sum, d2);
+        if (lane == 0) {
+            if (arc_cnt) atomicAdd(&s_sum[0], arc_cnt);
+            if (deg_sum) atomicAdd(&s_sum[1], deg_sum);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (s_sum[0]) atomicAdd(&c->arcs, s_sum[0]);
+            if (s_sum[1]) atomicAdd(&c->deg, s_sum[1]);
+        }
+        if (!small_grid_barrier(sh, &s_gen)) break;
+        // ---- level summary: this rank's row into every heap, flags, sum of the rows
+        const unsigned long long next_local = ld_volatile_u64(&c->next_cnt);
+        const int parity = (int)(stats_seq & 1u);
+        ++bar_epoch;
+        if (blockIdx.x == 0 && threadIdx.x < (unsigned)P) {
+            unsigned long long sent = 0;
+            for (int q = 0; q < P; ++q)
+                if (q != me) sent += ld_volatile_u64(&c->send_cnt[q]);
+            unsigned long long *dst = reinterpret_cast<Ctrl *>(a.peers.base[threadIdx.x])->stats[parity][me];
+            st_relaxed_sys(dst + ROW_NEXT, next_local);
+            st_relaxed_sys(dst + ROW_ARCS, ld_volatile_u64(&c->arcs));
+            st_relaxed_sys(dst + ROW_DEG, ld_volatile_u64(&c->deg));
+            st_relaxed_sys(dst + ROW_SENT, sent);
+            st_relaxed_sys(dst + ROW_OVERFLOW, ld_volatile_u64(&c->overflow));
+            if ((int)threadIdx.x != me) st_release_sys(&reinterpret_cast<Ctrl *>(a.peers.base[threadIdx.x])->flags[me], bar_epoch);
+        }
+        __syncthreads();                 // (CTA 0: its own row is written before its threads read it back)
+        loop_trace(&s->dyn, 24);
+        if (!small_wait_peers(a, bar_epoch)) break;
+        loop_trace(&s->dyn, 25);
+        if (threadIdx.x < 8) {
+            // own row from the local counters (final since the grid barrier; CTA 0's copy in the heap may still be in
+            // flight for the other CTAs), the peers' rows from the heap
+            unsigned long long t = 0;
+            if (threadIdx.x == ROW_NEXT) t = next_local;
+            else if (threadIdx.x == ROW_ARCS) t = ld_volatile_u64(&c->arcs);
+            else if (threadIdx.x == ROW_DEG) t = ld_volatile_u64(&c->deg);
+            else if (threadIdx.x == ROW_OVERFLOW) t = ld_volatile_u64(&c->overflow);
+            else if (threadIdx.x == ROW_SENT)
+                for (int q = 0; q < P; ++q)
+                    if (q != me) t += ld_volatile_u64(&c->send_cnt[q]);
+            for (int q = 0; q < P; ++q)
+                if (q != me) t += ld_relaxed_sys(&my_ctrl->stats[parity][q][threadIdx.x]);
+            s_sum[threadIdx.x] = t;
+        }
+        __syncthreads();
+        const long long found = (long long)s_sum[ROW_NEXT], arcs = (long long)s_sum[ROW_ARCS];
+        const long long next_deg = (long long)s_sum[ROW_DEG], sent_all = (long long)s_sum[ROW_SENT];
+        const bool overflow = s_sum[ROW_OVERFLOW] != 0ull;
+        __syncthreads();                 // s_sum is reused by the next level
+        // ---- the decision of p2p_stats_decide_kernel, in every CTA alike
+        if (lead && level < B200_MAX_LEVELS) {
+            P2PLevelRec *r = &a.res->level[level];
+            r->direction = 0;
+            r->exchange = 0;
+            r->frontier_len = flen;
+            r->arcs = arcs;
+            r->discovered = found;
+            r->sent = sent_all;
+        }
+        total_arcs += arcs;
+        launches += 1;
+        ++level;
+        ++stats_seq;
+        if (overflow) {
+            status = B200_ERR_OVERFLOW;
+            finished = true;
+            break;
+        }
+        if (found == 0) {
+            finished = true;
+            break;
+        }
+        reached += found;
+        m_unexplored -= arcs;
+        {
+            const int *t = in;
+            in = out;
+            out = const_cast<int *>(t);
+        }
+        len = (uint32_t)next_local;
+        const bool to_pull = mode == B200_BFS_BEAMER && (double)next_deg > (double)m_unexplored / alpha && found > flen;
+        flen = found;
+        if (to_pull) {
+            // the new frontier as this rank's bitmap slice (the first pull level gathers the slices), and the rows
+            // without in-arcs count as done from here on (engine.cuh): pull levels skip them
+            uint32_t *slice_w = reinterpret_cast<uint32_t *>(a.peers.base[me] + (bsel ? a.off_slice0 : a.off_slice1));
+            for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < a.wl; w += gridDim.x * blockDim.x) slice_w[w] = 0u;
+            or_no_in_arc_words(blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, a.pull_offsets, part.n_local, a.iso, a.done);
+            if (!small_grid_barrier(sh, &s_gen)) break;
+            for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
+                const uint32_t r = part.row((uint32_t)__ldcg(in + i));
+                atomicOr(slice_w + (r >> 5), 1u << (r & 31));
+            }
+            __threadfence_system();
+            if (!small_grid_barrier(sh, &s_gen)) break;
+            ++bar_epoch;
+            if (blockIdx.x == 0 && threadIdx.x < (unsigned)P && (int)threadIdx.x != me)
+                st_release_sys(&reinterpret_cast<Ctrl *>(a.peers.base[threadIdx.x])->flags[me], bar_epoch);
+            if (!small_wait_peers(a, bar_epoch)) break;
+            bsel ^= 1u;
+            next_run = LOOP_RUN_PULL;
+            break;
+        }
+        if (next_deg > small_arcs) {
+            next_run = LOOP_RUN_PUSH;    // a big level: scan + quad advance + bitmap absorb, in this same graph iteration
+            break;
+        }
+    }
+
+    // ---- hand the state back (CTA 0): to the kernels of this iteration, or to the host
+    const bool aborted = ld_relaxed_gpu_u32(&sh->abort) != 0u;
+    if (lead) {
+        for (int i = 0; i < SMALL_SLOTS; ++i)
+            for (int k = 0; k < B200_NUM_COUNTERS; ++k) a.pull_slots[i].c[k] = 0ull;
+        s->level = level;
+        s->m_unexplored = m_unexplored;
+        s->flen = flen;
+        s->reached = reached;
+        s->total_arcs = total_arcs;
+        s->bar_epoch = bar_epoch;
+        s->stats_seq = stats_seq;
+        s->launches = launches;
+        s->pull = next_run == LOOP_RUN_PULL ? 1 : 0;
+        s->dyn.in = in;
+        s->dyn.out = out;
+        s->dyn.len = len;
+        s->dyn.bsel = bsel;
+        s->dyn.next_label = level + 1;
+        if (aborted) {
+            s->timeout = 1u;             // the decide kernel of this iteration reports it and ends the loop
+        } else if (finished) {
+            a.res->status = status;
+            a.res->num_levels = level;
+            a.res->reached = reached;
+            a.res->total_arcs = total_arcs;
+            a.res->launches = launches;
+            a.res->bar_epoch = bar_epoch;
+            a.res->stats_seq = stats_seq;
+            __threadfence_system();
+            s->dyn.run = 0u;
+            cudaGraphSetConditional(a.h_while, 0u);
+        } else {
+            s->dyn.run = next_run;
+        }
     }
 }
 
-__global__ void __launch_bounds__(256) p2p_absorb_dyn_kernel(const int *__restrict__ inbox, size_t seg_stride,
-                                                             const unsigned long long *counts, int me, int P, uint32_t *known,
-                                                             int *labels, const LoopDyn *dyn, Partition part,
-                                                             unsigned long long capacity, unsigned long long *next_count,
-                                                             unsigned long long *counters, const uint32_t *__restrict__ offsets) {
+// ---------------------------------------------------------------------------------------------
+// Big push level, receiver side: the exchange IS the `known` bitmap.  After the level's advance
+// (BfsClaimPartQ: claim bits, emit nothing) and a flag barrier, every rank ORs ITS slice of every rank's
+// `known` (peer loads over NVLink: (P-1)/P * n/8 bytes, whatever the frontier size), and what is new against
+// `done` is labelled, appended to the next frontier (ascending ids) and written as the next frontier's
+// bitmap slice -- one pass, word-wise, with the look-back scan of tile_scan.cuh.  Replaces the routed flush
+// + publish + absorb + list -> slice of the vertex-id exchange, whose per-rank cost did not shrink with P.
+// ---------------------------------------------------------------------------------------------
+template <int NT, int VT>
+__global__ void __launch_bounds__(NT) p2p_absorb_bits_kernel(Peers peers, size_t off_known, int me, int P, uint32_t wl,
+                                                             uint32_t *__restrict__ done, uint32_t *slice0, uint32_t *slice1,
+                                                             int *__restrict__ labels, const uint32_t *__restrict__ offsets,
+                                                             Partition part, P2PLoopState *s, SmallShared *sh,
+                                                             unsigned long long capacity, unsigned long long *status,
+                                                             unsigned long long *counters) {
+    using TS = TileScan<NT, VT>;
+    __shared__ typename TS::Smem sm;
+    __shared__ uint32_t s_tile, s_bcast;
+    const LoopDyn *dyn = &s->dyn;
     loop_trace(dyn, 5);
     if (!(dyn->run & LOOP_RUN_PUSH)) return;
-    p2p_absorb_body(inbox, seg_stride, counts, me, P, known, labels, dyn->next_label, part, dyn->out, capacity, next_count,
-                    counters, offsets);
-}
-
-__global__ void p2p_list_to_slice_dyn_kernel(const LoopDyn *dyn, const unsigned long long *len_ptr, uint32_t *slice0,
-                                             uint32_t *slice1, Partition part) {
-    loop_trace(dyn, 6);
-    if (!(dyn->run & LOOP_RUN_PUSH)) return;
-    const int *__restrict__ list = dyn->out;
-    uint32_t *slice = dyn->bsel ? slice0 : slice1;
-    const unsigned long long len = *len_ptr;
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
-        const uint32_t r = part.row((uint32_t)list[i]);
-        atomicOr(slice + (r >> 5), 1u << (r & 31));
+    // ---- "my advance is done" to every peer; wait until theirs are (their claims are in their `known`)
+    const unsigned long long epoch = s->bar_epoch + 1ull;
+    if (P > 1) {
+        if (blockIdx.x == 0 && threadIdx.x < (unsigned)P && (int)threadIdx.x != me) {
+            __threadfence_system();
+            st_release_sys(&reinterpret_cast<Ctrl *>(peers.base[threadIdx.x])->flags[me], epoch);
+        }
+        if (threadIdx.x < (unsigned)P && (int)threadIdx.x != me) {
+            const unsigned long long *mine = &reinterpret_cast<const Ctrl *>(peers.base[me])->flags[threadIdx.x];
+            unsigned long long t0 = 0ull;
+            uint32_t polls = 0u;
+            while (ld_acquire_sys(mine) < epoch) {
+                if (spin_expired(polls, t0, P2P_TIMEOUT_NS)) {
+                    atomicExch(&sh->abort, 1u);
+                    break;
+                }
+                if ((polls & 63u) == 0u && ld_relaxed_gpu_u32(&sh->abort)) break;
+            }
+        }
+        __syncthreads();
+        if (ld_relaxed_gpu_u32(&sh->abort)) return;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) loop_trace(dyn, 13);
+    int *out = dyn->out;
+    uint32_t *slice_w = dyn->bsel ? slice0 : slice1;
+    const int next_label = dyn->next_label;
+    uint32_t *known_own = reinterpret_cast<uint32_t *>(peers.base[me] + off_known) + (size_t)me * wl;
+    unsigned int *tile_counter = &sh->absorb_tile;
+    LookbackState st;
+    st.status = status;
+    st.tile_counter = tile_counter;
+    st.epoch = (dyn->epoch + 1u) & 0x3FFFFFFFu;
+    st.num_tiles = (wl + TS::NV - 1) / TS::NV;
+    unsigned long long deg_sum = 0;
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= st.num_tiles) break;
+        const uint32_t base = tile * TS::NV + (threadIdx.x >> 5) * (32 * VT) + lane_id();
+        uint32_t word[VT], c[VT], ex[VT];
+#pragma unroll
+        for (int i = 0; i < VT; ++i) {
+            const uint32_t w = base + i * 32;
+            uint32_t acc = 0u;
+            if (w < wl) {
+                for (int q = 0; q < P; ++q)
+                    acc |= __ldcg(reinterpret_cast<const uint32_t *>(peers.base[q] + off_known) + (size_t)me * wl + w);
+                const uint32_t d = done[w];
+                word[i] = acc & ~d;
+                if (word[i]) done[w] = d | word[i];
+                known_own[w] = acc;
+                slice_w[w] = word[i];
+            } else {
+                word[i] = 0u;
+            }
+            c[i] = __popc(word[i]);
+        }
+        const uint32_t total = TS::run(c, ex, sm);
+        const uint32_t excl = lookback_exclusive(st, tile, total, &s_bcast);
+        bool over = false;
+#pragma unroll
+        for (int i = 0; i < VT; ++i) {
+            uint32_t bits = word[i];
+            unsigned long long dest = (unsigned long long)excl + ex[i];
+            const uint32_t r0 = (base + i * 32) << 5;
+            while (bits) {
+                const uint32_t b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const uint32_t r = r0 + b;
+                labels[r] = next_label;
+                deg_sum += __ldg(offsets + r + 1) - __ldg(offsets + r);
+                if (dest < capacity) out[dest] = (int)part.global_id((uint32_t)me, r);
+                else over = true;
+                ++dest;
+            }
+        }
+        if (over) counters[B200_CNT_OVERFLOW] = 1ull;
+        if (tile == st.num_tiles - 1 && threadIdx.x == 0) counters[B200_CNT_OUT] = (unsigned long long)excl + total;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int d2 = 16; d2 > 0; d2 >>= 1) deg_sum += __shfl_xor_sync(FULL_MASK, deg_sum, d2);
+    if (lane_id() == 0 && deg_sum) atomicAdd(&counters[B200_CNT_AUX], deg_sum);
 }
 
 __global__ void __launch_bounds__(256) p2p_gather_or_dyn_kernel(Peers peers, size_t off_slice0, size_t off_slice1,
-                                                                uint32_t quads_per_slice, int P, const LoopDyn *dyn,
+                                                                uint32_t quads_per_slice, int P, int me, const LoopDyn *dyn,
                                                                 uint32_t run_bit, uint4 *__restrict__ full,
-                                                                uint4 *__restrict__ known) {
+                                                                uint4 *__restrict__ known, uint32_t *done,
+                                                                const uint32_t *__restrict__ iso,
+                                                                const uint32_t *__restrict__ pull_offsets) {
     loop_trace(dyn, run_bit == LOOP_RUN_PULL ? 7 : 10);
     if (!(dyn->run & run_bit)) return;
+    if (run_bit == LOOP_RUN_PULL && (dyn->run & LOOP_RUN_TO_PULL)) {
+        // first pull level after a big push level: rows without in-arcs count as done from here on (engine.cuh)
+        or_no_in_arc_words(blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, pull_offsets, quads_per_slice * 128u, iso, done);
+    }
     const size_t slice_off = dyn->bsel ? off_slice1 : off_slice0;
     const size_t total = (size_t)quads_per_slice * (size_t)P;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -423,42 +968,247 @@ __global__ void __launch_bounds__(256) p2p_gather_or_dyn_kernel(Peers peers, siz
             known[i] = k;
         }
     }
+    (void)me;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT, B200_PULL_MINB) p2p_pull_dyn_kernel(uint32_t n_local, const uint32_t *__restrict__ offsets,
-                                                          const int *__restrict__ indices, const uint32_t *__restrict__ full,
-                                                          uint32_t *slice0, uint32_t *slice1, uint32_t *__restrict__ known_slice,
-                                                          int *__restrict__ labels, const LoopDyn *dyn,
-                                                          unsigned long long *counters, Partition part,
-                                                          const int *__restrict__ first_nbr) {
-    loop_trace(dyn, 8);
-    if (!(dyn->run & LOOP_RUN_PULL)) return;
-    bfs_pull_body<NT>(n_local, offsets, indices, full, dyn->bsel ? slice0 : slice1, known_slice, labels, dyn->next_label,
-                      counters, part, first_nbr);
+// ---------------------------------------------------------------------------------------------
+// The pull phase of a direction-optimising traversal in ONE launch (the levels between the push -> pull switch and
+// the hand-over back to push).  As kernels of the flat graph body a pull level cost ~40 us on top of its work at
+// 2 GPUs (round-2 trace: four idle push nodes, the WHILE iteration, two idle hand-over nodes, a flag barrier with
+// its kernel boundary, the decide kernel) -- three pull levels of a scale-26 traversal at 8 GPUs are 12 / 8 / 7 us
+// of pull work each.  Per level here: gather + OR of every rank's frontier slice (peer loads: the allgather), grid
+// barrier, early-exit pull over the local rows (bfs_pull_body, bitmaps read through L2), grid barrier, stats row +
+// flag to every peer, wait, and the same decision in every CTA.  The level-closing flag barrier is the only
+// cross-GPU synchronisation of a pull level: it also tells the peers that this rank's new slice is complete.
+// ---------------------------------------------------------------------------------------------
+constexpr int PULL_NT = 256;
+struct PullArgs {
+    Peers peers;
+    int me, P;
+    Partition part;
+    const uint32_t *pull_offsets;
+    const int *pull_indices, *first_nbr;
+    uint32_t *known, *full, *done;
+    int *labels;
+    size_t off_slice0, off_slice1;
+    uint32_t wl;
+    const uint32_t *iso;
+    P2PLoopState *s;
+    SmallShared *sh;
+    PullCounters *slots;          // [SMALL_SLOTS], one per level (level & 3)
+    unsigned int *tile_counters;  // workspace tile counters: [1] is re-armed for the hand-over compaction that follows
+    P2PLoopResult *res;
+    cudaGraphConditionalHandle h_while;
+};
+
+__global__ void __launch_bounds__(PULL_NT, 4) p2p_pull_levels_kernel(PullArgs a) {
+    __shared__ unsigned s_gen;
+    __shared__ unsigned long long s_sum[8];
+    P2PLoopState *s = a.s;
+    loop_trace(&s->dyn, 30);
+    if (!(s->dyn.run & LOOP_RUN_PULL)) return;
+    SmallShared *sh = a.sh;
+    if (ld_relaxed_gpu_u32(&sh->abort)) return;
+    const int me = a.me, P = a.P;
+    const Partition part = a.part;
+    const Ctrl *my_ctrl = reinterpret_cast<const Ctrl *>(a.peers.base[me]);
+    const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+    if (threadIdx.x == 0) s_gen = ld_relaxed_gpu_u32(&sh->bar_gen);
+    uint32_t *slice[2] = {reinterpret_cast<uint32_t *>(a.peers.base[me] + a.off_slice0),
+                          reinterpret_cast<uint32_t *>(a.peers.base[me] + a.off_slice1)};
+
+    int level = s->level;
+    const int mode = s->mode;
+    const float beta = s->beta;
+    const long long n = s->n, small_verts = s->small_verts;
+    const uint32_t small_on = s->small_on;
+    long long flen = s->flen, reached = s->reached, total_arcs = s->total_arcs, launches = s->launches;
+    unsigned long long bar_epoch = s->bar_epoch;
+    uint32_t stats_seq = s->stats_seq, bsel = s->dyn.bsel;
+    int status = B200_OK;
+    uint32_t next_run = 0u;
+    unsigned long long next_local = 0ull;
+    bool finished = false;
+    // first pull level after a big push level: rows without in-arcs count as done from here on (engine.cuh); the grid
+    // barrier after the gather orders this before the first read of `done`
+    if (s->dyn.run & LOOP_RUN_TO_PULL)
+        or_no_in_arc_words(blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, a.pull_offsets, part.n_local, a.iso, a.done);
+    __syncthreads();
+
+    for (;;) {
+        PullCounters *c = &a.slots[level & (SMALL_SLOTS - 1)];
+        if (lead) {
+            PullCounters *z = &a.slots[(level + 1) & (SMALL_SLOTS - 1)];
+            for (int i = 0; i < B200_NUM_COUNTERS; ++i) z->c[i] = 0ull;
+        }
+        // ---- the allgather: every rank's slice of the frontier -> full; folded into known
+        loop_trace(&s->dyn, 31);
+        {
+            const size_t slice_off = bsel ? a.off_slice1 : a.off_slice0;
+            const uint32_t qps = a.wl / 4;
+            const size_t total = (size_t)qps * (size_t)P, stride = (size_t)gridDim.x * blockDim.x;
+            uint4 *full4 = reinterpret_cast<uint4 *>(a.full), *known4 = reinterpret_cast<uint4 *>(a.known);
+            for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+                const uint32_t p = (uint32_t)(i / qps);
+                const uint32_t j = (uint32_t)(i - (size_t)p * qps);
+                const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(a.peers.base[p] + slice_off) + j);
+                full4[i] = v;
+                if (v.x | v.y | v.z | v.w) {
+                    uint4 k = __ldcg(known4 + i);
+                    k.x |= v.x; k.y |= v.y; k.z |= v.z; k.w |= v.w;
+                    known4[i] = k;
+                }
+            }
+        }
+        if (!small_grid_barrier(sh, &s_gen)) break;
+        loop_trace(&s->dyn, 32);
+        bfs_pull_body<PULL_NT, true>(part.n_local, a.pull_offsets, a.pull_indices, a.full, slice[bsel ^ 1u], a.done, a.labels, level + 1,
+                                     c->c, part, a.first_nbr);
+        __threadfence_system();          // the new slice, before the flag that tells the peers it is complete
+        if (!small_grid_barrier(sh, &s_gen)) break;
+        // ---- level summary: row to every peer, flags, sums
+        next_local = ld_volatile_u64(&c->c[B200_CNT_OUT]);
+        const int parity = (int)(stats_seq & 1u);
+        ++bar_epoch;
+        if (blockIdx.x == 0 && threadIdx.x < (unsigned)P && (int)threadIdx.x != me) {
+            Ctrl *pc = reinterpret_cast<Ctrl *>(a.peers.base[threadIdx.x]);
+            unsigned long long *dst = pc->stats[parity][me];
+            st_relaxed_sys(dst + ROW_NEXT, next_local);
+            st_relaxed_sys(dst + ROW_ARCS, ld_volatile_u64(&c->c[B200_CNT_ARCS]));
+            st_relaxed_sys(dst + ROW_DEG, ld_volatile_u64(&c->c[B200_CNT_AUX]));
+            st_relaxed_sys(dst + ROW_SENT, 0ull);
+            st_relaxed_sys(dst + ROW_OVERFLOW, 0ull);
+            st_release_sys(&pc->flags[me], bar_epoch);
+        }
+        loop_trace(&s->dyn, 33);
+        {   // wait for every peer's flag (local polling)
+            if (threadIdx.x < (unsigned)P && (int)threadIdx.x != me) {
+                const unsigned long long *mine = &my_ctrl->flags[threadIdx.x];
+                unsigned long long t0 = 0ull;
+                uint32_t polls = 0u;
+                while (ld_acquire_sys(mine) < bar_epoch) {
+                    if (spin_expired(polls, t0, P2P_TIMEOUT_NS)) {
+                        atomicExch(&sh->abort, 1u);
+                        break;
+                    }
+                    if ((polls & 63u) == 0u && ld_relaxed_gpu_u32(&sh->abort)) break;
+                }
+            }
+            __syncthreads();
+            if (ld_relaxed_gpu_u32(&sh->abort)) break;
+        }
+        loop_trace(&s->dyn, 34);
+        if (threadIdx.x < 8) {
+            unsigned long long t = 0;
+            if (threadIdx.x == ROW_NEXT) t = next_local;
+            else if (threadIdx.x == ROW_ARCS) t = ld_volatile_u64(&c->c[B200_CNT_ARCS]);
+            else if (threadIdx.x == ROW_DEG) t = ld_volatile_u64(&c->c[B200_CNT_AUX]);
+            for (int q = 0; q < P; ++q)
+                if (q != me) t += ld_relaxed_sys(&my_ctrl->stats[parity][q][threadIdx.x]);
+            s_sum[threadIdx.x] = t;
+        }
+        __syncthreads();
+        const long long found = (long long)s_sum[ROW_NEXT], arcs = (long long)s_sum[ROW_ARCS];
+        __syncthreads();
+        if (lead && level < B200_MAX_LEVELS) {
+            P2PLevelRec *r = &a.res->level[level];
+            r->direction = 1;
+            r->exchange = 1;
+            r->frontier_len = flen;
+            r->arcs = arcs;
+            r->discovered = found;
+            r->sent = 0;
+        }
+        total_arcs += arcs;
+        launches += 1;
+        ++level;
+        ++stats_seq;
+        if (found == 0) {
+            finished = true;
+            break;
+        }
+        reached += found;
+        bsel ^= 1u;
+        const bool hand_over = mode == B200_BFS_BEAMER && (double)found < (double)n / beta && found < flen;
+        flen = found;
+        if (hand_over) {
+            // back to push: the hand-over kernels of this graph iteration fold the last discoveries into `known`
+            // and turn this rank's slice into its frontier list
+            next_run = LOOP_RUN_TO_PUSH | ((small_on && found <= small_verts) ? LOOP_RUN_SMALL : LOOP_RUN_PUSH);
+            break;
+        }
+    }
+
+    const bool aborted = ld_relaxed_gpu_u32(&sh->abort) != 0u;
+    if (lead) {
+        for (int i = 0; i < SMALL_SLOTS; ++i) small_zero_slot(&sh->slot[i]);   // the small-level kernel may run next
+        a.tile_counters[1] = 0u;
+        s->level = level;
+        s->flen = flen;
+        s->reached = reached;
+        s->total_arcs = total_arcs;
+        s->bar_epoch = bar_epoch;
+        s->stats_seq = stats_seq;
+        s->launches = launches;
+        s->pull = 0;
+        s->dyn.bsel = bsel;
+        s->dyn.next_label = level + 1;
+        s->dyn.len = (uint32_t)next_local;
+        s->dyn.epoch = (s->dyn.epoch + 2u) & 0x3FFFFFFFu;   // the hand-over compaction gets a look-back tag nobody used
+        if (aborted) {
+            s->timeout = 1u;             // the decide kernel of the next iteration reports it and ends the loop
+        } else if (finished) {
+            a.res->status = status;
+            a.res->num_levels = level;
+            a.res->reached = reached;
+            a.res->total_arcs = total_arcs;
+            a.res->launches = launches;
+            a.res->bar_epoch = bar_epoch;
+            a.res->stats_seq = stats_seq;
+            __threadfence_system();
+            s->dyn.run = 0u;
+            cudaGraphSetConditional(a.h_while, 0u);
+        } else {
+            s->dyn.run = next_run;
+        }
+    }
 }
 
-// Level summary (as p2p_stats_kernel) + the host loop's decision, on every rank identically.
+// Level summary of a big push / pull level (this rank's row into every heap, flag barrier, sum of the rows = the
+// allreduce) + the host loop's decision, on every rank identically.
 __global__ void __launch_bounds__(32) p2p_stats_decide_kernel(Peers peers, int me, int P, P2PLoopState *s,
-                                                              unsigned long long *counters, unsigned long long *box_counts,
-                                                              unsigned int *tile_counters, P2PLoopResult *res,
+                                                              unsigned long long *counters, unsigned int *tile_counters,
+                                                              SmallShared *sh, PullCounters *pull_slots, P2PLoopResult *res,
                                                               cudaGraphConditionalHandle h_while) {
     const int p = (int)lane_id();
     loop_trace(&s->dyn, 9);
-    const bool was_pull = s->pull != 0;
-    const unsigned long long epoch = s->bar_epoch + 1ull;
+    const uint32_t run = s->dyn.run;
+    const bool aborted = ld_relaxed_gpu_u32(&sh->abort) != 0u || s->timeout != 0u;
+    if (!(run & LOOP_RUN_PUSH) || aborted) {
+        // the small-level and the pull-levels kernels close their levels themselves; only a time-out is left to report
+        if (aborted && p == 0) {
+            res->status = B200_ERR_TIMEOUT;
+            res->num_levels = s->level;
+            res->reached = s->reached;
+            res->total_arcs = s->total_arcs;
+            res->launches = s->launches;
+            res->bar_epoch = s->bar_epoch;
+            res->stats_seq = s->stats_seq;
+            __threadfence_system();
+            s->dyn.run = 0u;
+            cudaGraphSetConditional(h_while, 0u);
+        }
+        return;
+    }
+    const bool was_pull = false;   // (pull levels: p2p_pull_levels_kernel)
+    // a big push level used one epoch for its "advance done" barrier (p2p_absorb_bits_kernel)
+    const unsigned long long epoch = s->bar_epoch + ((!was_pull && P > 1) ? 2ull : 1ull);
     const int parity = (int)(s->stats_seq & 1u);
     __syncwarp();
     unsigned long long row[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) row[k] = 0;
-    if (!was_pull) {
-        row[ROW_NEXT] = box_counts[me];
-        for (int q = 0; q < P; ++q)
-            if (q != me) row[ROW_SENT] += box_counts[q];
-    } else {
-        row[ROW_NEXT] = counters[B200_CNT_OUT];
-    }
+    row[ROW_NEXT] = counters[B200_CNT_OUT];
     row[ROW_ARCS] = counters[B200_CNT_ARCS];
     row[ROW_DEG] = counters[B200_CNT_AUX];
     row[ROW_OVERFLOW] = counters[B200_CNT_OVERFLOW];
@@ -477,8 +1227,12 @@ __global__ void __launch_bounds__(32) p2p_stats_decide_kernel(Peers peers, int m
     const long long found = (long long)__shfl_sync(FULL_MASK, mysum, ROW_NEXT);
     const long long arcs = (long long)__shfl_sync(FULL_MASK, mysum, ROW_ARCS);
     const long long next_deg = (long long)__shfl_sync(FULL_MASK, mysum, ROW_DEG);
-    const long long sent = (long long)__shfl_sync(FULL_MASK, mysum, ROW_SENT);
     const bool overflow = __shfl_sync(FULL_MASK, mysum, ROW_OVERFLOW) != 0ull;
+    // re-arm the small-level kernel's counter slots (it may run in the next iteration)
+    for (int i = p; i < SMALL_SLOTS; i += 32) {
+        small_zero_slot(&sh->slot[i]);
+        for (int k = 0; k < B200_NUM_COUNTERS; ++k) pull_slots[i].c[k] = 0ull;
+    }
     if (p != 0) return;
 
     const long long next_local = (long long)row[ROW_NEXT];
@@ -487,10 +1241,11 @@ __global__ void __launch_bounds__(32) p2p_stats_decide_kernel(Peers peers, int m
     if (level < B200_MAX_LEVELS) {
         P2PLevelRec *r = &res->level[level];
         r->direction = was_pull ? 1 : 0;
+        r->exchange = 1;
         r->frontier_len = s->flen;
         r->arcs = arcs;
         r->discovered = found;
-        r->sent = sent;
+        r->sent = 0;
     }
     s->total_arcs += arcs;
     s->launches += s->kernels_per_level;
@@ -501,7 +1256,8 @@ __global__ void __launch_bounds__(32) p2p_stats_decide_kernel(Peers peers, int m
     bool done = false;
     uint32_t trans = 0u;
     int status = B200_OK;
-    if (!ok || s->timeout) {
+    bool next_small = false;
+    if (!ok) {
         status = B200_ERR_TIMEOUT;
         done = true;
     } else if (overflow) {
@@ -520,7 +1276,10 @@ __global__ void __launch_bounds__(32) p2p_stats_decide_kernel(Peers peers, int m
             s->dyn.len = (uint32_t)next_local;
             if (s->mode == B200_BFS_BEAMER && (double)next_deg > (double)s->m_unexplored / s->alpha && found > flen) {
                 pull = true;
-                s->dyn.bsel ^= 1u;   // the slice written this level is the frontier of the first pull level
+                trans = LOOP_RUN_TO_PULL;   // (the gather of the first pull level also applies the no-in-arc preset)
+                s->dyn.bsel ^= 1u;          // the slice written this level is the frontier of the first pull level
+            } else {
+                next_small = s->small_on && next_deg <= s->small_arcs;
             }
         } else {
             s->dyn.bsel ^= 1u;
@@ -530,6 +1289,7 @@ __global__ void __launch_bounds__(32) p2p_stats_decide_kernel(Peers peers, int m
                 trans = LOOP_RUN_TO_PUSH;
                 s->dyn.len = (uint32_t)next_local;
                 pull = false;
+                next_small = s->small_on && found <= s->small_verts;   // (pull levels do not sum the degrees of what they find)
             }
         }
         s->flen = found;
@@ -538,9 +1298,9 @@ __global__ void __launch_bounds__(32) p2p_stats_decide_kernel(Peers peers, int m
     s->dyn.next_label = level + 1;
     s->dyn.epoch = (s->dyn.epoch + 2u) & 0x3FFFFFFFu;
     for (int i = 0; i < B200_NUM_COUNTERS; ++i) counters[i] = 0ull;
-    for (int i = 0; i < P2P_MAX; ++i) box_counts[i] = 0ull;
     tile_counters[0] = 0u;
     tile_counters[1] = 0u;
+    sh->absorb_tile = 0u;
     if (done) {
         res->status = status;
         res->num_levels = level;
@@ -551,7 +1311,7 @@ __global__ void __launch_bounds__(32) p2p_stats_decide_kernel(Peers peers, int m
         res->stats_seq = s->stats_seq;
         __threadfence_system();
     }
-    s->dyn.run = done ? 0u : ((pull ? LOOP_RUN_PULL : LOOP_RUN_PUSH) | trans);
+    s->dyn.run = done ? 0u : ((pull ? LOOP_RUN_PULL : (next_small ? LOOP_RUN_SMALL : LOOP_RUN_PUSH)) | trans);
     cudaGraphSetConditional(h_while, done ? 0u : 1u);
 }
 
@@ -578,16 +1338,14 @@ cudaError_t preload_kernels() {
     if ((e = preload(scan_sizes_kernel<SCAN_NT, SCAN_VT, FrontierDegree>)) != cudaSuccess) return e;
     if ((e = preload(bitmap_list_kernel<COMPACT_NT, BITLIST_VT, BitmapWords, PartItem>)) != cudaSuccess) return e;
     if ((e = preload(quad_advance_kernel<BfsPushPartQ, OUT_ROUTED, true, QUAD_NT, VT, QUAD_WSEG>)) != cudaSuccess) return e;
-    if ((e = preload(quad_advance_kernel<BfsPushPartQDyn, OUT_ROUTED, true, QUAD_NT, VT, QUAD_WSEG>)) != cudaSuccess) return e;
     if ((e = preload(scan_sizes_dyn_kernel<SCAN_NT, SCAN_VT, FrontierQuadsDynPart>)) != cudaSuccess) return e;
     if ((e = preload(bitmap_list_dyn_kernel<COMPACT_NT, BITLIST_VT, BitmapWordsDyn, PartItem>)) != cudaSuccess) return e;
     if ((e = preload(p2p_loop_init_kernel)) != cudaSuccess) return e;
-    if ((e = preload(p2p_clear_slice_dyn_kernel)) != cudaSuccess) return e;
-    if ((e = preload(p2p_publish_counts_dyn_kernel)) != cudaSuccess) return e;
-    if ((e = preload(p2p_absorb_dyn_kernel)) != cudaSuccess) return e;
-    if ((e = preload(p2p_list_to_slice_dyn_kernel)) != cudaSuccess) return e;
+    if ((e = preload(p2p_small_levels_kernel)) != cudaSuccess) return e;
+    if ((e = preload(p2p_pull_levels_kernel)) != cudaSuccess) return e;
+    if ((e = preload(p2p_absorb_bits_kernel<COMPACT_NT, BITLIST_VT>)) != cudaSuccess) return e;
+    if ((e = preload(quad_advance_kernel<BfsClaimPartQ, OUT_NONE, false, QUAD_NT, VT, QUAD_WSEG>)) != cudaSuccess) return e;
     if ((e = preload(p2p_gather_or_dyn_kernel)) != cudaSuccess) return e;
-    if ((e = preload(p2p_pull_dyn_kernel<256>)) != cudaSuccess) return e;
     if ((e = preload(p2p_stats_decide_kernel)) != cudaSuccess) return e;
     if ((e = preload(lbs_advance_kernel<BfsPushPartOp, OUT_ROUTED, true, LBS_NT, LBS_VT, LBS_SEG_T>)) != cudaSuccess) return e;
     return cudaSuccess;
@@ -602,11 +1360,19 @@ struct b200_p2p_bfs {
     int64_t n_global, n_local;
     uint32_t wl;                       // words per bitmap slice
     unsigned char *heap;
-    size_t heap_bytes, off_slice[2], off_inbox;
+    size_t heap_bytes, off_slice[2], off_known, off_inbox;
     bool connected;
     Peers peers;
     void *opened[P2P_MAX];             // cudaIpcOpenMemHandle results (closed in destroy)
-    uint32_t *known, *full;            // [n_global/32] each, local
+    uint32_t *known, *full;            // [n_global/32] each; known lives in the heap (peers read their slices of it), full is local
+    uint32_t *done;                    // [n_local/32] labelled set of the owned vertices (graph-driven loop)
+    SmallShared *small;                // counters + grid barrier of the small-level kernel
+    uint32_t *big_rows;                // [n_local] long rows of a small level
+    int small_grid;                    // CTAs of the small-level kernel (all resident)
+    PullCounters *pull_slots;          // [SMALL_SLOTS] per-level counters of the pull-levels kernel
+    int pull_grid;                     // CTAs of the pull-levels kernel (all resident)
+    unsigned long long *absorb_status; // look-back tile states of p2p_absorb_bits_kernel (its own array: the scan and the
+    int64_t absorb_tiles;              // hand-over compaction share the workspace's, with tags of their own)
     unsigned long long *box_counts;    // [P2P_MAX] device counters of the routed boxes
     unsigned long long *h_res, *d_res; // mapped pinned result block
     unsigned long long epoch;
@@ -622,7 +1388,7 @@ struct b200_p2p_bfs {
     cudaGraph_t graph;
     cudaGraphExec_t exec;
     unsigned long long *d_trace;
-    const void *k_offsets, *k_indices, *k_labels, *k_scratch, *k_iso, *k_first;
+    const void *k_offsets, *k_indices, *k_labels, *k_scratch, *k_iso, *k_first, *k_pull_offsets, *k_pull_indices;
     uint64_t k_gen;            // b200_ctx::scratch_gen the graph was built against
     int k_mode;
     int graph_failed;
@@ -636,6 +1402,7 @@ void p2p_drop_graph(b200_p2p_bfs *s) {
     s->exec = nullptr;
     s->graph = nullptr;
     s->k_offsets = s->k_indices = s->k_labels = s->k_scratch = s->k_iso = s->k_first = nullptr;
+    s->k_pull_offsets = s->k_pull_indices = nullptr;
 }
 
 int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int mode) {
@@ -646,8 +1413,6 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
     const bool beamer = mode == B200_BFS_BEAMER;
     const uint32_t *pull_off = g->col_offsets ? g->col_offsets : g->row_offsets;
     const int32_t *pull_idx = g->row_indices ? g->row_indices : g->col_indices;
-    Ctrl *my_ctrl = reinterpret_cast<Ctrl *>(s->heap);
-    int *my_inbox = reinterpret_cast<int *>(s->heap + s->off_inbox);
     uint32_t *slice0 = reinterpret_cast<uint32_t *>(s->heap + s->off_slice[0]);
     uint32_t *slice1 = reinterpret_cast<uint32_t *>(s->heap + s->off_slice[1]);
     cudaStream_t cs = s->cap_stream;
@@ -661,7 +1426,7 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
     size_t ndeps = 0;
     cudaGraphNodeParams np_w = {};
     const LoopDyn *dyn = &s->d_lstate->dyn;
-    const int kernels_per_level = 2 + (P > 1 ? 2 : 0) + (beamer ? 6 : 0) + 1;
+    const int kernels_per_level = 4 + (beamer ? 4 : 0);
 
     p2p_drop_graph(s);
     ws->stream = (void *)cs;
@@ -673,16 +1438,10 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
     capturing = true;
     LL_CUDA(cudaMemsetAsync(d_labels, 0xFF, sizeof(int32_t) * (size_t)s->n_local, cs));
     LL_CUDA(cudaMemsetAsync(s->known, 0, (size_t)(s->n_global / 8), cs));
-    if (beamer) {   // own rows without in-arcs start "known": pull levels skip them (engine.cuh)
-        uint32_t *own = s->known + (size_t)me * s->wl;
-        if (g->no_in_arc_bitmap)
-            LL_CUDA(cudaMemcpyAsync(own, g->no_in_arc_bitmap, sizeof(uint32_t) * (size_t)s->wl, cudaMemcpyDeviceToDevice, cs));
-        else
-            LL_CUDA(launch_no_in_arc_bitmap(ws, pull_off, s->n_local, own));
-    }
-    p2p_loop_init_kernel<<<1, 1, 0, cs>>>(s->d_lparams, s->d_lstate, d_labels, s->known, ctx->frontier[0], ctx->frontier[1],
-                                          (long long)s->n_global, part, ws->d_counters, ws->d_tile_counter, s->box_counts,
-                                          kernels_per_level);
+    LL_CUDA(cudaMemsetAsync(s->done, 0, sizeof(uint32_t) * (size_t)s->wl, cs));
+    p2p_loop_init_kernel<<<1, 1, 0, cs>>>(s->d_lparams, s->d_lstate, d_labels, s->known, s->done, ctx->frontier[0], ctx->frontier[1],
+                                          (long long)s->n_global, part, ws->d_counters, ws->d_tile_counter, s->small,
+                                          s->pull_slots, kernels_per_level);
     LL_CUDA(cudaGetLastError());
     capturing = false;
     if ((st = end_capture(cs, deps, &ndeps, 8)) != B200_OK) goto fail;
@@ -694,16 +1453,38 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
     LL_CUDA(cudaGraphAddNode(&n_while, G, deps, ndeps, &np_w));
     body = np_w.conditional.phGraph_out[0];
 
-    // ---- the flat body of one level
+    // ---- the flat body of one graph iteration: every kernel returns at once unless its LOOP_RUN_* bit is set
     LL_CUDA(cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
     capturing = true;
     {
-        // push level
-        if (beamer) {
-            p2p_clear_slice_dyn_kernel<<<ws->num_sms, 256, 0, cs>>>(dyn, reinterpret_cast<uint4 *>(slice0),
-                                                                     reinterpret_cast<uint4 *>(slice1), s->wl / 4);
-            LL_CUDA(cudaGetLastError());
-        }
+        // (1) consecutive SMALL push levels in one persistent kernel (vertex ids through the inboxes)
+        SmallArgs sa;
+        std::memset(&sa, 0, sizeof sa);
+        sa.peers = s->peers;
+        sa.me = me;
+        sa.P = P;
+        sa.part = part;
+        sa.offsets = g->row_offsets;
+        sa.indices = g->col_indices;
+        sa.known = s->known;
+        sa.done = s->done;
+        sa.labels = d_labels;
+        sa.s = s->d_lstate;
+        sa.sh = s->small;
+        sa.big = s->big_rows;
+        sa.off_inbox = s->off_inbox;
+        sa.off_slice0 = s->off_slice[0];
+        sa.off_slice1 = s->off_slice[1];
+        sa.wl = s->wl;
+        sa.iso = g->no_in_arc_bitmap;
+        sa.pull_offsets = pull_off;
+        sa.res = s->d_lresult;
+        sa.h_while = h_while;
+        sa.pull_slots = s->pull_slots;
+        p2p_small_levels_kernel<<<(unsigned)s->small_grid, SMALL_NT, 0, cs>>>(sa);
+        LL_CUDA(cudaGetLastError());
+
+        // (2) a BIG push level: quad scan, quad advance that only claims bits in `known`, then the bitmap exchange
         const int64_t max_tiles = (s->n_local + SCAN_NT * SCAN_VT - 1) / (SCAN_NT * SCAN_VT);
         int64_t grid = (int64_t)ws->num_sms * 8;
         if (grid > max_tiles) grid = max_tiles;
@@ -711,50 +1492,55 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
         scan_sizes_dyn_kernel<SCAN_NT, SCAN_VT><<<(unsigned)grid, SCAN_NT, 0, cs>>>(
             fn, dyn, (uint32_t)LOOP_RUN_PUSH, ws->d_scanned, ws->d_status, ws->d_tile_counter, ws->d_counters + B200_CNT_TOTAL);
         LL_CUDA(cudaGetLastError());
-        RoutedOut r;
-        std::memset(&r, 0, sizeof r);
-        r.num_dest = P;
-        r.count = s->box_counts;
-        r.self = me;
-        for (int p = 0; p < P; ++p) {
-            r.box[p] = p == me ? ctx->frontier[1]
-                               : reinterpret_cast<int *>(s->peers.base[p] + s->off_inbox) + (size_t)me * (size_t)s->n_local;
-            r.capacity[p] = (unsigned long long)s->n_local;
-        }
         QuadArgs a = make_quad_args(ws, ctx->frontier[0], 0u, g->row_offsets, g->col_indices, nullptr, part.log_p);
         a.dyn = dyn;
-        BfsPushPartQDyn op{{s->known, d_labels, 0, part}, dyn};
-        LL_CUDA((launch_quad_advance<OUT_ROUTED, true>(ws, a, op, nullptr, 0ull, &r)));
-        if (P > 1) {
-            p2p_publish_counts_dyn_kernel<<<1, 32, 0, cs>>>(s->peers, me, P, s->d_lstate, s->box_counts);
-            LL_CUDA(cudaGetLastError());
-            p2p_absorb_dyn_kernel<<<ws->num_sms * 2, 256, 0, cs>>>(my_inbox, (size_t)s->n_local, my_ctrl->counts, me, P, s->known,
-                                                                   d_labels, dyn, part, (unsigned long long)s->n_local,
-                                                                   s->box_counts + me, ws->d_counters, g->row_offsets);
-            LL_CUDA(cudaGetLastError());
-        }
-        if (beamer) {
-            p2p_list_to_slice_dyn_kernel<<<ws->num_sms, 256, 0, cs>>>(dyn, s->box_counts + me, slice0, slice1, part);
-            LL_CUDA(cudaGetLastError());
-            // pull level
-            p2p_gather_or_dyn_kernel<<<ws->num_sms * 4, 256, 0, cs>>>(s->peers, s->off_slice[0], s->off_slice[1], s->wl / 4, P, dyn,
-                                                                      (uint32_t)LOOP_RUN_PULL, reinterpret_cast<uint4 *>(s->full),
-                                                                      reinterpret_cast<uint4 *>(s->known));
-            LL_CUDA(cudaGetLastError());
-            p2p_pull_dyn_kernel<256><<<ws->num_sms * 8, 256, 0, cs>>>((uint32_t)s->n_local, pull_off, pull_idx, s->full, slice0, slice1,
-                                                                      s->known + (size_t)me * s->wl, d_labels, dyn, ws->d_counters, part,
-                                                                      g->first_in_neighbor);
-            LL_CUDA(cudaGetLastError());
-        }
-        // level summary across the ranks + decision
-        p2p_stats_decide_kernel<<<1, 32, 0, cs>>>(s->peers, me, P, s->d_lstate, ws->d_counters, s->box_counts, ws->d_tile_counter,
-                                                  s->d_lresult, h_while);
+        BfsClaimPartQ op{s->known, part};
+        LL_CUDA((launch_quad_advance<OUT_NONE, false>(ws, a, op, nullptr, 0ull)));
+        const int64_t atiles = ((int64_t)s->wl + COMPACT_NT * BITLIST_VT - 1) / (COMPACT_NT * BITLIST_VT);
+        int64_t agrid = (int64_t)ws->num_sms * 8;
+        if (agrid > atiles) agrid = atiles;
+        p2p_absorb_bits_kernel<COMPACT_NT, BITLIST_VT><<<(unsigned)agrid, COMPACT_NT, 0, cs>>>(
+            s->peers, s->off_known, me, P, s->wl, s->done, slice0, slice1, d_labels, g->row_offsets, part, s->d_lstate, s->small,
+            (unsigned long long)s->n_local, s->absorb_status, ws->d_counters);
+        LL_CUDA(cudaGetLastError());
+        // (3) level summary across the ranks + decision of a big push level
+        p2p_stats_decide_kernel<<<1, 32, 0, cs>>>(s->peers, me, P, s->d_lstate, ws->d_counters, ws->d_tile_counter, s->small,
+                                                  s->pull_slots, s->d_lresult, h_while);
         LL_CUDA(cudaGetLastError());
         if (beamer) {
-            // pull -> push hand-over
-            p2p_gather_or_dyn_kernel<<<ws->num_sms * 4, 256, 0, cs>>>(s->peers, s->off_slice[0], s->off_slice[1], s->wl / 4, P, dyn,
+            // (4) the whole pull phase in one persistent kernel (after the push -> pull switch of (1) or (3))
+            PullArgs pa;
+            std::memset(&pa, 0, sizeof pa);
+            pa.peers = s->peers;
+            pa.me = me;
+            pa.P = P;
+            pa.part = part;
+            pa.pull_offsets = pull_off;
+            pa.pull_indices = pull_idx;
+            pa.first_nbr = g->first_in_neighbor;
+            pa.known = s->known;
+            pa.full = s->full;
+            pa.done = s->done;
+            pa.labels = d_labels;
+            pa.off_slice0 = s->off_slice[0];
+            pa.off_slice1 = s->off_slice[1];
+            pa.wl = s->wl;
+            pa.iso = g->no_in_arc_bitmap;
+            pa.s = s->d_lstate;
+            pa.sh = s->small;
+            pa.slots = s->pull_slots;
+            pa.tile_counters = ws->d_tile_counter;
+            pa.res = s->d_lresult;
+            pa.h_while = h_while;
+            p2p_pull_levels_kernel<<<(unsigned)s->pull_grid, PULL_NT, 0, cs>>>(pa);
+            LL_CUDA(cudaGetLastError());
+        }
+        if (beamer) {
+            // (5) pull -> push hand-over
+            p2p_gather_or_dyn_kernel<<<ws->num_sms * 4, 256, 0, cs>>>(s->peers, s->off_slice[0], s->off_slice[1], s->wl / 4, P, me, dyn,
                                                                       (uint32_t)LOOP_RUN_TO_PUSH, reinterpret_cast<uint4 *>(s->full),
-                                                                      reinterpret_cast<uint4 *>(s->known));
+                                                                      reinterpret_cast<uint4 *>(s->known), s->done,
+                                                                      g->no_in_arc_bitmap, pull_off);
             LL_CUDA(cudaGetLastError());
             const int64_t ctiles = ((int64_t)s->wl + COMPACT_NT * BITLIST_VT - 1) / (COMPACT_NT * BITLIST_VT);
             int64_t cgrid = (int64_t)ws->num_sms * 8;
@@ -777,6 +1563,8 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
     s->k_scratch = ctx->frontier[0];
     s->k_iso = g->no_in_arc_bitmap;
     s->k_first = g->first_in_neighbor;
+    s->k_pull_offsets = pull_off;
+    s->k_pull_indices = pull_idx;
     s->k_gen = ctx->scratch_gen;
     s->k_mode = mode;
     ws->stream = user_stream;
@@ -810,7 +1598,9 @@ int p2p_ensure_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, in
     }
     if (!s->exec || s->k_offsets != g->row_offsets || s->k_indices != g->col_indices || s->k_labels != d_labels ||
         s->k_scratch != ctx->frontier[0] || s->k_mode != mode || s->k_iso != g->no_in_arc_bitmap ||
-        s->k_first != g->first_in_neighbor || s->k_gen != ctx->scratch_gen) {
+        s->k_first != g->first_in_neighbor || s->k_gen != ctx->scratch_gen ||
+        s->k_pull_offsets != (g->col_offsets ? g->col_offsets : g->row_offsets) ||
+        s->k_pull_indices != (g->row_indices ? g->row_indices : g->col_indices)) {
         B200_CUDA(cudaStreamSynchronize(st));
         const int bs = p2p_build_graph(s, g, d_labels, mode);
         if (bs != B200_OK) {
@@ -843,11 +1633,20 @@ int p2p_run_graph(b200_p2p_bfs *s, const b200_graph *g, int64_t m_global, int32_
     pr->bar_epoch0 = s->epoch;
     pr->lb_epoch0 = ws->epoch + 1;
     pr->stats_seq0 = s->stats_seq;
-    static const bool want_trace = getenv("B200_LOOP_TRACE") != nullptr;
+    const bool want_trace = getenv("B200_LOOP_TRACE") != nullptr;   // (read per run)
     constexpr uint32_t TRACE_CAP = 4096;
     if (want_trace && !s->d_trace) B200_CUDA(cudaMalloc(&s->d_trace, sizeof(unsigned long long) * TRACE_CAP));
     pr->trace = want_trace ? s->d_trace : nullptr;
     pr->trace_cap = TRACE_CAP;
+    // small-level kernel: on unless B200_P2P_SMALL=0; a push level is "small" while the degree sum of its frontier
+    // stays below B200_P2P_SMALL_ARCS (after a pull phase: while the frontier has at most B200_P2P_SMALL_VERTS vertices)
+    // (read per run: all ranks of a job see the same environment)
+    const long long env_small = getenv("B200_P2P_SMALL") ? atoll(getenv("B200_P2P_SMALL")) : 1;
+    const long long env_arcs = getenv("B200_P2P_SMALL_ARCS") ? atoll(getenv("B200_P2P_SMALL_ARCS")) : (2ll << 20);
+    const long long env_verts = getenv("B200_P2P_SMALL_VERTS") ? atoll(getenv("B200_P2P_SMALL_VERTS")) : (64ll << 10);
+    pr->small_on = env_small != 0 ? 1u : 0u;
+    pr->small_arcs = env_arcs;
+    pr->small_verts = env_verts;
     s->h_lresult->status = -1;
     s->h_lresult->num_levels = 0;
     B200_CUDA(cudaEventRecord(s->ev_run[0], st));
@@ -856,14 +1655,21 @@ int p2p_run_graph(b200_p2p_bfs *s, const b200_graph *g, int64_t m_global, int32_
     B200_CUDA(cudaEventSynchronize(s->ev_run[1]));
     const P2PLoopResult *r = s->h_lresult;
     if (r->status < 0) return B200_ERR_CUDA;
-    if (want_trace && s->rank == 0) {   // debug aid: kernel-entry timeline of rank 0 (ids: see loop_trace call sites)
-        static unsigned long long h[TRACE_CAP];
-        B200_CUDA(cudaMemcpy(h, s->d_trace, sizeof h, cudaMemcpyDeviceToHost));
+    const bool trace_all = want_trace && !strcmp(getenv("B200_LOOP_TRACE"), "all");
+    if (want_trace && (s->rank == 0 || trace_all)) {   // debug aid: kernel-entry timeline (ids: see loop_trace call sites)
+        unsigned long long *h = new (std::nothrow) unsigned long long[TRACE_CAP];
+        if (!h) return B200_ERR_NOMEM;
+        cudaError_t ce = cudaMemcpy(h, s->d_trace, sizeof(unsigned long long) * TRACE_CAP, cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) {
+            delete[] h;
+            return cuda_status(ce);
+        }
         const unsigned long long cnt = h[0] < TRACE_CAP - 1 ? h[0] : TRACE_CAP - 1;
-        fprintf(stderr, "B200_LOOP_TRACE rank0 %llu entries (us since first, kernel id):", cnt);
+        fprintf(stderr, "B200_LOOP_TRACE rank%d %llu entries (us since first, kernel id):", s->rank, cnt);
         for (unsigned long long i = 1; i <= cnt; ++i)
             fprintf(stderr, " %.1f:%llu", (double)((h[i] >> 8) - (h[1] >> 8)) * 1e-3, h[i] & 255ull);
         fprintf(stderr, "\n");
+        delete[] h;
     }
     s->epoch = r->bar_epoch;
     s->stats_seq = r->stats_seq;
@@ -887,6 +1693,7 @@ int p2p_run_graph(b200_p2p_bfs *s, const b200_graph *g, int64_t m_global, int32_
         for (int l = 0; l < nl; ++l) {
             b200_level_stat *ls = &stats->level[l];
             ls->direction = r->level[l].direction;
+            ls->reserved = r->level[l].exchange;   // 0 = vertex ids through the inboxes (small level), 1 = bitmap slices
             ls->frontier_len = r->level[l].frontier_len;
             ls->arcs = r->level[l].arcs;
             ls->discovered = r->level[l].discovered;
@@ -908,7 +1715,8 @@ int b200_p2p_bfs_heap_bytes(int num_ranks, int64_t n_global, int64_t *bytes) {
     const int64_t n_local = n_global / num_ranks;
     if (n_local * num_ranks != n_global || n_local % 128) return B200_ERR_INVALID;
     const size_t slice = ((size_t)(n_local / 32) * 4 + 255) & ~(size_t)255;
-    *bytes = (int64_t)(P2P_CTRL_BYTES + 2 * slice + (size_t)n_global * 4);
+    const size_t known = ((size_t)(n_global / 8) + 255) & ~(size_t)255;
+    *bytes = (int64_t)(P2P_CTRL_BYTES + 2 * slice + known + (size_t)n_global * 4);
     return B200_OK;
 }
 
@@ -932,14 +1740,44 @@ int b200_p2p_bfs_create(b200_ctx *ctx, int rank, int num_ranks, int64_t n_global
     const size_t slice = ((size_t)s->wl * 4 + 255) & ~(size_t)255;
     s->off_slice[0] = P2P_CTRL_BYTES;
     s->off_slice[1] = P2P_CTRL_BYTES + slice;
-    s->off_inbox = P2P_CTRL_BYTES + 2 * slice;
+    s->off_known = P2P_CTRL_BYTES + 2 * slice;
+    s->off_inbox = s->off_known + (((size_t)(n_global / 8) + 255) & ~(size_t)255);
     s->heap_bytes = (size_t)bytes;
     int st = B200_OK;
     do {
         if ((st = cuda_status(cudaMalloc(&s->heap, s->heap_bytes)))) break;
-        if ((st = cuda_status(cudaMemset(s->heap, 0, P2P_CTRL_BYTES + 2 * slice)))) break;
-        if ((st = cuda_status(cudaMalloc(&s->known, (size_t)(n_global / 8))))) break;
+        if ((st = cuda_status(cudaMemset(s->heap, 0, s->off_inbox)))) break;
+        s->known = reinterpret_cast<uint32_t *>(s->heap + s->off_known);   // in the heap: the bitmap exchange reads peers' slices of it
         if ((st = cuda_status(cudaMalloc(&s->full, (size_t)(n_global / 8))))) break;
+        if ((st = cuda_status(cudaMalloc(&s->done, sizeof(uint32_t) * (size_t)s->wl)))) break;
+        if ((st = cuda_status(cudaMalloc(&s->small, sizeof(SmallShared))))) break;
+        if ((st = cuda_status(cudaMemset(s->small, 0, sizeof(SmallShared))))) break;
+        if ((st = cuda_status(cudaMalloc(&s->big_rows, sizeof(uint32_t) * (size_t)s->n_local)))) break;
+        {
+            // the small-level kernel synchronises its grid itself: every CTA must be resident
+            int occ = 0;
+            if ((st = cuda_status(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p2p_small_levels_kernel, SMALL_NT, 0)))) break;
+            if (occ < 1) {
+                st = B200_ERR_UNSUPPORTED;
+                break;
+            }
+            s->small_grid = ctx->ws.num_sms;
+            const char *eg = getenv("B200_P2P_SMALL_GRID");   // e.g. several ranks sharing one GPU (tests): their grids must fit together
+            if (eg && atoi(eg) > 0 && atoi(eg) < s->small_grid) s->small_grid = atoi(eg);
+            if ((st = cuda_status(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p2p_pull_levels_kernel, PULL_NT, 0)))) break;
+            if (occ < 1) {
+                st = B200_ERR_UNSUPPORTED;
+                break;
+            }
+            s->pull_grid = ctx->ws.num_sms * (occ > 4 ? 4 : occ);
+            const char *pg = getenv("B200_P2P_PULL_GRID");
+            if (pg && atoi(pg) > 0 && atoi(pg) < s->pull_grid) s->pull_grid = atoi(pg);
+        }
+        if ((st = cuda_status(cudaMalloc(&s->pull_slots, sizeof(PullCounters) * SMALL_SLOTS)))) break;
+        if ((st = cuda_status(cudaMemset(s->pull_slots, 0, sizeof(PullCounters) * SMALL_SLOTS)))) break;
+        s->absorb_tiles = ((int64_t)s->wl + COMPACT_NT * BITLIST_VT - 1) / (COMPACT_NT * BITLIST_VT) + 1;
+        if ((st = cuda_status(cudaMalloc(&s->absorb_status, sizeof(unsigned long long) * (size_t)s->absorb_tiles)))) break;
+        if ((st = cuda_status(cudaMemset(s->absorb_status, 0, sizeof(unsigned long long) * (size_t)s->absorb_tiles)))) break;
         if ((st = cuda_status(cudaMalloc(&s->box_counts, sizeof(unsigned long long) * P2P_MAX)))) break;
         if ((st = cuda_status(cudaHostAlloc(&s->h_res, sizeof(unsigned long long) * RES_WORDS, cudaHostAllocMapped)))) break;
         std::memset(s->h_res, 0, sizeof(unsigned long long) * RES_WORDS);
@@ -1003,8 +1841,12 @@ int b200_p2p_bfs_destroy(b200_p2p_bfs *s) {
     for (int p = 0; p < P2P_MAX; ++p)
         if (s->opened[p]) cudaIpcCloseMemHandle(s->opened[p]);
     if (s->heap) cudaFree(s->heap);
-    if (s->known) cudaFree(s->known);
     if (s->full) cudaFree(s->full);
+    if (s->done) cudaFree(s->done);
+    if (s->small) cudaFree(s->small);
+    if (s->big_rows) cudaFree(s->big_rows);
+    if (s->pull_slots) cudaFree(s->pull_slots);
+    if (s->absorb_status) cudaFree(s->absorb_status);
     if (s->box_counts) cudaFree(s->box_counts);
     if (s->h_res) cudaFreeHost(s->h_res);
     if (s->ev_run[0]) cudaEventDestroy(s->ev_run[0]);

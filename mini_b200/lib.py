@@ -167,7 +167,8 @@ class Stats:
         self.level_loop = "graph" if c.level_loop == LOOP_GRAPH else "host"
         self.levels = [
             dict(direction="pull" if l.direction else "push", frontier_len=l.frontier_len, arcs=l.arcs,
-                 discovered=l.discovered, advance_ms=l.advance_ms, level_ms=l.level_ms)
+                 discovered=l.discovered, advance_ms=l.advance_ms, level_ms=l.level_ms,
+                 exchange="bitmap" if l.reserved else "ids")   # peer-memory BFS: what crossed NVLink in this level
             for l in c.level[:min(c.num_levels, MAX_LEVELS)]
         ]
 

@@ -72,7 +72,7 @@ class P2PBfs:
                                           self.labels.data_ptr(), C.byref(cs), sent), "b200_p2p_bfs_run")
         st = L.Stats(cs)
         self.levels = [dict(direction=l["direction"], frontier=l["frontier_len"], arcs=l["arcs"], discovered=l["discovered"],
-                            sent=int(sent[i]), level_ms=l["level_ms"]) for i, l in enumerate(st.levels)]
+                            sent=int(sent[i]), level_ms=l["level_ms"], exchange=l["exchange"]) for i, l in enumerate(st.levels)]
         self.device_ms, self.launches, self.level_loop = st.device_ms, st.launches, st.level_loop
         return st.num_levels
 

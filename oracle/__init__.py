@@ -67,6 +67,8 @@ def lib():
         L.orc_bfs_push_level.restype = C.c_int64
         L.orc_reached_arcs_i32.argtypes = [C.c_int64, _i64p, _i32p]
         L.orc_reached_arcs_i32.restype = C.c_int64
+        L.orc_kcore.argtypes = [C.c_int64, _i64p, _i32p, _i32p]
+        L.orc_kcore.restype = C.c_int32
         L.orc_num_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -237,6 +239,67 @@ def sssp_ref_preds(g: CSR, src: int = 0):
     dist = np.empty(g.n, np.int32)
     lib().orc_sssp_ref_preds(g.n, g.offsets, g.indices, g.weights, src, preds, dist.ctypes.data)
     return preds, dist
+
+
+def kcore(g: CSR):
+    """(num_cores, largest k-core) of the reference's peel, kcore_problem.hxx:54-105 restated (oracle.c orc_kcore).
+    PARITY UNPINNED: the reference's kcore_problem.hxx does not compile (kcore_problem.hxx:44), so its cpu() could
+    not be built here to check this restatement; the hand-computed cases in tests/test_oracle.py stand in."""
+    cores = np.empty(g.n, np.int32)
+    largest = lib().orc_kcore(g.n, g.offsets, g.indices, cores)
+    return cores, int(largest)
+
+
+def mt19937_hashes(n: int, prime: int, state=None):
+    """n draws of std::uniform_int_distribution<int>(0, prime) from a default-seeded std::mt19937 -- what
+    mgpu::fill_random(0, prime, n, false, ctx) hands the colouring problem (memory.hxx:112-129,
+    coloring_problem.hxx:44,50).  libstdc++'s algorithm: with R = 2^32 and range = prime + 1, draw 32-bit words until
+    one is below range * (R // range), then divide by R // range.  `state`: a numpy RandomState carried from call to
+    call (the reference's engine is one process-wide static); returns (hashes, state)."""
+    if state is None:
+        state = np.random.RandomState(5489)          # init_genrand(5489) == std::mt19937's default seed
+    rng = prime + 1
+    scaling = (1 << 32) // rng
+    past = rng * scaling
+    out = np.empty(n, np.int32)
+    k = 0
+    while k < n:
+        raw = state.randint(0, 1 << 32, size=n - k, dtype=np.uint64)   # full range: the generator's raw 32-bit words
+        ok = raw[raw < past]
+        out[k:k + len(ok)] = (ok // scaling).astype(np.int32)
+        # (a rejected word is simply skipped by the C++ loop: order of the accepted ones is unchanged)
+        k += len(ok)
+    return out, state
+
+
+def coloring(g: CSR, prime: int = 15485863, max_iter: int = 10):
+    """Hash-extrema colouring of coloring_enactor.hxx:43-92 + coloring_functor.hxx:10-70, restated with numpy:
+    every iteration the uncoloured vertices whose hash is below (above) every UNCOLOURED neighbour's take colour
+    2*it+1 (2*it+2); all hashes are redrawn.  Returns (colors, uncoloured count after every iteration)."""
+    n = g.n
+    deg = np.diff(g.offsets)
+    rows = np.repeat(np.arange(n, dtype=np.int64), deg)
+    colors = np.zeros(n, np.int32)
+    frontier = np.arange(n, dtype=np.int64)
+    hashes, st = mt19937_hashes(n, prime)
+    lens = []
+    it = 0
+    imin, imax = np.iinfo(np.int32).min, np.iinfo(np.int32).max
+    while len(frontier) and it < max_iter:
+        live = colors[g.indices] == 0
+        hv = hashes[g.indices].astype(np.int64)
+        rmax = np.full(n, imin, np.int64)
+        rmin = np.full(n, imax, np.int64)
+        np.maximum.at(rmax, rows, np.where(live, hv, imin))
+        np.minimum.at(rmin, rows, np.where(live, hv, imax))
+        h = hashes[frontier].astype(np.int64)
+        col = np.where(h < rmin[frontier], 2 * it + 1, np.where(h > rmax[frontier], 2 * it + 2, 0))
+        colors[frontier[col > 0]] = col[col > 0]
+        frontier = frontier[col == 0]
+        lens.append(len(frontier))
+        it += 1
+        hashes, st = mt19937_hashes(n, prime, st)
+    return colors, lens
 
 
 def neighborhood_reduce(g: CSR, frontier, values, op: str = "plus", identity: float = 0.0):

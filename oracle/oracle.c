@@ -334,6 +334,41 @@ ORC_API int orc_pr(int64_t n, const int64_t *offsets, const int32_t *indices, in
 }
 
 /* ------------------------------------------------------------------------- */
+/* k-core peel: gunrock/src/kcore/kcore_problem.hxx:54-105 (the reference's CPU  */
+/* validation), which the device enactor mirrors round by round                  */
+/* (kcore_enactor.hxx:41-84).  For k = 1, 2, ...: repeat { every vertex with     */
+/* remaining degree in (0, k) gets core number k - 1 and degree 0; stop the      */
+/* rounds if nobody was peeled; every arc out of a peeled vertex lowers its head's*/
+/* degree }; the first k that leaves no vertex of degree >= k ends it.  Note the  */
+/* reference's quirk, kept: a vertex whose degree reaches 0 only through its      */
+/* neighbours' removal is never numbered (it stays 0).  Returns the largest core. */
+/* ------------------------------------------------------------------------- */
+ORC_API int32_t orc_kcore(int64_t n, const int64_t *offsets, const int32_t *indices, int32_t *num_cores) {
+    int64_t *deg = (int64_t *)malloc((size_t)n * sizeof(int64_t));
+    int32_t *peeled = (int32_t *)malloc((size_t)(n ? n : 1) * sizeof(int32_t));
+    char *remain = (char *)malloc((size_t)(n ? n : 1));
+    int32_t largest = -1;
+    for (int64_t v = 0; v < n; ++v) { deg[v] = offsets[v + 1] - offsets[v]; num_cores[v] = 0; }
+    for (int64_t k = 1; k <= n && largest < 0; ++k) {
+        int64_t num_remain = 0;
+        memset(remain, 1, (size_t)n);
+        for (;;) {
+            int64_t np = 0;
+            for (int64_t v = 0; v < n; ++v)
+                if (deg[v] < k && deg[v] > 0 && remain[v]) { num_cores[v] = (int32_t)(k - 1); deg[v] = 0; peeled[np++] = (int32_t)v; }
+            num_remain = 0;
+            for (int64_t v = 0; v < n; ++v) { remain[v] = deg[v] >= k; num_remain += remain[v]; }
+            if (np == 0) break;
+            for (int64_t i = 0; i < np; ++i)
+                for (int64_t e = offsets[peeled[i]]; e < offsets[peeled[i] + 1]; ++e) deg[indices[e]]--;
+        }
+        if (num_remain == 0) largest = (int32_t)(k - 1);
+    }
+    free(deg); free(peeled); free(remain);
+    return largest;
+}
+
+/* ------------------------------------------------------------------------- */
 /* Operator-level restatements used to check the drop-in operators one call at */
 /* a time (advance.hxx:20-67, filter.hxx:11-31 with the BFS functor).          */
 /* ------------------------------------------------------------------------- */

@@ -48,6 +48,10 @@ double ref_sssp_cpu(int n, int m, const int *offsets, const int *indices, const 
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// (kcore: gunrock/src/kcore/kcore_problem.hxx does not compile -- its constructor hands a mem_t<int> to
+// problem_t::GetDegrees(mem_t<float>&), kcore_problem.hxx:44 -- so its cpu() cannot be built unmodified;
+// oracle.c restates it, unpinned.)
+
 // load_graph + copy-out.  First call with offsets == NULL to get sizes.
 // NOTE: the reference's sort comparator is not a strict weak order
 // (graph.hxx:139-157); only feed it files without duplicate edges.

@@ -86,11 +86,27 @@ def test_partitioned_bfs_other_sources(src):
     assert np.array_equal(labels, ref)
 
 
-def _virtual_ranks_p2p(scale, ef, seed, world, src, mode, repeat=2, loop="graph"):
+SMALL_VARIANTS = {   # B200_P2P_SMALL / _SMALL_ARCS / _SMALL_VERTS (p2p_bfs.cu): which levels the persistent small-level kernel runs
+    "small-default": ("1", None, None),     # scale-14 graphs: every push level is "small"
+    "small-tiny": ("1", "3000", "64"),      # only the first / last levels: exercises small -> big push -> pull -> small
+    "small-off": ("0", None, None),         # every push level through scan + claim-only advance + bitmap exchange
+}
+
+
+def _virtual_ranks_p2p(scale, ef, seed, world, src, mode, repeat=2, loop="graph", small="small-default"):
     """P ranks as threads of this process, each with its OWN stream on GPU 0 (the cross-rank flag
     barriers spin inside kernels, so the ranks' kernels must be able to run concurrently); heaps are
     wired by address (b200_p2p_bfs_connect with peer_bases)."""
     import mini_b200 as mb
+    on, arcs, verts = SMALL_VARIANTS[small]
+    for k, v in (("B200_P2P_SMALL", on), ("B200_P2P_SMALL_ARCS", arcs), ("B200_P2P_SMALL_VERTS", verts)):
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+    # the small-level kernel synchronises its own grid: the grids of all ranks sharing this GPU must be resident together
+    os.environ["B200_P2P_SMALL_GRID"] = str(max(1, 128 // world))
+    os.environ["B200_P2P_PULL_GRID"] = str(max(1, 256 // world))
     from mini_b200 import dist as D
     from mini_b200.p2p import P2PBfs
     bar = threading.Barrier(world)
@@ -131,13 +147,14 @@ def _virtual_ranks_p2p(scale, ef, seed, world, src, mode, repeat=2, loop="graph"
     return out
 
 
-@pytest.mark.parametrize("loop", ["graph", "host"])
+@pytest.mark.parametrize("loop,small", [("graph", "small-default"), ("graph", "small-tiny"), ("graph", "small-off"),
+                                        ("host", "small-default")])
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
 @pytest.mark.parametrize("mode", ["push", "beamer"])
-def test_p2p_bfs_virtual_ranks(world, mode, loop):
+def test_p2p_bfs_virtual_ranks(world, mode, loop, small):
     scale, ef, seed, src = 14, 16, 1, 0
     ref = oracle.bfs(oracle.rmat_csr(scale, ef, seed), src)
-    res = _virtual_ranks_p2p(scale, ef, seed, world, src, mode, loop=loop)
+    res = _virtual_ranks_p2p(scale, ef, seed, world, src, mode, loop=loop, small=small)
     labels = np.empty(1 << scale, np.int32)
     for r in range(world):
         labels[PT.global_ids(r, world, (1 << scale) // world)] = res[r][0]
@@ -148,15 +165,19 @@ def test_p2p_bfs_virtual_ranks(world, mode, loop):
     assert sum(l["discovered"] for l in stats) + 1 == int((ref >= 0).sum())
     if mode == "beamer":
         assert any(l["direction"] == "pull" for l in stats)
-    if world > 1 and mode == "push":
+    if world > 1 and mode == "push" and (loop == "host" or small != "small-off"):
         assert 0 < sum(l["sent"] for l in stats) <= (world - 1) * (1 << scale)
+    if loop == "graph":
+        kinds = {l["exchange"] for l in stats if l["direction"] == "push"}
+        assert kinds == {"small-default": {"ids"}, "small-tiny": {"ids", "bitmap"}, "small-off": {"bitmap"}}[small], kinds
 
 
+@pytest.mark.parametrize("small", ["small-default", "small-tiny"])
 @pytest.mark.parametrize("src", [1, 77, 12345])
-def test_p2p_bfs_other_sources(src):
+def test_p2p_bfs_other_sources(src, small):
     scale, ef, seed, world = 14, 8, 3, 4
     ref = oracle.bfs(oracle.rmat_csr(scale, ef, seed), src)
-    res = _virtual_ranks_p2p(scale, ef, seed, world, src, "beamer")
+    res = _virtual_ranks_p2p(scale, ef, seed, world, src, "beamer", small=small)
     labels = np.empty(1 << scale, np.int32)
     for r in range(world):
         labels[PT.global_ids(r, world, (1 << scale) // world)] = res[r][0]
