@@ -20,6 +20,45 @@ def _level_rows(levels):
     return [dict(d=l["direction"], F=l["frontier"], arcs=l["arcs"], found=l["discovered"], sent=l["sent"]) for l in levels]
 
 
+def _mg_roofline(levels, level_ms, timeline, n, world, sent):
+    """Per-GPU roofline of the heaviest pull level (B_pull = |U|*12 + a*(4 + 1/8) + |F_next|*4 + n/8,
+    uint32 offsets; |U| = vertices still unlabelled when the level starts, a = in-arcs inspected, counted by the kernel)
+    and the NVLink figure of its allgather (8d: (P-1)/P * n/8 bytes received per GPU over the gather's own time)."""
+    from bench import _peaks
+    peak, peak_src = _peaks()
+    out = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+           "nvlink": {"vertex_ids_sent_bytes_per_bfs": sent * 4, "bitmap_bytes_gathered_per_pull_level_per_gpu": (world - 1) * (n // 8) // world,
+                      "peak_gbs_per_direction": 900.0, "achieved_gbs": None, "frac": None}}
+    pulls = [i for i, l in enumerate(levels) if l["direction"] == "pull"]
+    if not pulls or len(level_ms) != len(levels):
+        out["note"] = "no pull level in this traversal"
+        return out
+    top = max(pulls, key=lambda i: levels[i]["arcs"])
+    unvisited = n - 1 - sum(l["discovered"] for l in levels[:top])
+    b = unvisited * 12 + levels[top]["arcs"] * (4 + 1 / 8) + levels[top]["discovered"] * 4 + n / 8
+    # time of the pull body alone (trace ids 32 = pull starts, 33 = stats posted) if the timeline has it, else the level
+    t_ms, t_gather = level_ms[top], None
+    if timeline:
+        k = -1
+        for j, (t, ident) in enumerate(timeline):
+            if ident == 31:
+                k += 1
+                if k == pulls.index(top):
+                    seq = timeline[j:j + 3]
+                    if len(seq) == 3 and seq[1][1] == 32 and seq[2][1] == 33:
+                        t_gather, t_ms = (seq[1][0] - seq[0][0]) * 1e-3, (seq[2][0] - seq[1][0]) * 1e-3
+                    break
+    gbs = b / world / (t_ms * 1e-3) / 1e9
+    out.update({"kernel": "p2p_pull_levels_kernel: bfs_pull_body of the heaviest pull level (per GPU: 1/P of the rows)",
+                "achieved": gbs, "frac": gbs / peak, "algorithmic_bytes_per_launch": b / world, "launch_ms": t_ms,
+                "bytes_model": "SURVEY.md 8d pull: |U|*12 + a*(4+1/8) + |F_next|*4 + n/8, divided by P", "level": top})
+    if t_gather:
+        nb = (world - 1) * (n // 8) // world
+        out["nvlink"].update({"achieved_gbs": nb / (t_gather * 1e-3) / 1e9, "frac": nb / (t_gather * 1e-3) / 1e9 / 900.0,
+                              "gather_ms": t_gather, "note": "the allgather of the heaviest pull level: peer loads of (P-1) bitmap slices"})
+    return out
+
+
 def run(args) -> int:
     import torch
     from bench import METRIC_MG
@@ -105,9 +144,20 @@ def run(args) -> int:
         rk.level_loop_timed = rk.level_loop
     levels = list(run_bfs())
     level_ms = [round(l.get("level_ms", 0.0), 4) for l in levels]
-    if exchange == "p2p":                       # one more run with per-level events (outside the timed region)
-        rk.run(0, mode, timing=True)
-        level_ms = [round(l["level_ms"], 4) for l in rk.levels]
+    timeline = None
+    if exchange == "p2p":
+        # one more run with the kernels' own timeline (outside the timed region; graph-driven loop: the levels run
+        # inside persistent kernels, so the per-level times come from %globaltimer marks, not from CUDA events)
+        rk.set_trace(True)
+        run_bfs()
+        rk.set_trace(False)
+        timeline = rk.last_trace()
+        lt = rk.level_times_ms()
+        if len(lt) == len(levels):
+            level_ms = [round(x, 4) for x in lt]
+        else:                                   # host-driven loop: CUDA events per level
+            rk.run(0, mode, timing=True)
+            level_ms = [round(l["level_ms"], 4) for l in rk.levels]
     reached_arcs, reached_vertices = comm.all_reduce_sum([rk.reached_degree_sum(), rk.reached_count()])
     value = reached_arcs * args.steps / (ms_total * 1e-3) / 1e9
     props_ok, level_hist = D.verify_bfs_properties(rk, comm, 0)
@@ -232,10 +282,7 @@ def run(args) -> int:
                     "h2d_bytes_per_step": rk.n_local * 4 * world, "d2h_bytes_per_step": rk.n_local * 4 * world,
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": all_launches,
-            "roofline": {"bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
-                         "note": "per-kernel roofline is reported by the N=1 line",
-                         "nvlink": {"bytes_sent_per_bfs": sent * 4, "bitmap_bytes_gathered_per_pull_level_per_gpu":
-                                    (world - 1) * (n // 8) // world, "peak_gbs_per_direction": 900.0}},
+            "roofline": _mg_roofline(levels, level_ms, timeline, n, world, sent),
             "cpu_baseline": None,
             "other_mode": other_line,
             "single_gpu_same_graph": single,

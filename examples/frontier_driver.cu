@@ -6,7 +6,12 @@
 //   frontier_driver --algo=bfs  (--file=g.mtx | --rmat-scale=16) [--src=0] [--alpha=A] [--builtin] [--mode=0|1|2]
 //   frontier_driver --algo=sssp (--file=g.mtx [--undirected] | --rmat-scale=16) [--queue-sizing=1.5] [--builtin]
 //   frontier_driver --algo=pr   (--file=g.mtx | --rmat-scale=16) [--max_iter=10] [--scatter]
+//   frontier_driver --algo=kcore    (--file=g.mtx | --rmat-scale=10)                       (kcore_enactor.hxx:41-84)
+//   frontier_driver --algo=coloring (--file=g.mtx | --rmat-scale=12) [--prime=P] [--max_iter=10]   (coloring_enactor.hxx:43-92)
+//   --dump=<file>: the result vector (labels / distances / ranks / core numbers / colours) as raw 4-byte values
 #include "bfs/bfs_enactor.hxx"
+#include "coloring/coloring_enactor.hxx"
+#include "kcore/kcore_enactor.hxx"
 #include "pr/pr_enactor.hxx"
 #include "sssp/sssp_enactor.hxx"
 #include "test_utils.hxx"
@@ -33,8 +38,8 @@ static std::shared_ptr<graph_t> rmat_graph(int scale, int edge_factor, uint64_t 
 
 int main(int argc, char **argv) {
     CommandLineArgs args(argc, argv);
-    std::string algo = "bfs", filename;
-    int src = 0, scale = 0, edge_factor = 16, max_iter = 10, mode = B200_BFS_PUSH;
+    std::string algo = "bfs", filename, dump;
+    int src = 0, scale = 0, edge_factor = 16, max_iter = 10, mode = B200_BFS_PUSH, prime = 15485863;
     unsigned long long seed = 1;
     float queue_sizing = 1.0f, beta = 18.0f;
     args.GetCmdLineArgument("algo", algo);
@@ -46,6 +51,8 @@ int main(int argc, char **argv) {
     args.GetCmdLineArgument("max_iter", max_iter);
     args.GetCmdLineArgument("queue-sizing", queue_sizing);
     args.GetCmdLineArgument("mode", mode);
+    args.GetCmdLineArgument("dump", dump);
+    args.GetCmdLineArgument("prime", prime);
     const bool builtin = args.CheckCmdLineFlag("builtin"), scatter = args.CheckCmdLineFlag("scatter");
     const bool undirected = args.CheckCmdLineFlag("undirected") || algo != "sssp";
 
@@ -61,6 +68,12 @@ int main(int argc, char **argv) {
     std::cout << "graph: " << d_graph->num_nodes << " nodes, " << d_graph->num_edges << " arcs" << std::endl;
     test_timer_t timer;
     bool ok = true;
+    auto dump_result = [&](const void *data, size_t count) {
+        if (dump.empty()) return;
+        FILE *f = std::fopen(dump.c_str(), "wb");
+        if (!f || std::fwrite(data, 4, count, f) != count) ok = false;
+        if (f) std::fclose(f);
+    };
 
     if (algo == "bfs") {
         float alpha = 1.0f / d_graph->num_nodes;   // never switch to pull unless asked (test_bfs.cu:30)
@@ -79,6 +92,7 @@ int main(int argc, char **argv) {
         problem->extract();
         problem->cpu(validation_labels, graph->csr->offsets, graph->csr->indices);
         ok = validate(problem->labels, validation_labels);
+        dump_result(problem->labels.data(), problem->labels.size());
     } else if (algo == "sssp") {
         auto problem = std::make_shared<sssp::sssp_problem_t>(d_graph, src, context);
         auto enactor = std::make_shared<sssp::sssp_enactor_t>(context, d_graph->num_nodes, d_graph->num_edges, queue_sizing);
@@ -106,6 +120,7 @@ int main(int argc, char **argv) {
                     tight |= graph->csr->indices[k] == v && validation_dist[p] + graph->csr->edge_weights[k] == validation_dist[v];
             if (builtin) ok = tight;   // operator path keeps the reference's racy last-writer preds
         }
+        dump_result(problem->labels.data(), problem->labels.size());
     } else if (algo == "pr") {
         auto problem = std::make_shared<pr::pr_problem_t>(d_graph, max_iter, context);
         auto enactor = std::make_shared<pr::pr_enactor_t>(context, d_graph->num_nodes, d_graph->num_edges);
@@ -121,6 +136,39 @@ int main(int argc, char **argv) {
                 const bool has = graph->csr->offsets[v + 1] > graph->csr->offsets[v];
                 ok = ok && std::fabs(ranks[v] - (has ? 0.15f + 0.85f * 0.15f : 0.15f)) < 1e-5f;
             }
+        dump_result(ranks.data(), ranks.size());
+    } else if (algo == "kcore") {
+        // tests/kcore/test_kcore.cu:26-50: enact, then the host peel of kcore_problem_t::cpu validates core numbers
+        auto problem = std::make_shared<kcore::kcore_problem_t>(d_graph, context);
+        auto enactor = std::make_shared<kcore::kcore_enactor_t>(context, d_graph->num_nodes, d_graph->num_edges);
+        timer.start();
+        enactor->enact(problem, context);
+        cout << "elapsed time: " << timer.end() << "s." << std::endl;
+        std::vector<int> validation_num_cores(d_graph->num_nodes, 0);
+        problem->extract();
+        const int ref_largest = problem->cpu(validation_num_cores, graph->csr->offsets, graph->csr->indices);
+        if (ref_largest != problem->largest_k_core)
+            cout << "Validation Error for largest k-core. ref: " << ref_largest << " gpu: " << problem->largest_k_core << endl;
+        ok = ref_largest == problem->largest_k_core && validate(problem->num_cores, validation_num_cores);
+        dump_result(problem->num_cores.data(), problem->num_cores.size());
+    } else if (algo == "coloring") {
+        // tests/coloring/test_coloring.cu:32-41 (which only prints the colours): here the colouring is checked --
+        // two coloured end points of an arc never share a colour
+        auto problem = std::make_shared<coloring::coloring_problem_t>(d_graph, prime, max_iter, context);
+        auto enactor = std::make_shared<coloring::coloring_enactor_t>(context, d_graph->num_nodes, d_graph->num_edges);
+        timer.start();
+        enactor->enact(problem, context);
+        cout << "elapsed time: " << timer.end() << "s." << std::endl;
+        problem->extract();
+        cout << "uncoloured after each iteration:";
+        for (int x : enactor->frontier_lengths) cout << ' ' << x;
+        cout << endl;
+        for (int v = 0; ok && v < d_graph->num_nodes; ++v)
+            for (int k = graph->csr->offsets[v]; k < graph->csr->offsets[v + 1]; ++k) {
+                const int u = graph->csr->indices[k];
+                if (u != v && problem->colors[v] > 0 && problem->colors[v] == problem->colors[u]) ok = false;
+            }
+        dump_result(problem->colors.data(), problem->colors.size());
     } else {
         std::cout << "unknown --algo" << std::endl;
         return 2;

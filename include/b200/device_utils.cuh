@@ -83,23 +83,39 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 // visited |= "row has no in-arc" for the words first, first + stride, ... (ONE WORD PER THREAD: a word per warp
 // iteration is a chain of dependent loads -- 0.27 ms for the 2 M words of a scale-26 bitmap).  iso: the prebuilt
 // bitmap (b200_graph::no_in_arc_bitmap), else derived from the pull offsets.
+// Nobody else may be updating `visited` meanwhile (the word is read through L2 and stored back).
 __device__ __forceinline__ void or_no_in_arc_words(uint32_t first, uint32_t stride, const uint32_t *__restrict__ pull_offsets,
                                                    uint32_t n, const uint32_t *__restrict__ iso, uint32_t *visited) {
     const uint32_t num_words = (n + 31u) >> 5;
+    if (iso) {   // four words per thread in flight (one at a time is a chain of dependent L2 round trips)
+        for (uint32_t w0 = first; w0 < num_words; w0 += 4u * stride) {
+            uint32_t m[4], v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t w = w0 + (uint32_t)k * stride;
+                m[k] = w < num_words ? iso[w] : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t w = w0 + (uint32_t)k * stride;
+                v[k] = m[k] ? __ldcg(visited + w) : 0u;   // (through L2: a persistent kernel may hold a stale L1 line)
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (m[k]) visited[w0 + (uint32_t)k * stride] = v[k] | m[k];
+        }
+        return;
+    }
     for (uint32_t w = first; w < num_words; w += stride) {
         uint32_t m = 0u;
-        if (iso) {
-            m = iso[w];
-        } else {
-            const uint32_t v0 = w << 5;
-            uint32_t prev = pull_offsets[v0];
-            for (uint32_t b = 0; b < 32u && v0 + b < n; ++b) {
-                const uint32_t next = pull_offsets[v0 + b + 1];
-                m |= (next == prev ? 1u : 0u) << b;
-                prev = next;
-            }
+        const uint32_t v0 = w << 5;
+        uint32_t prev = pull_offsets[v0];
+        for (uint32_t b = 0; b < 32u && v0 + b < n; ++b) {
+            const uint32_t next = pull_offsets[v0 + b + 1];
+            m |= (next == prev ? 1u : 0u) << b;
+            prev = next;
         }
-        if (m) atomicOr(visited + w, m);   // (through L2: a persistent kernel may hold a stale L1 line of this word)
+        if (m) visited[w] = __ldcg(visited + w) | m;
     }
 }
 

@@ -359,6 +359,11 @@ int b200_p2p_bfs_run(b200_p2p_bfs *s, const b200_graph *g_local, int64_t m_globa
  * spin in a flag barrier (ranks that are threads of ONE process share a CUDA context).  A no-op when the ctx
  * uses B200_LOOP_HOST.  b200_p2p_bfs_run builds lazily if this was not called. */
 int b200_p2p_bfs_prepare(b200_p2p_bfs *s, const b200_graph *g_local, int mode, int32_t *d_labels_local);
+/* Timeline of the graph-driven loop (new; with no host between the levels there are no CUDA events to hang a
+ * per-level time on): when on, the kernels of a run log (globaltimer ns << 8 | id) at their phase boundaries; ids
+ * 64 + (level & 63) mark "level closed".  b200_p2p_bfs_last_trace copies the entries of the last traced run. */
+int b200_p2p_bfs_set_trace(b200_p2p_bfs *s, int on);
+int b200_p2p_bfs_last_trace(b200_p2p_bfs *s, uint64_t *entries, int64_t capacity, int64_t *count);
 int b200_p2p_bfs_destroy(b200_p2p_bfs *s);
 
 /* ---- graph ingest on the host (no GPU involved): the .mtx loader of the reference and a binary CSR cache ---- */

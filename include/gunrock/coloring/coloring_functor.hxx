@@ -1,7 +1,7 @@
 // coloring_functor.hxx -- the functors of the hash-extrema colouring (names and argument lists of
 // gunrock/src/coloring/coloring_functor.hxx:10-70).
 #pragma once
-#include <limits>
+#include <climits>
 #include "coloring/coloring_problem.hxx"
 #include "intrinsics.hxx"
 
@@ -33,7 +33,7 @@ struct reduce_hash_t {
     GUNROCK_FN bool apply_advance(GUNROCK_ARC_ARGS(coloring_slice_t)) { return true; }
     GUNROCK_FN int get_value_to_reduce(GUNROCK_VERTEX_ARGS(coloring_slice_t)) {
         if (data->d_colors[idx] == 0) return data->d_hashs[idx];
-        return MAX ? std::numeric_limits<int>::min() : std::numeric_limits<int>::max();
+        return MAX ? INT_MIN : INT_MAX;   // (numeric_limits is host-only without --expt-relaxed-constexpr)
     }
 };
 typedef reduce_hash_t<true> reduce_max_t;

@@ -45,6 +45,7 @@ struct Ctrl {                                  // heap offset 0 on every rank
     unsigned long long flags[P2P_MAX];         // flags[p]: last barrier epoch rank p signalled to me
     unsigned long long counts[P2P_MAX];        // counts[p]: vertices rank p left in my inbox segment p
     unsigned long long stats[2][P2P_MAX][8];   // stats[parity][p]: rank p's row of the level summary
+    unsigned long long hub_degree;             // level 0: degree of the source's row if its owner split it over the ranks, else 0
 };
 static_assert(sizeof(Ctrl) <= P2P_CTRL_BYTES, "control block");
 
@@ -282,6 +283,7 @@ struct P2PLoopParams {      // mapped pinned, read by the init kernel
     unsigned long long *trace;
     uint32_t trace_cap, small_on;
     long long small_arcs, small_verts;   // a push level runs in the persistent small-level kernel while its frontier is this small
+    long long hub_min;                   // level 0: a source row of at least this many arcs is split over the ranks
 };
 struct P2PLevelRec {
     int32_t direction, exchange;   // exchange: 0 = vertex ids through the inboxes, 1 = bitmap slices
@@ -301,8 +303,9 @@ struct P2PLoopState {       // device
     int32_t level, pull, mode, kernels_per_level;
     float alpha, beta;
     long long n, m_unexplored, flen, reached, total_arcs, launches;
-    long long small_arcs, small_verts;
-    uint32_t small_on, pad;
+    long long small_arcs, small_verts, hub_min;
+    uint32_t small_on;
+    int32_t src;
 };
 
 // ---- persistent small-level kernel: shared state -------------------------------------------
@@ -393,6 +396,8 @@ __global__ void p2p_loop_init_kernel(const P2PLoopParams *p, P2PLoopState *s, in
     s->small_arcs = p->small_arcs;
     s->small_verts = p->small_verts;
     s->small_on = p->small_on;
+    s->hub_min = p->hub_min;
+    s->src = p->src;
     for (int i = 0; i < B200_NUM_COUNTERS; ++i) counters[i] = 0ull;
     tile_counters[0] = 0u;
     tile_counters[1] = 0u;
@@ -454,11 +459,15 @@ __device__ __forceinline__ unsigned ld_relaxed_gpu_u32(const unsigned *p) {
 }
 
 // Whole grid.  s_gen: this CTA's copy of the barrier generation (shared memory).  Returns false once aborted.
-__device__ __forceinline__ bool small_grid_barrier(SmallShared *sh, unsigned *s_gen) {
+// sys = true: what this CTA stored into PEER memory is ordered before whatever a thread signals after the barrier --
+// one system-scope fence by thread 0 after the CTA barrier (cumulative over the CTA's stores), not one per thread
+// (75 K MEMBAR.SYS per level made a small level 15 us longer in the 2-GPU trace).
+__device__ __forceinline__ bool small_grid_barrier(SmallShared *sh, unsigned *s_gen, bool sys = false) {
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned g = *s_gen;
-        __threadfence();
+        if (sys) __threadfence_system();
+        else __threadfence();
         if (atomicAdd(&sh->bar_count, 1u) == gridDim.x - 1u) {
             sh->bar_count = 0u;
             __threadfence();
@@ -499,7 +508,7 @@ __device__ __forceinline__ bool small_wait_peers(const SmallArgs &a, unsigned lo
 }
 
 __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs a) {
-    constexpr int NW = SMALL_NT / 32, U = 4;
+    constexpr int NW = SMALL_NT / 32, U = 8;
     __shared__ unsigned s_gen;
     __shared__ unsigned long long s_sum[8];
     P2PLoopState *s = a.s;
@@ -533,6 +542,57 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
     bool finished = false;
     __syncthreads();
 
+    // ---- level 0 from a hub: one row (1.7 M arcs at scale 26) on ONE rank while the others wait was 65 us of a 0.78 ms
+    // traversal at 2 GPUs and does not shrink with P.  The owner deals the row out -- piece p, a plain copy over NVLink,
+    // into the tail of its inbox segment in rank p's heap -- and after one flag barrier every rank expands its share.
+    unsigned long long hub_deg = 0ull;   // != 0: the source's row was split (same value on every rank)
+    uint32_t hub_cnt = 0u;
+    const int *hub_idx = nullptr;
+    bool hub_coherent = false;
+    if (level == 0 && P > 1) {
+        const uint32_t src = (uint32_t)s->src;
+        const int owner0 = (int)part.owner(src);
+        uint32_t chunk = 0u, rb = 0u;
+        if (owner0 == me) {
+            const uint32_t r = part.row(src);
+            rb = __ldg(a.offsets + r);
+            const uint32_t deg = __ldg(a.offsets + r + 1) - rb;
+            chunk = ((deg + (uint32_t)P - 1u) / (uint32_t)P + 3u) & ~3u;
+            if ((long long)deg >= s->hub_min && 2ull * chunk <= part.n_local) {
+                hub_deg = deg;
+                for (int p = 0; p < P; ++p) {
+                    if (p == me) continue;
+                    const uint32_t pb = (uint32_t)p * chunk;
+                    const uint32_t cnt = pb >= deg ? 0u : (deg - pb < chunk ? deg - pb : chunk);
+                    int *stage = reinterpret_cast<int *>(a.peers.base[p] + a.off_inbox) + (size_t)me * part.n_local + (part.n_local - chunk);
+                    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x)
+                        stage[i] = __ldg(a.indices + rb + pb + i);
+                }
+            }
+        }
+        if (!small_grid_barrier(sh, &s_gen, true)) hub_deg = 0ull;
+        ++bar_epoch;
+        if (blockIdx.x == 0 && threadIdx.x < (unsigned)P && (int)threadIdx.x != me) {
+            Ctrl *pc = reinterpret_cast<Ctrl *>(a.peers.base[threadIdx.x]);
+            if (owner0 == me) st_relaxed_sys(&pc->hub_degree, hub_deg);
+            st_release_sys(&pc->flags[me], bar_epoch);
+        }
+        const bool ok0 = small_wait_peers(a, bar_epoch);
+        if (owner0 != me) hub_deg = ok0 ? ld_relaxed_sys(&my_ctrl->hub_degree) : 0ull;
+        if (hub_deg) {
+            const uint32_t deg = (uint32_t)hub_deg;
+            chunk = ((deg + (uint32_t)P - 1u) / (uint32_t)P + 3u) & ~3u;
+            const uint32_t pb = (uint32_t)me * chunk;
+            hub_cnt = pb >= deg ? 0u : (deg - pb < chunk ? deg - pb : chunk);
+            if (owner0 == me) {
+                hub_idx = a.indices + rb + pb;
+            } else {
+                hub_idx = my_inbox + (size_t)owner0 * part.n_local + (part.n_local - chunk);
+                hub_coherent = true;
+            }
+        }
+    }
+
     for (;;) {
         SmallCounters *c = &sh->slot[level & (SMALL_SLOTS - 1)];
         if (lead) small_zero_slot(&sh->slot[(level + 1) & (SMALL_SLOTS - 1)]);   // last used three levels ago
@@ -542,14 +602,15 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
         // the per-arc step of a warp over arcs [b, e) of one row piece, 32 * U arcs at a time: all index loads, then all
         // probes, then all claims are in flight together; the winners are counted per destination over the whole tile and
         // every destination's slots are reserved with ONE atomic, the P atomics issued side by side by lanes 0 .. P-1
-        auto expand = [&](uint32_t b, uint32_t e) {
+        // (idx: the local col_indices, or -- coherent -- a piece of the source's row a peer staged in this rank's heap)
+        auto expand = [&](const int *idx, bool coherent, uint32_t b, uint32_t e) {
             for (uint32_t e0 = b; e0 < e; e0 += 32u * U) {
                 int d[U], owner[U];
                 uint32_t kb[U], w[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const uint32_t ee = e0 + 32u * u + lane;
-                    d[u] = ee < e ? __ldg(a.indices + ee) : -1;
+                    d[u] = ee < e ? (coherent ? __ldcg(idx + ee) : __ldg(idx + ee)) : -1;
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -615,16 +676,27 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
             // may hold a line of an earlier level, so they are read through L2)
             const uint32_t r = (uint32_t)__ldcg(in + i) >> part.log_p;
             const uint32_t b = __ldg(a.offsets + r), e = __ldg(a.offsets + r + 1);
+            if (hub_deg && level == 0) continue;     // the source's row was split over the ranks: see pass 2
             if (e - b > SMALL_ROW) {
                 if (lane == 0) a.big[atomicAdd(&c->big_cnt, 1ull)] = r;
                 continue;
             }
-            if (e > b) expand(b, e);
+            if (e > b) expand(a.indices, false, b, e);
         }
-        if (!small_grid_barrier(sh, &s_gen)) break;
+        // (system scope: when no long row was queued this is already the "sends are out" barrier)
+        if (!small_grid_barrier(sh, &s_gen, true)) break;
         // ---- pass 2: the pieces of the long rows, dealt round-robin over the warps of the grid
-        {
-            const uint32_t nbig = (uint32_t)ld_volatile_u64(&c->big_cnt);
+        const uint32_t nbig = (uint32_t)ld_volatile_u64(&c->big_cnt);
+        const bool hub_level = hub_deg != 0ull && level == 0;
+        if (hub_level) {
+            // this rank's share of the source's row (from its own CSR on the owner, from the staged copy elsewhere)
+            const uint32_t pieces = (hub_cnt + SMALL_ROW - 1) / SMALL_ROW;
+            for (uint32_t p = gwarp; p < pieces; p += total_warps) {
+                const uint32_t pb = p * SMALL_ROW;
+                expand(hub_idx, hub_coherent, pb, hub_cnt - pb > SMALL_ROW ? pb + SMALL_ROW : hub_cnt);
+            }
+        }
+        if (nbig) {
             uint32_t skew = 0;
             for (uint32_t k = 0; k < nbig; ++k) {
                 const uint32_t r = __ldcg(a.big + k);
@@ -632,13 +704,14 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
                 const uint32_t pieces = (e - b + SMALL_ROW - 1) / SMALL_ROW;
                 for (uint32_t p = (gwarp + total_warps - skew) % total_warps; p < pieces; p += total_warps) {
                     const uint32_t pb = b + p * SMALL_ROW;
-                    expand(pb, e - pb > SMALL_ROW ? pb + SMALL_ROW : e);
+                    expand(a.indices, false, pb, e - pb > SMALL_ROW ? pb + SMALL_ROW : e);
                 }
                 skew = (skew + pieces) % total_warps;
             }
         }
-        __threadfence_system();          // this thread's stores into the peers' inboxes, before the flag
-        if (!small_grid_barrier(sh, &s_gen)) break;
+        if (nbig || hub_level) {
+            if (!small_grid_barrier(sh, &s_gen, true)) break;   // (system scope: the stores into the peers' inboxes, before the flag)
+        }
         // ---- everybody's sends are out: counts + flag to every peer, then wait for theirs
         ++bar_epoch;
         if (blockIdx.x == 0 && threadIdx.x < (unsigned)P && (int)threadIdx.x != me) {
@@ -654,31 +727,55 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
             if (q == me) continue;
             const unsigned long long cnt = ld_relaxed_sys(&my_ctrl->counts[q]);
             const int *seg = my_inbox + (size_t)q * part.n_local;
-            for (unsigned long long base = (unsigned long long)gwarp * 32ull; base < cnt; base += (unsigned long long)total_warps * 32ull) {
-                const unsigned long long i = base + lane;
-                bool fresh = false;
-                int u = -1;
-                if (i < cnt) {
-                    u = __ldcg(seg + i);
-                    const uint32_t r = part.row((uint32_t)u), bit = 1u << (r & 31);
-                    fresh = !(a.done[r >> 5] & bit) && !(atomicOr(a.done + (r >> 5), bit) & bit);
+            // a warp takes 32 * G entries at a time and reserves their frontier slots with ONE atomic (a same-address
+            // atomic per 32 entries was what the absorb of level 0 -- 0.5 M ids -- spent its 30 us on)
+            constexpr int G = 8;
+            for (unsigned long long base = (unsigned long long)gwarp * (32ull * G); base < cnt; base += (unsigned long long)total_warps * (32ull * G)) {
+                int u[G];
+                unsigned mask[G];
+                uint32_t tot = 0u, dw[G], old[G];
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    const unsigned long long i = base + 32ull * j + lane;
+                    u[j] = i < cnt ? __ldcg(seg + i) : -1;
+                }
+#pragma unroll
+                for (int j = 0; j < G; ++j) {          // all probes of `done` in flight
+                    dw[j] = 0xffffffffu;
+                    if (u[j] >= 0) dw[j] = a.done[part.row((uint32_t)u[j]) >> 5];
+                }
+#pragma unroll
+                for (int j = 0; j < G; ++j) {          // then all claims
+                    const uint32_t r = part.row((uint32_t)(u[j] >= 0 ? u[j] : 0)), bit = 1u << (r & 31);
+                    old[j] = 0xffffffffu;
+                    if (u[j] >= 0 && !(dw[j] & bit)) old[j] = atomicOr(a.done + (r >> 5), bit);
+                }
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    const uint32_t r = part.row((uint32_t)(u[j] >= 0 ? u[j] : 0)), bit = 1u << (r & 31);
+                    const bool fresh = !(old[j] & bit);
                     if (fresh) {
                         a.labels[r] = next_label;
                         atomicOr(a.known + (size_t)me * a.wl + (r >> 5), bit);
                         deg_sum += __ldg(a.offsets + r + 1) - __ldg(a.offsets + r);
+                    } else {
+                        u[j] = -1;
                     }
+                    mask[j] = __ballot_sync(FULL_MASK, fresh);
+                    tot += __popc(mask[j]);
                 }
-                const unsigned mask = __ballot_sync(FULL_MASK, fresh);
-                if (mask) {
-                    unsigned long long pos0 = 0;
-                    const unsigned leader = __ffs(mask) - 1;
-                    if (lane == leader) pos0 = atomicAdd(&c->next_cnt, (unsigned long long)__popc(mask));
-                    pos0 = __shfl_sync(FULL_MASK, pos0, leader);
-                    if (fresh) {
-                        const unsigned long long pos = pos0 + __popc(mask & lt_mask);
-                        if (pos < part.n_local) out[pos] = u;
+                if (tot == 0u) continue;
+                unsigned long long pos0 = 0;
+                if (lane == 0) pos0 = atomicAdd(&c->next_cnt, (unsigned long long)tot);
+                pos0 = __shfl_sync(FULL_MASK, pos0, 0);
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    if (u[j] >= 0) {
+                        const unsigned long long pos = pos0 + __popc(mask[j] & lt_mask);
+                        if (pos < part.n_local) out[pos] = u[j];
                         else c->overflow = 1ull;
                     }
+                    pos0 += __popc(mask[j]);
                 }
             }
         }
@@ -747,6 +844,7 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
             r->discovered = found;
             r->sent = sent_all;
         }
+        loop_trace(&s->dyn, 64u + ((unsigned)level & 63u));   // level `level` closed
         total_arcs += arcs;
         launches += 1;
         ++level;
@@ -773,16 +871,16 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
         if (to_pull) {
             // the new frontier as this rank's bitmap slice (the first pull level gathers the slices), and the rows
             // without in-arcs count as done from here on (engine.cuh): pull levels skip them
+            // (The slice is NOT cleared first: the prologue zeroes both slices, and whatever a big push level or an earlier
+            // pull phase of THIS traversal left there are vertices of earlier levels, all of whose neighbours are visited --
+            // as frontier bits they cannot label anybody.)
             uint32_t *slice_w = reinterpret_cast<uint32_t *>(a.peers.base[me] + (bsel ? a.off_slice0 : a.off_slice1));
-            for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < a.wl; w += gridDim.x * blockDim.x) slice_w[w] = 0u;
             or_no_in_arc_words(blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, a.pull_offsets, part.n_local, a.iso, a.done);
-            if (!small_grid_barrier(sh, &s_gen)) break;
             for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
                 const uint32_t r = part.row((uint32_t)__ldcg(in + i));
                 atomicOr(slice_w + (r >> 5), 1u << (r & 31));
             }
-            __threadfence_system();
-            if (!small_grid_barrier(sh, &s_gen)) break;
+            if (!small_grid_barrier(sh, &s_gen, true)) break;
             ++bar_epoch;
             if (blockIdx.x == 0 && threadIdx.x < (unsigned)P && (int)threadIdx.x != me)
                 st_release_sys(&reinterpret_cast<Ctrl *>(a.peers.base[threadIdx.x])->flags[me], bar_epoch);
@@ -843,7 +941,10 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
 // bitmap slice -- one pass, word-wise, with the look-back scan of tile_scan.cuh.  Replaces the routed flush
 // + publish + absorb + list -> slice of the vertex-id exchange, whose per-rank cost did not shrink with P.
 // ---------------------------------------------------------------------------------------------
-template <int NT, int VT>
+// DEG: also sum the degrees of the new vertices (the push -> pull decision of a direction-optimising traversal needs
+// it; a push-only traversal does not, and the two dependent offset loads per vertex made this kernel latency-bound:
+// 349 us for 14 M new vertices per rank in the 2-GPU trace)
+template <int NT, int VT, bool DEG>
 __global__ void __launch_bounds__(NT) p2p_absorb_bits_kernel(Peers peers, size_t off_known, int me, int P, uint32_t wl,
                                                              uint32_t *__restrict__ done, uint32_t *slice0, uint32_t *slice1,
                                                              int *__restrict__ labels, const uint32_t *__restrict__ offsets,
@@ -927,7 +1028,7 @@ __global__ void __launch_bounds__(NT) p2p_absorb_bits_kernel(Peers peers, size_t
                 bits &= bits - 1;
                 const uint32_t r = r0 + b;
                 labels[r] = next_label;
-                deg_sum += __ldg(offsets + r + 1) - __ldg(offsets + r);
+                if (DEG) deg_sum += __ldg(offsets + r + 1) - __ldg(offsets + r);
                 if (dest < capacity) out[dest] = (int)part.global_id((uint32_t)me, r);
                 else over = true;
                 ++dest;
@@ -1064,8 +1165,7 @@ __global__ void __launch_bounds__(PULL_NT, 4) p2p_pull_levels_kernel(PullArgs a)
         loop_trace(&s->dyn, 32);
         bfs_pull_body<PULL_NT, true>(part.n_local, a.pull_offsets, a.pull_indices, a.full, slice[bsel ^ 1u], a.done, a.labels, level + 1,
                                      c->c, part, a.first_nbr);
-        __threadfence_system();          // the new slice, before the flag that tells the peers it is complete
-        if (!small_grid_barrier(sh, &s_gen)) break;
+        if (!small_grid_barrier(sh, &s_gen, true)) break;   // (system scope: the new slice, before the flag that says it is complete)
         // ---- level summary: row to every peer, flags, sums
         next_local = ld_volatile_u64(&c->c[B200_CNT_OUT]);
         const int parity = (int)(stats_seq & 1u);
@@ -1119,6 +1219,7 @@ __global__ void __launch_bounds__(PULL_NT, 4) p2p_pull_levels_kernel(PullArgs a)
             r->discovered = found;
             r->sent = 0;
         }
+        loop_trace(&s->dyn, 64u + ((unsigned)level & 63u));   // level `level` closed
         total_arcs += arcs;
         launches += 1;
         ++level;
@@ -1132,9 +1233,41 @@ __global__ void __launch_bounds__(PULL_NT, 4) p2p_pull_levels_kernel(PullArgs a)
         const bool hand_over = mode == B200_BFS_BEAMER && (double)found < (double)n / beta && found < flen;
         flen = found;
         if (hand_over) {
-            // back to push: the hand-over kernels of this graph iteration fold the last discoveries into `known`
-            // and turn this rank's slice into its frontier list
-            next_run = LOOP_RUN_TO_PUSH | ((small_on && found <= small_verts) ? LOOP_RUN_SMALL : LOOP_RUN_PUSH);
+            // Back to push, inside this launch: this rank's slice of the new frontier becomes its frontier list (order is
+            // free: warp-aggregated appends, no scan) and is folded into known[own slice] -- the push kernels rely on
+            // known >= done for owned vertices.  The peers' slices are NOT folded: a vertex they found in this last pull
+            // level may be claimed and offered to its owner once more, and the owner's `done` turns it away.
+            const unsigned lane = lane_id();
+            const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, total_warps = (gridDim.x * blockDim.x) >> 5;
+            const uint32_t *fr = slice[bsel];
+            uint32_t *known_own = a.known + (size_t)me * a.wl;
+            int *list = const_cast<int *>(s->dyn.in);
+            unsigned long long *cnt = &c->c[B200_CNT_AUX2];
+            for (uint32_t w0 = gwarp * 32u; w0 < a.wl; w0 += total_warps * 32u) {
+                const uint32_t w = w0 + lane;
+                uint32_t bits = w < a.wl ? __ldcg(fr + w) : 0u;
+                if (bits) known_own[w] = __ldcg(known_own + w) | bits;
+                const uint32_t k = __popc(bits);
+                uint32_t incl = k;
+#pragma unroll
+                for (int d2 = 1; d2 < 32; d2 <<= 1) {
+                    const uint32_t t = __shfl_up_sync(FULL_MASK, incl, d2);
+                    if (lane >= (unsigned)d2) incl += t;
+                }
+                const uint32_t tot = __shfl_sync(FULL_MASK, incl, 31);
+                if (tot == 0u) continue;
+                unsigned long long base = 0;
+                if (lane == 31) base = atomicAdd(cnt, (unsigned long long)tot);
+                base = __shfl_sync(FULL_MASK, base, 31) + incl - k;
+                while (bits) {
+                    const uint32_t b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if (base < part.n_local) list[base] = (int)part.global_id((uint32_t)me, (w << 5) + b);
+                    ++base;
+                }
+            }
+            if (!small_grid_barrier(sh, &s_gen)) break;
+            next_run = (small_on && found <= small_verts) ? LOOP_RUN_SMALL : LOOP_RUN_PUSH;
             break;
         }
     }
@@ -1247,6 +1380,7 @@ __global__ void __launch_bounds__(32) p2p_stats_decide_kernel(Peers peers, int m
         r->discovered = found;
         r->sent = 0;
     }
+    loop_trace(&s->dyn, 64u + ((unsigned)level & 63u));   // level `level` closed
     s->total_arcs += arcs;
     s->launches += s->kernels_per_level;
     ++level;
@@ -1279,7 +1413,8 @@ __global__ void __launch_bounds__(32) p2p_stats_decide_kernel(Peers peers, int m
                 trans = LOOP_RUN_TO_PULL;   // (the gather of the first pull level also applies the no-in-arc preset)
                 s->dyn.bsel ^= 1u;          // the slice written this level is the frontier of the first pull level
             } else {
-                next_small = s->small_on && next_deg <= s->small_arcs;
+                // (push-only traversals do not sum the degrees of what they find: the vertex count stands in)
+                next_small = s->small_on && (s->mode == B200_BFS_BEAMER ? next_deg <= s->small_arcs : found <= s->small_verts);
             }
         } else {
             s->dyn.bsel ^= 1u;
@@ -1343,7 +1478,8 @@ cudaError_t preload_kernels() {
     if ((e = preload(p2p_loop_init_kernel)) != cudaSuccess) return e;
     if ((e = preload(p2p_small_levels_kernel)) != cudaSuccess) return e;
     if ((e = preload(p2p_pull_levels_kernel)) != cudaSuccess) return e;
-    if ((e = preload(p2p_absorb_bits_kernel<COMPACT_NT, BITLIST_VT>)) != cudaSuccess) return e;
+    if ((e = preload(p2p_absorb_bits_kernel<COMPACT_NT, BITLIST_VT, true>)) != cudaSuccess) return e;
+    if ((e = preload(p2p_absorb_bits_kernel<COMPACT_NT, BITLIST_VT, false>)) != cudaSuccess) return e;
     if ((e = preload(quad_advance_kernel<BfsClaimPartQ, OUT_NONE, false, QUAD_NT, VT, QUAD_WSEG>)) != cudaSuccess) return e;
     if ((e = preload(p2p_gather_or_dyn_kernel)) != cudaSuccess) return e;
     if ((e = preload(p2p_stats_decide_kernel)) != cudaSuccess) return e;
@@ -1388,6 +1524,8 @@ struct b200_p2p_bfs {
     cudaGraph_t graph;
     cudaGraphExec_t exec;
     unsigned long long *d_trace;
+    unsigned long long *h_trace;       // host copy of the last traced run: [0] = entries, then (globaltimer ns << 8 | id)
+    int trace_on;                      // b200_p2p_bfs_set_trace
     const void *k_offsets, *k_indices, *k_labels, *k_scratch, *k_iso, *k_first, *k_pull_offsets, *k_pull_indices;
     uint64_t k_gen;            // b200_ctx::scratch_gen the graph was built against
     int k_mode;
@@ -1433,15 +1571,45 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
     LL_CUDA(cudaGraphCreate(&G, 0));
     LL_CUDA(cudaGraphConditionalHandleCreate(&h_while, G, 1, cudaGraphCondAssignDefault));
 
+    // the persistent small-level kernel (consecutive SMALL push levels, vertex ids through the inboxes): once in the
+    // prologue (level 0 is always small) and as the LAST node of the loop body, so that the iteration it finishes the
+    // traversal in ends there -- no trailing idle nodes
+    SmallArgs sa;
+    std::memset(&sa, 0, sizeof sa);
+    sa.peers = s->peers;
+    sa.me = me;
+    sa.P = P;
+    sa.part = part;
+    sa.offsets = g->row_offsets;
+    sa.indices = g->col_indices;
+    sa.known = s->known;
+    sa.done = s->done;
+    sa.labels = d_labels;
+    sa.s = s->d_lstate;
+    sa.sh = s->small;
+    sa.big = s->big_rows;
+    sa.off_inbox = s->off_inbox;
+    sa.off_slice0 = s->off_slice[0];
+    sa.off_slice1 = s->off_slice[1];
+    sa.wl = s->wl;
+    sa.iso = g->no_in_arc_bitmap;
+    sa.pull_offsets = pull_off;
+    sa.res = s->d_lresult;
+    sa.h_while = h_while;
+    sa.pull_slots = s->pull_slots;
+
     // ---- prologue
     LL_CUDA(cudaStreamBeginCaptureToGraph(cs, G, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
     capturing = true;
     LL_CUDA(cudaMemsetAsync(d_labels, 0xFF, sizeof(int32_t) * (size_t)s->n_local, cs));
     LL_CUDA(cudaMemsetAsync(s->known, 0, (size_t)(s->n_global / 8), cs));
     LL_CUDA(cudaMemsetAsync(s->done, 0, sizeof(uint32_t) * (size_t)s->wl, cs));
+    LL_CUDA(cudaMemsetAsync(s->heap + s->off_slice[0], 0, s->off_known - s->off_slice[0], cs));   // both frontier slices
     p2p_loop_init_kernel<<<1, 1, 0, cs>>>(s->d_lparams, s->d_lstate, d_labels, s->known, s->done, ctx->frontier[0], ctx->frontier[1],
                                           (long long)s->n_global, part, ws->d_counters, ws->d_tile_counter, s->small,
                                           s->pull_slots, kernels_per_level);
+    LL_CUDA(cudaGetLastError());
+    p2p_small_levels_kernel<<<(unsigned)s->small_grid, SMALL_NT, 0, cs>>>(sa);
     LL_CUDA(cudaGetLastError());
     capturing = false;
     if ((st = end_capture(cs, deps, &ndeps, 8)) != B200_OK) goto fail;
@@ -1457,33 +1625,6 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
     LL_CUDA(cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
     capturing = true;
     {
-        // (1) consecutive SMALL push levels in one persistent kernel (vertex ids through the inboxes)
-        SmallArgs sa;
-        std::memset(&sa, 0, sizeof sa);
-        sa.peers = s->peers;
-        sa.me = me;
-        sa.P = P;
-        sa.part = part;
-        sa.offsets = g->row_offsets;
-        sa.indices = g->col_indices;
-        sa.known = s->known;
-        sa.done = s->done;
-        sa.labels = d_labels;
-        sa.s = s->d_lstate;
-        sa.sh = s->small;
-        sa.big = s->big_rows;
-        sa.off_inbox = s->off_inbox;
-        sa.off_slice0 = s->off_slice[0];
-        sa.off_slice1 = s->off_slice[1];
-        sa.wl = s->wl;
-        sa.iso = g->no_in_arc_bitmap;
-        sa.pull_offsets = pull_off;
-        sa.res = s->d_lresult;
-        sa.h_while = h_while;
-        sa.pull_slots = s->pull_slots;
-        p2p_small_levels_kernel<<<(unsigned)s->small_grid, SMALL_NT, 0, cs>>>(sa);
-        LL_CUDA(cudaGetLastError());
-
         // (2) a BIG push level: quad scan, quad advance that only claims bits in `known`, then the bitmap exchange
         const int64_t max_tiles = (s->n_local + SCAN_NT * SCAN_VT - 1) / (SCAN_NT * SCAN_VT);
         int64_t grid = (int64_t)ws->num_sms * 8;
@@ -1497,11 +1638,16 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
         BfsClaimPartQ op{s->known, part};
         LL_CUDA((launch_quad_advance<OUT_NONE, false>(ws, a, op, nullptr, 0ull)));
         const int64_t atiles = ((int64_t)s->wl + COMPACT_NT * BITLIST_VT - 1) / (COMPACT_NT * BITLIST_VT);
-        int64_t agrid = (int64_t)ws->num_sms * 8;
+        int64_t agrid = (int64_t)ws->num_sms * 4;   // (a persistent tile loop; an idle node of 148 x 8 CTAs cost 3.7 us)
         if (agrid > atiles) agrid = atiles;
-        p2p_absorb_bits_kernel<COMPACT_NT, BITLIST_VT><<<(unsigned)agrid, COMPACT_NT, 0, cs>>>(
-            s->peers, s->off_known, me, P, s->wl, s->done, slice0, slice1, d_labels, g->row_offsets, part, s->d_lstate, s->small,
-            (unsigned long long)s->n_local, s->absorb_status, ws->d_counters);
+        if (beamer)
+            p2p_absorb_bits_kernel<COMPACT_NT, BITLIST_VT, true><<<(unsigned)agrid, COMPACT_NT, 0, cs>>>(
+                s->peers, s->off_known, me, P, s->wl, s->done, slice0, slice1, d_labels, g->row_offsets, part, s->d_lstate, s->small,
+                (unsigned long long)s->n_local, s->absorb_status, ws->d_counters);
+        else
+            p2p_absorb_bits_kernel<COMPACT_NT, BITLIST_VT, false><<<(unsigned)agrid, COMPACT_NT, 0, cs>>>(
+                s->peers, s->off_known, me, P, s->wl, s->done, slice0, slice1, d_labels, g->row_offsets, part, s->d_lstate, s->small,
+                (unsigned long long)s->n_local, s->absorb_status, ws->d_counters);
         LL_CUDA(cudaGetLastError());
         // (3) level summary across the ranks + decision of a big push level
         p2p_stats_decide_kernel<<<1, 32, 0, cs>>>(s->peers, me, P, s->d_lstate, ws->d_counters, ws->d_tile_counter, s->small,
@@ -1535,22 +1681,9 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
             p2p_pull_levels_kernel<<<(unsigned)s->pull_grid, PULL_NT, 0, cs>>>(pa);
             LL_CUDA(cudaGetLastError());
         }
-        if (beamer) {
-            // (5) pull -> push hand-over
-            p2p_gather_or_dyn_kernel<<<ws->num_sms * 4, 256, 0, cs>>>(s->peers, s->off_slice[0], s->off_slice[1], s->wl / 4, P, me, dyn,
-                                                                      (uint32_t)LOOP_RUN_TO_PUSH, reinterpret_cast<uint4 *>(s->full),
-                                                                      reinterpret_cast<uint4 *>(s->known), s->done,
-                                                                      g->no_in_arc_bitmap, pull_off);
-            LL_CUDA(cudaGetLastError());
-            const int64_t ctiles = ((int64_t)s->wl + COMPACT_NT * BITLIST_VT - 1) / (COMPACT_NT * BITLIST_VT);
-            int64_t cgrid = (int64_t)ws->num_sms * 8;
-            if (cgrid > ctiles) cgrid = ctiles;
-            bitmap_list_dyn_kernel<COMPACT_NT, BITLIST_VT><<<(unsigned)cgrid, COMPACT_NT, 0, cs>>>(
-                BitmapWordsDyn{dyn, slice0, slice1}, PartItem{part}, s->wl, dyn, (uint32_t)LOOP_RUN_TO_PUSH,
-                (unsigned long long)s->n_local, ws->d_status, ws->d_tile_counter + 1, ws->d_counters + B200_CNT_AUX2,
-                ws->d_counters + B200_CNT_OVERFLOW, nullptr);
-            LL_CUDA(cudaGetLastError());
-        }
+        // (5) the small levels that follow (the tail of the traversal, usually)
+        p2p_small_levels_kernel<<<(unsigned)s->small_grid, SMALL_NT, 0, cs>>>(sa);
+        LL_CUDA(cudaGetLastError());
     }
     capturing = false;
     if ((st = end_capture(cs, deps, &ndeps, 8)) != B200_OK) goto fail;
@@ -1633,7 +1766,7 @@ int p2p_run_graph(b200_p2p_bfs *s, const b200_graph *g, int64_t m_global, int32_
     pr->bar_epoch0 = s->epoch;
     pr->lb_epoch0 = ws->epoch + 1;
     pr->stats_seq0 = s->stats_seq;
-    const bool want_trace = getenv("B200_LOOP_TRACE") != nullptr;   // (read per run)
+    const bool want_trace = getenv("B200_LOOP_TRACE") != nullptr || s->trace_on;   // (read per run)
     constexpr uint32_t TRACE_CAP = 4096;
     if (want_trace && !s->d_trace) B200_CUDA(cudaMalloc(&s->d_trace, sizeof(unsigned long long) * TRACE_CAP));
     pr->trace = want_trace ? s->d_trace : nullptr;
@@ -1644,6 +1777,7 @@ int p2p_run_graph(b200_p2p_bfs *s, const b200_graph *g, int64_t m_global, int32_
     const long long env_small = getenv("B200_P2P_SMALL") ? atoll(getenv("B200_P2P_SMALL")) : 1;
     const long long env_arcs = getenv("B200_P2P_SMALL_ARCS") ? atoll(getenv("B200_P2P_SMALL_ARCS")) : (2ll << 20);
     const long long env_verts = getenv("B200_P2P_SMALL_VERTS") ? atoll(getenv("B200_P2P_SMALL_VERTS")) : (64ll << 10);
+    pr->hub_min = getenv("B200_P2P_HUB_MIN") ? atoll(getenv("B200_P2P_HUB_MIN")) : (32ll << 10);
     pr->small_on = env_small != 0 ? 1u : 0u;
     pr->small_arcs = env_arcs;
     pr->small_verts = env_verts;
@@ -1655,21 +1789,21 @@ int p2p_run_graph(b200_p2p_bfs *s, const b200_graph *g, int64_t m_global, int32_
     B200_CUDA(cudaEventSynchronize(s->ev_run[1]));
     const P2PLoopResult *r = s->h_lresult;
     if (r->status < 0) return B200_ERR_CUDA;
-    const bool trace_all = want_trace && !strcmp(getenv("B200_LOOP_TRACE"), "all");
-    if (want_trace && (s->rank == 0 || trace_all)) {   // debug aid: kernel-entry timeline (ids: see loop_trace call sites)
-        unsigned long long *h = new (std::nothrow) unsigned long long[TRACE_CAP];
-        if (!h) return B200_ERR_NOMEM;
-        cudaError_t ce = cudaMemcpy(h, s->d_trace, sizeof(unsigned long long) * TRACE_CAP, cudaMemcpyDeviceToHost);
-        if (ce != cudaSuccess) {
-            delete[] h;
-            return cuda_status(ce);
-        }
-        const unsigned long long cnt = h[0] < TRACE_CAP - 1 ? h[0] : TRACE_CAP - 1;
+    const char *tenv = getenv("B200_LOOP_TRACE");
+    const bool trace_all = tenv && !strcmp(tenv, "all");
+    if (want_trace) {
+        if (!s->h_trace) s->h_trace = new (std::nothrow) unsigned long long[TRACE_CAP];
+        if (!s->h_trace) return B200_ERR_NOMEM;
+        B200_CUDA(cudaMemcpy(s->h_trace, s->d_trace, sizeof(unsigned long long) * TRACE_CAP, cudaMemcpyDeviceToHost));
+        if (s->h_trace[0] > TRACE_CAP - 1) s->h_trace[0] = TRACE_CAP - 1;
+    }
+    if (tenv && (s->rank == 0 || trace_all)) {   // debug aid: kernel-entry timeline (ids: see loop_trace call sites)
+        const unsigned long long *h = s->h_trace;
+        const unsigned long long cnt = h[0];
         fprintf(stderr, "B200_LOOP_TRACE rank%d %llu entries (us since first, kernel id):", s->rank, cnt);
         for (unsigned long long i = 1; i <= cnt; ++i)
             fprintf(stderr, " %.1f:%llu", (double)((h[i] >> 8) - (h[1] >> 8)) * 1e-3, h[i] & 255ull);
         fprintf(stderr, "\n");
-        delete[] h;
     }
     s->epoch = r->bar_epoch;
     s->stats_seq = r->stats_seq;
@@ -1857,9 +1991,27 @@ int b200_p2p_bfs_destroy(b200_p2p_bfs *s) {
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
     if (s->d_lstate) cudaFree(s->d_lstate);
     if (s->d_trace) cudaFree(s->d_trace);
+    delete[] s->h_trace;
     if (s->h_lparams) cudaFreeHost(s->h_lparams);
     if (s->h_lresult) cudaFreeHost(s->h_lresult);
     delete s;
+    return B200_OK;
+}
+
+int b200_p2p_bfs_set_trace(b200_p2p_bfs *s, int on) {
+    if (!s) return B200_ERR_INVALID;
+    s->trace_on = on != 0;
+    return B200_OK;
+}
+
+int b200_p2p_bfs_last_trace(b200_p2p_bfs *s, uint64_t *entries, int64_t capacity, int64_t *count) {
+    if (!s || !count || capacity < 0 || (capacity && !entries)) return B200_ERR_INVALID;
+    *count = 0;
+    if (!s->h_trace) return B200_OK;
+    int64_t n = (int64_t)s->h_trace[0];
+    if (n > capacity) n = capacity;
+    for (int64_t i = 0; i < n; ++i) entries[i] = (uint64_t)s->h_trace[i + 1];
+    *count = n;
     return B200_OK;
 }
 

@@ -127,6 +127,8 @@ def load_library():
         "b200_p2p_bfs_run": ([vp, pg, i64, i32, i32, f32, f32, vp, ps, pi64], i32),
         "b200_p2p_bfs_prepare": ([vp, pg, i32, vp], i32),
         "b200_p2p_bfs_destroy": ([vp], i32),
+        "b200_p2p_bfs_set_trace": ([vp, i32], i32),
+        "b200_p2p_bfs_last_trace": ([vp, vp, i64, vp], i32),
         "b200_mtx_load": ([C.c_char_p, i32, C.POINTER(CHostCSR)], i32),
         "b200_csr_cache_write": ([C.c_char_p, C.POINTER(CHostCSR)], i32),
         "b200_csr_cache_read": ([C.c_char_p, C.POINTER(CHostCSR)], i32),

@@ -76,6 +76,30 @@ class P2PBfs:
         self.device_ms, self.launches, self.level_loop = st.device_ms, st.launches, st.level_loop
         return st.num_levels
 
+    def set_trace(self, on: bool = True):
+        L._check(self._L.b200_p2p_bfs_set_trace(self._h, int(on)), "b200_p2p_bfs_set_trace")
+
+    def last_trace(self):
+        """[(microseconds since the first entry, id)] of the last traced run (ids: include/b200_frontier.h)."""
+        cap = 4096
+        buf = (C.c_uint64 * cap)()
+        n = C.c_int64()
+        L._check(self._L.b200_p2p_bfs_last_trace(self._h, buf, cap, C.byref(n)), "b200_p2p_bfs_last_trace")
+        if n.value == 0:
+            return []
+        t0 = buf[0] >> 8
+        return [(((buf[i] >> 8) - t0) * 1e-3, int(buf[i] & 255)) for i in range(n.value)]
+
+    def level_times_ms(self):
+        """Per-level device time of the last traced run, from the "level closed" markers (64 + level)."""
+        tr = self.last_trace()
+        out, prev = [], 0.0
+        for t, k in tr:
+            if k >= 64:
+                out.append((t - prev) * 1e-3)
+                prev = t
+        return out
+
     def close(self):
         if getattr(self, "_h", None):
             self._L.b200_p2p_bfs_destroy(self._h)

@@ -32,12 +32,12 @@ def dump(name, obj):
     print("wrote", name)
 
 
-def fixture(algo, undirected, src=0):
-    path = f"{REF}/{algo}/test.mtx"
+def fixture(algo, undirected, src=0, mtx="test.mtx"):
+    path = f"{REF}/{algo}/{mtx}"
     header, edges = mtx_edges(path)
     g, csc_eq = oracle.ref_load_graph(path, undirected)
     rec = {
-        "source": f"gunrock/tests/{algo}/test.mtx via load_graph(file,{str(undirected).lower()},false) graph.hxx:96-223",
+        "source": f"gunrock/tests/{algo}/{mtx} via load_graph(file,{str(undirected).lower()},false) graph.hxx:96-223",
         "mtx_header": header, "mtx_edges": edges, "undirected": undirected, "src": src,
         "n": g.n, "m": g.m, "offsets": g.offsets.tolist(), "indices": g.indices.tolist(),
         "weights": g.weights.tolist(), "csc_equals_csr": csc_eq,
@@ -74,6 +74,8 @@ if __name__ == "__main__":
     dump("ref_fixture_sssp_directed.json", fixture("sssp", False))
     dump("ref_fixture_sssp_undirected.json", fixture("sssp", True))
     dump("ref_fixture_pr.json", fixture("pr", True))
+    dump("ref_fixture_kcore.json", fixture("kcore", True, mtx="test_kcore.mtx"))
+    dump("ref_fixture_coloring.json", fixture("coloring", True))
     dump("ref_rmat_s8.json", rmat_case(8, 16, 1))
     dump("ref_rmat_s10.json", rmat_case(10, 16, 1))
     dump("ref_rmat_s16.json", rmat_case(16, 16, 1))

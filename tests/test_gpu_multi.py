@@ -86,10 +86,10 @@ def test_partitioned_bfs_other_sources(src):
     assert np.array_equal(labels, ref)
 
 
-SMALL_VARIANTS = {   # B200_P2P_SMALL / _SMALL_ARCS / _SMALL_VERTS (p2p_bfs.cu): which levels the persistent small-level kernel runs
-    "small-default": ("1", None, None),     # scale-14 graphs: every push level is "small"
-    "small-tiny": ("1", "3000", "64"),      # only the first / last levels: exercises small -> big push -> pull -> small
-    "small-off": ("0", None, None),         # every push level through scan + claim-only advance + bitmap exchange
+SMALL_VARIANTS = {   # B200_P2P_SMALL / _SMALL_ARCS / _SMALL_VERTS / _HUB_MIN (p2p_bfs.cu): which levels the persistent small-level kernel runs
+    "small-default": ("1", None, None, "64"),    # scale-14 graphs: every push level is "small"; a source row of >= 64 arcs is split over the ranks
+    "small-tiny": ("1", "3000", "64", None),     # only the first / last levels: exercises small -> big push -> pull -> small
+    "small-off": ("0", None, None, None),        # every push level through scan + claim-only advance + bitmap exchange
 }
 
 
@@ -98,8 +98,8 @@ def _virtual_ranks_p2p(scale, ef, seed, world, src, mode, repeat=2, loop="graph"
     barriers spin inside kernels, so the ranks' kernels must be able to run concurrently); heaps are
     wired by address (b200_p2p_bfs_connect with peer_bases)."""
     import mini_b200 as mb
-    on, arcs, verts = SMALL_VARIANTS[small]
-    for k, v in (("B200_P2P_SMALL", on), ("B200_P2P_SMALL_ARCS", arcs), ("B200_P2P_SMALL_VERTS", verts)):
+    on, arcs, verts, hub = SMALL_VARIANTS[small]
+    for k, v in (("B200_P2P_SMALL", on), ("B200_P2P_SMALL_ARCS", arcs), ("B200_P2P_SMALL_VERTS", verts), ("B200_P2P_HUB_MIN", hub)):
         if v is None:
             os.environ.pop(k, None)
         else:

@@ -204,6 +204,58 @@ def test_traversals_match_reference_gpu(golden, name, which):
         assert hashlib.sha256(oracle.sssp_dist(g, c["src"]).tobytes()).hexdigest() == c["sssp_dist_sha256"]
 
 
+# ---------------------------------------------------------------- kcore / coloring, oracle side
+def test_kcore_restatement_hand_cases():
+    """kcore_problem.hxx:54-105 restated (unpinned: the reference's kcore headers do not compile, see oracle.kcore).
+    Hand-computed peels, including the reference's quirk: a vertex whose degree reaches 0 only because its neighbours
+    were peeled is never numbered."""
+    star = oracle.CSR(4, [0, 3, 4, 5, 6], [1, 2, 3, 0, 0, 0])                     # centre 0, three leaves
+    cores, largest = oracle.kcore(star)
+    assert cores.tolist() == [0, 1, 1, 1] and largest == 1                        # the centre keeps 0 (quirk)
+    tri = oracle.build_csr(4, np.array([0, 1, 2, 0], np.int32), np.array([1, 2, 0, 3], np.int32), True)
+    cores, largest = oracle.kcore(tri)                                            # triangle 0-1-2 + pendant 3
+    assert cores.tolist() == [2, 2, 2, 1] and largest == 2
+    k5 = oracle.build_csr(6, *np.array([(a, b) for a in range(5) for b in range(a)], np.int32).T.copy(), True)
+    cores, largest = oracle.kcore(k5)                                             # K5 + an isolated vertex
+    assert cores.tolist() == [4, 4, 4, 4, 4, 0] and largest == 4
+    path = oracle.build_csr(5, np.arange(4, dtype=np.int32), np.arange(1, 5, dtype=np.int32), True)
+    cores, largest = oracle.kcore(path)      # k = 2 peels the two ends (core 1); the next round peels 1 and 3; vertex 2 drops to 0 un-numbered
+    assert cores.tolist() == [1, 1, 0, 1, 1] and largest == 1
+
+
+def test_kcore_on_reference_fixture(golden):
+    rec = golden("ref_fixture_kcore.json")
+    cores, largest = oracle.kcore(_csr_from(rec))
+    # tests/kcore/test_kcore.mtx lists every edge in both directions and load_graph(undirected) doubles it again:
+    # a multigraph whose degrees are twice the simple graph's
+    assert cores.tolist() == [4, 4, 6, 6, 6, 4, 6, 6, 4] and largest == 6
+
+
+def test_mt19937_hashes_match_libstdcxx():
+    """The hash stream of coloring_problem_t (mgpu::fill_random, memory.hxx:112-129): default-seeded std::mt19937
+    through std::uniform_int_distribution<int>(0, prime).  First raw words of mt19937: 3499211612, 581869302, ..."""
+    h, st = oracle.mt19937_hashes(4, 15485863)
+    scaling = (1 << 32) // 15485864
+    assert h.tolist()[:2] == [3499211612 // scaling, 581869302 // scaling]
+    h2, _ = oracle.mt19937_hashes(4, 15485863, st)             # the engine is carried on, not re-seeded
+    assert h2.tolist() != h.tolist() and h.min() >= 0 and h.max() <= 15485863
+
+
+@pytest.mark.parametrize("which", ["fixture", "rmat10"])
+def test_coloring_restatement_is_a_proper_partial_colouring(golden, which):
+    g = _csr_from(golden("ref_fixture_coloring.json")) if which == "fixture" else oracle.rmat_csr(10, 16, 1)
+    colors, lens = oracle.coloring(g, 15485863, 10)
+    assert lens == sorted(lens, reverse=True) and lens[0] < g.n
+    rows = np.repeat(np.arange(g.n), np.diff(g.offsets))
+    cols = g.indices
+    both = (colors[rows] > 0) & (colors[cols] > 0) & (rows != cols)
+    assert not np.any(colors[rows][both] == colors[cols][both])    # two coloured end points never share a colour
+    assert int((colors == 0).sum()) == (lens[-1] if lens else g.n)
+    self_loop = np.zeros(g.n, bool)
+    self_loop[rows[rows == cols]] = True
+    assert np.all(colors[self_loop] == 0)    # a vertex with a self loop is its own neighbour: never a strict extremum
+
+
 def test_push_level_restates_bfs():
     g = oracle.rmat_csr(10, 16, 1)
     labels = np.full(g.n, -1, np.int32)
