@@ -191,6 +191,20 @@ def run_reduce_leg(ctx, mb, args, peak):
     import torch
     scale = args.reduce_scale
     g = ctx.rmat_graph(scale, 16, 1)
+    plain_ms = None
+    if args.hot_columns:
+        # A/B: the plain index array first, then the same graph with the hot-column derived data (built once per graph,
+        # outside the timed region, like graph_to_device)
+        for _ in range(2):
+            ctx.pr(g, 10, False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ctx.pr(g, 10, False)
+        torch.cuda.synchronize()
+        plain_ms = 1e3 * (time.perf_counter() - t0) / 3
+        plain_top = min(l["advance_ms"] for l in [ctx.pr(g, 1, False, timing=True)[3].levels[0] for _ in range(3)])
+        ctx.prepare_hot_columns(g)
     for _ in range(2):
         ctx.pr(g, 10, False)
     torch.cuda.synchronize()
@@ -205,7 +219,10 @@ def run_reduce_leg(ctx, mb, args, peak):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     roof = _per_level(lambda: ctx.pr(g, 10, False, timing=True)[3], 3, reduce_level_bytes, peak)
-    roof["kernel"] = "quad_segreduce_kernel<float,PlusF32> (heaviest iteration: frontier = all vertices)"
+    roof["kernel"] = "quad_segreduce_kernel<float,PlusF32%s> (heaviest iteration: frontier = all vertices)" % (",HOT" if args.hot_columns else "")
+    if plain_ms is not None:
+        roof["without_hot_columns"] = {"ms_per_step": plain_ms, "top_launch_ms": plain_top,
+                                       "frac": reduce_level_bytes({"frontier_len": g.n, "arcs": g.m}) / (plain_top * 1e-3) / 1e9 / peak}
     roof["traffic"] = None
     tp = os.path.join(ROOT, "profiles", "advance_traffic.json")
     if scale == 24 and os.path.exists(tp):
@@ -546,6 +563,8 @@ def main():
     ap.add_argument("--no-ref-gpu", dest="ref_gpu", action="store_false", help="skip the reference-GPU baseline column")
     ap.add_argument("--no-ref-gpu-pr", dest="ref_gpu_pr", action="store_false", help="skip the reference GPU PR run (scale-24: ~1 min)")
     ap.add_argument("--no-seeds", dest="seeds", action="store_false", help="skip the seed-2 / seed-3 graphs")
+    ap.add_argument("--no-hot-columns", dest="hot_columns", action="store_false",
+                    help="reduce leg: plain index array only (no b200_graph_hot_columns derived data)")
     ap.add_argument("--reduce-scale", dest="reduce_scale", type=int, default=24)
     ap.add_argument("--mg-mode", dest="mg_mode", default="beamer", choices=["push", "beamer"])
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],

@@ -251,8 +251,29 @@ template <class Value, class ROp, class ValueFn>
 cudaError_t launch_quad_segreduce(b200_workspace *ws, const QuadArgs &a, ValueFn vf, Value *d_reduced, int scatter) {
     auto k = quad_segreduce_kernel<Value, ROp, ValueFn, QSEG_NT, QSEG_VT, QSEG_WSEG>;
     const int grid = persistent_grid<SegTag<Value, ROp, ValueFn>>(k, QSEG_NT, ws);
-    k<<<grid, QSEG_NT, 0, ws_stream(ws)>>>(a, vf, d_reduced, scatter, ws->d_counters);
+    k<<<grid, QSEG_NT, 0, ws_stream(ws)>>>(a, vf, d_reduced, scatter, ws->d_counters, (const Value *)nullptr, 0u);
     ws->launches++;
+    return cudaGetLastError();
+}
+
+// The same over the remapped index copy of b200_graph::hot_indices (QuadArgs::indices4 must point at it): the values
+// of the hot vertices are evaluated once into d_hot_vals and served from shared memory.  1 CTA x 1024 threads per SM.
+constexpr int QSEG_HOT_MAX = 40960;   // == B200_HOT_MAX (b200_frontier.h): 160 KB of fp32 in shared memory
+template <class Value, class ROp, class ValueFn>
+cudaError_t launch_quad_segreduce_hot(b200_workspace *ws, const QuadArgs &a, ValueFn vf, Value *d_reduced, int scatter,
+                                      const int *d_hot_ids, uint32_t hot_count, Value *d_hot_vals) {
+    constexpr int NT = 1024;
+    auto k = quad_segreduce_kernel<Value, ROp, ValueFn, NT, QSEG_VT, QSEG_WSEG, true, 1>;
+    const size_t smem = sizeof(Value) * (size_t)hot_count;
+    static unsigned long long opted_in = 0;   // per instantiation, one bit per device
+    if (!(opted_in >> (ws->device & 63) & 1ull)) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Value) * QSEG_HOT_MAX));
+        if (e != cudaSuccess) return e;
+        opted_in |= 1ull << (ws->device & 63);
+    }
+    hot_values_kernel<Value><<<(hot_count + 255) / 256, 256, 0, ws_stream(ws)>>>(vf, d_hot_ids, hot_count, d_hot_vals);
+    k<<<ws->num_sms, NT, smem, ws_stream(ws)>>>(a, vf, d_reduced, scatter, ws->d_counters, d_hot_vals, hot_count);
+    ws->launches += 2;
     return cudaGetLastError();
 }
 

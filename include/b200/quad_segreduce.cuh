@@ -72,12 +72,23 @@ struct NeighborhoodQuads {
 
 // ValueFn: Value operator()(int src, int nbr, uint32_t edge_id) -- plays Functor::get_value_to_reduce
 // (pr_functor.hxx:27-29).  counters[B200_CNT_ARCS] += arcs reduced.
-template <class Value, class ROp, class ValueFn, int NT, int VT, int WSEG>
-__global__ void __launch_bounds__(NT, B200_QSEG_MINB)
-quad_segreduce_kernel(QuadArgs a, ValueFn vf, Value *__restrict__ reduced, int scatter, unsigned long long *counters) {
+//
+// HOT (b200_graph::hot_indices, see b200_frontier.h): the index array is the remapped copy in which an occurrence of
+// hot vertex k is stored as ~k, and hot_vals[k] = the value of hot vertex k (evaluated once per launch by
+// hot_values_kernel).  The CTA copies the table into shared memory; a negative index is served from there.  The
+// plain kernel is bound by one L1 wavefront per divergent 4-byte gather (profiles/r01_ncu_segreduce_v2_quad.txt:
+// l1tex 78 % busy, L1 hit rate 11 %); on RMAT graphs 40 K hot vertices take 40 % of the gathers off that path.
+template <class Value, class ROp, class ValueFn, int NT, int VT, int WSEG, bool HOT = false, int MINB = B200_QSEG_MINB>
+__global__ void __launch_bounds__(NT, MINB)
+quad_segreduce_kernel(QuadArgs a, ValueFn vf, Value *__restrict__ reduced, int scatter, unsigned long long *counters,
+                      const Value *__restrict__ hot_vals = nullptr, uint32_t hot_count = 0) {
     constexpr int NW = NT / 32;
     __shared__ uint32_t s_win[NW][4 * WSEG];
     __shared__ unsigned long long s_sum;
+    extern __shared__ uint4 s_hot_raw[];
+    Value *s_hot = reinterpret_cast<Value *>(s_hot_raw);
+    if (HOT)
+        for (uint32_t k = threadIdx.x; k < hot_count; k += NT) s_hot[k] = hot_vals[k];
 
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5, le_mask = lanemask_lt() | (1u << lane);
     const unsigned long long Q = *a.total;
@@ -127,10 +138,14 @@ quad_segreduce_kernel(QuadArgs a, ValueFn vf, Value *__restrict__ reduced, int s
         Value x[VT];
 #pragma unroll
         for (int i = 0; i < VT; ++i) {
-            const Value v0 = (valid[i] & 1u) ? vf(src[i], d[i].x, e0[i]) : ROp::neutral();
-            const Value v1 = (valid[i] & 2u) ? vf(src[i], d[i].y, e0[i] + 1u) : ROp::neutral();
-            const Value v2 = (valid[i] & 4u) ? vf(src[i], d[i].z, e0[i] + 2u) : ROp::neutral();
-            const Value v3 = (valid[i] & 8u) ? vf(src[i], d[i].w, e0[i] + 3u) : ROp::neutral();
+            auto value_of = [&](int nbr, uint32_t e) -> Value {
+                if (HOT && nbr < 0) return s_hot[~nbr];
+                return vf(src[i], nbr, e);
+            };
+            const Value v0 = (valid[i] & 1u) ? value_of(d[i].x, e0[i]) : ROp::neutral();
+            const Value v1 = (valid[i] & 2u) ? value_of(d[i].y, e0[i] + 1u) : ROp::neutral();
+            const Value v2 = (valid[i] & 4u) ? value_of(d[i].z, e0[i] + 2u) : ROp::neutral();
+            const Value v3 = (valid[i] & 8u) ? value_of(d[i].w, e0[i] + 3u) : ROp::neutral();
             x[i] = ROp::apply(ROp::apply(v0, v1), ROp::apply(v2, v3));
             arc_cnt += __popc(valid[i]);
         }
@@ -217,6 +232,13 @@ quad_segreduce_kernel(QuadArgs a, ValueFn vf, Value *__restrict__ reduced, int s
     if (lane == 0 && arc_cnt) atomicAdd(&s_sum, arc_cnt);
     __syncthreads();
     if (threadIdx.x == 0 && s_sum) atomicAdd(&counters[B200_CNT_ARCS], s_sum);
+}
+
+// hot_vals[k] = vf(-, hot_ids[k], -): the values the HOT kernel serves from shared memory
+template <class Value, class ValueFn>
+__global__ void hot_values_kernel(ValueFn vf, const int *__restrict__ hot_ids, uint32_t hot_count, Value *hot_vals) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < hot_count) hot_vals[k] = vf(hot_ids[k], hot_ids[k], 0u);
 }
 
 }  // namespace b200

@@ -38,6 +38,39 @@ struct RefFunctorOp {
     }
 };
 
+// The same functor contract on the quad kernel's two-stage protocol (include/b200/quad_advance.cuh): a user functor has
+// no separable "cheap probe" half, so every arc inside its row becomes a stage-2 candidate (probe_eval = true) and
+// cond_advance / apply_advance run there, densely, one candidate per lane -- both always evaluated, exactly like
+// advance.hxx:57-58.  What the adapter gains over the arc-wise kernel is the quad walk: one segment search and one
+// 128-bit index load per four arcs, warp-private windows, no CTA barrier.
+// rank = the arc's position in its row; output_idx: the reference's position in the un-compacted output does not exist
+// here (the output is compacted) -- the arc id is passed, which is also unique per arc.
+template <typename Problem, typename Functor, bool idempotence>
+struct RefFunctorQ {
+    typename Problem::data_slice_t *data;
+    int iteration;
+    const int *offsets;
+    static constexpr bool WEIGHTED = false;
+    using SrcVal = b200::NoSrc;
+    using Evidence = b200::NoSrc;
+    using Token = bool;
+    using Cand = b200::CandWords<3>;   // dst, src, arc id
+    __device__ __forceinline__ SrcVal load_src(int) const { return SrcVal(); }
+    __device__ __forceinline__ Evidence probe_load(bool, SrcVal, int, int, uint32_t) const { return Evidence(); }
+    __device__ __forceinline__ bool probe_eval(Evidence, SrcVal, int, float) const { return true; }
+    __device__ __forceinline__ Cand make_cand(SrcVal, int src, int dst, uint32_t eid, float) const {
+        return Cand{{(uint32_t)dst, (uint32_t)src, eid}};
+    }
+    __device__ __forceinline__ Token claim(const Cand &c) const {
+        const int src = (int)c.w[1], dst = (int)c.w[0], eid = (int)c.w[2];
+        const int rank = eid - offsets[src];   // (dead code unless the functor reads it)
+        const bool cond = Functor::cond_advance(src, dst, eid, rank, eid, data, iteration);
+        const bool applied = Functor::apply_advance(src, dst, eid, rank, eid, data, iteration);
+        return idempotence ? true : (cond && applied);
+    }
+    __device__ __forceinline__ int finish(Token accepted, const Cand &c) const { return accepted ? (int)c.w[0] : -1; }
+};
+
 // degree scan of `input` over `offsets`; also mirrors the scan into the graph's
 // d_scanned_row_offsets like the reference does (advance.hxx:40).
 inline void scan_frontier(b200_workspace *ws, const int *frontier, size_t len, const int *offsets, int *mirror,
@@ -61,12 +94,32 @@ int advance_forward_kernel(std::shared_ptr<Problem> problem, std::shared_ptr<fro
     if (b200_ctx_reserve(context.engine(), (int64_t)len) != B200_OK) throw cuda_exception_t(cudaErrorMemoryAllocation);
     b200_workspace *ws = context.workspace();
     const int *in = input->data()->data();
+    int *out = has_output ? output->data()->data() : nullptr;
+    const unsigned long long cap = has_output ? output->capacity() : 0;
+#ifndef B200_ADVANCE_RAW_OUTPUT
+    // default: the quad kernel (the raw -1-holed layout and index arrays that are not 16-byte aligned take the
+    // arc-wise kernel below; -DB200_ADVANCE_LBS forces it)
+#ifndef B200_ADVANCE_LBS
+    if ((reinterpret_cast<uintptr_t>(g.d_col_indices.data()) & 15u) == 0) {
+        const uint32_t *off = reinterpret_cast<const uint32_t *>(g.d_row_offsets.data());
+        detail::check(b200::reset_counters(ws));
+        detail::check(b200::launch_quad_scan(ws, in, (uint32_t)len, off));
+        const b200::QuadArgs qa = b200::make_quad_args(ws, in, (uint32_t)len, off, g.d_col_indices.data(), nullptr);
+        detail::RefFunctorQ<Problem, Functor, idempotence> qop{problem->d_data_slice.data(), iteration, g.d_row_offsets.data()};
+        if (has_output) detail::check((b200::launch_quad_advance<b200::OUT_COMPACT, false>(ws, qa, qop, out, cap)));
+        else detail::check((b200::launch_quad_advance<b200::OUT_NONE, false>(ws, qa, qop, nullptr, 0ull)));
+        detail::check(b200::read_counters(ws));
+        if (!has_output) return 0;
+        const size_t produced = (size_t)ws->h_counters[B200_CNT_OUT];
+        output->resize(produced);   // prints the reference's overflow message and exits if it does not fit
+        return (int)produced;
+    }
+#endif
+#endif
     detail::scan_frontier(ws, in, len, g.d_row_offsets.data(), g.d_scanned_row_offsets.data(), g.d_scanned_row_offsets.size());
     const b200::LbsArgs a = b200::make_lbs_args(ws, in, (uint32_t)len, reinterpret_cast<const uint32_t *>(g.d_row_offsets.data()),
                                                 g.d_col_indices.data());
     detail::RefFunctorOp<Problem, Functor, idempotence> op{problem->d_data_slice.data(), iteration};
-    int *out = has_output ? output->data()->data() : nullptr;
-    const unsigned long long cap = has_output ? output->capacity() : 0;
     if (!has_output) {
         detail::check(b200::launch_lbs_advance<b200::OUT_NONE, false>(ws, a, op, out, cap));
     } else {

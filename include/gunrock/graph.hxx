@@ -76,6 +76,9 @@ struct graph_device_t {
         g.row_values = d_row_values.data();
         g.no_in_arc_bitmap = nullptr;   // the engine derives it per traversal
         g.first_in_neighbor = nullptr;
+        g.hot_ids = nullptr;
+        g.hot_indices = nullptr;
+        g.hot_count = 0;
         return g;
     }
 };

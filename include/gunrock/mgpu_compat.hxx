@@ -88,7 +88,9 @@ class standard_context_t : public context_t {
     void synchronize() override { throw_on_error(cudaStreamSynchronize(_stream)); }
     void *alloc(size_t bytes, memory_space_t space) override {
         void *p = nullptr;
-        if (bytes) throw_on_error(space == memory_space_device ? cudaMalloc(&p, bytes) : cudaMallocHost(&p, bytes));
+        // (+16 bytes on the device: index / value arrays are read as aligned 128-bit quads, the last of which may reach
+        // past the final element -- b200_frontier.h, b200_graph)
+        if (bytes) throw_on_error(space == memory_space_device ? cudaMalloc(&p, bytes + 16) : cudaMallocHost(&p, bytes));
         return p;
     }
     void free(void *p, memory_space_t space) override {

@@ -291,6 +291,7 @@ int b200_ctx_destroy(b200_ctx *ctx) {
     if (ctx->ws.d_counters) cudaFree(ctx->ws.d_counters);
     if (ctx->ws.h_counters) cudaFreeHost(ctx->ws.h_counters);
     if (ctx->ws.d_tile_counter) cudaFree(ctx->ws.d_tile_counter);
+    if (ctx->hot_vals) cudaFree(ctx->hot_vals);
     if (ctx->own_stream) cudaStreamDestroy((cudaStream_t)ctx->ws.stream);
     delete ctx;
     return B200_OK;

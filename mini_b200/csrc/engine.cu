@@ -146,6 +146,17 @@ struct FiniteValueFn {
     }
 };
 
+// The pull index array of a reduce and whether it is the remapped copy of b200_graph::hot_indices (b200_frontier.h).
+static_assert(QSEG_HOT_MAX == B200_HOT_MAX, "operators.cuh and b200_frontier.h disagree");
+bool use_hot_columns(b200_ctx *ctx, const b200_graph *g, int push) {
+    return !push && ctx->adv_impl != B200_ADVANCE_LBS && g->hot_indices && g->hot_ids && g->hot_count > 0 &&
+           g->hot_count <= B200_HOT_MAX && quad_aligned(g->hot_indices);
+}
+int ensure_hot_vals(b200_ctx *ctx) {
+    if (!ctx->hot_vals) B200_CUDA(cudaMalloc(&ctx->hot_vals, sizeof(float) * B200_HOT_MAX));
+    return B200_OK;
+}
+
 int check_counts(b200_ctx *ctx, int64_t len) {
     if (len < 0 || len >= (1ll << 32)) return B200_ERR_INVALID;
     return b200_ctx_reserve(ctx, len);
@@ -378,7 +389,17 @@ int b200_neighborhood_reduce_f32(b200_ctx *ctx, const b200_graph *g, const int32
     FiniteValueFn vf{d_values};
     cudaError_t e;
     const bool quad = ctx->adv_impl != B200_ADVANCE_LBS && quad_aligned(idx);
-    if (quad) {
+    if (quad && use_hot_columns(ctx, g, push)) {
+        // hot columns: the remapped index copy, hot values served from shared memory (quad_segreduce.cuh)
+        B200_TRY(ensure_hot_vals(ctx));
+        B200_CUDA(launch_neighborhood_quad_scan<float>(ws, d_in, (uint32_t)in_len, off, d_reduced, identity, neutral, scatter));
+        const QuadArgs a = make_quad_args(ws, d_in, (uint32_t)in_len, off, g->hot_indices, nullptr);
+        const uint32_t hc = (uint32_t)g->hot_count;
+        if (op == B200_OP_PLUS) e = launch_quad_segreduce_hot<float, PlusF32>(ws, a, vf, d_reduced, scatter, g->hot_ids, hc, ctx->hot_vals);
+        else if (op == B200_OP_MIN) e = launch_quad_segreduce_hot<float, MinF32>(ws, a, vf, d_reduced, scatter, g->hot_ids, hc, ctx->hot_vals);
+        else if (op == B200_OP_MAX) e = launch_quad_segreduce_hot<float, MaxF32>(ws, a, vf, d_reduced, scatter, g->hot_ids, hc, ctx->hot_vals);
+        else return B200_ERR_INVALID;
+    } else if (quad) {
         B200_CUDA(launch_neighborhood_quad_scan<float>(ws, d_in, (uint32_t)in_len, off, d_reduced, identity, neutral, scatter));
         const QuadArgs a = make_quad_args(ws, d_in, (uint32_t)in_len, off, idx, nullptr);
         if (op == B200_OP_PLUS) e = launch_quad_segreduce<float, PlusF32>(ws, a, vf, d_reduced, scatter);
@@ -713,6 +734,8 @@ int b200_pr_run(b200_ctx *ctx, const b200_graph *g, int max_iter, int scatter, f
     int sel = 0, it = 0;
     int64_t flen = n, total_arcs = 0;
     const bool quad = ctx->adv_impl != B200_ADVANCE_LBS && quad_aligned(idx);
+    const bool hot = quad && use_hot_columns(ctx, g, 0);
+    if (hot) B200_TRY(ensure_hot_vals(ctx));
     while (flen > 0 && it < max_iter) {
         b200_level_stat *ls = (stats && it < B200_MAX_LEVELS) ? &stats->level[it] : nullptr;
         const bool tl = timing && it < B200_MAX_LEVELS;
@@ -720,9 +743,13 @@ int b200_pr_run(b200_ctx *ctx, const b200_graph *g, int max_iter, int scatter, f
         B200_CUDA(reset_counters(ws));
         if (quad) {
             B200_CUDA(launch_neighborhood_quad_scan<float>(ws, ctx->frontier[sel], (uint32_t)flen, off, d_reduced, 0.0f, 0.0f, scatter));
-            const QuadArgs a = make_quad_args(ws, ctx->frontier[sel], (uint32_t)flen, off, idx, nullptr);
+            const QuadArgs a = make_quad_args(ws, ctx->frontier[sel], (uint32_t)flen, off, hot ? g->hot_indices : idx, nullptr);
             if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 1], st));
-            B200_CUDA((launch_quad_segreduce<float, PlusF32>(ws, a, FiniteValueFn{d_current}, d_reduced, scatter)));
+            if (hot)
+                B200_CUDA((launch_quad_segreduce_hot<float, PlusF32>(ws, a, FiniteValueFn{d_current}, d_reduced, scatter, g->hot_ids,
+                                                                     (uint32_t)g->hot_count, ctx->hot_vals)));
+            else
+                B200_CUDA((launch_quad_segreduce<float, PlusF32>(ws, a, FiniteValueFn{d_current}, d_reduced, scatter)));
         } else {
             NeighborhoodDegree<float> deg{ctx->frontier[sel], off, d_reduced, 0.0f, 0.0f, scatter};
             B200_CUDA(launch_scan(ws, deg, (uint32_t)flen, ws->d_scanned, ws->d_counters + B200_CNT_TOTAL));
@@ -827,6 +854,9 @@ int b200_host_graph_view(const b200_host_graph *hg, b200_graph *out) {
     out->row_values = hg->d_col_values;
     out->no_in_arc_bitmap = hg->d_no_in_arc;
     out->first_in_neighbor = hg->d_first_in_nbr;
+    out->hot_ids = nullptr;
+    out->hot_indices = nullptr;
+    out->hot_count = 0;
     return B200_OK;
 }
 

@@ -25,6 +25,7 @@ struct b200_ctx {
     int adv_impl;              // B200_ADVANCE_QUAD | B200_ADVANCE_LBS
     int loop_impl;             // B200_LOOP_GRAPH | B200_LOOP_HOST
     b200::LevelLoop *loop;     // graph-driven level loop (level_loop.cu), created on first use
+    float *hot_vals;           // [B200_HOT_MAX] values of a graph's hot columns, refreshed by every hot neighbourhood reduce
     uint64_t scratch_gen;      // bumped whenever workspace / traversal scratch is reallocated: cached traversal graphs
                                // (level_loop.cu, p2p_bfs.cu) hold those addresses and are rebuilt when it changes
 };

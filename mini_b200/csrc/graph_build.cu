@@ -135,9 +135,78 @@ int sort_and_emit(b200_ctx *ctx, unsigned long long *keys_a, unsigned long long 
     return B200_OK;
 }
 
+// ---- b200_graph_hot_columns: the most frequent columns of an index array, and the remapped copy --------------
+__global__ void hot_count_kernel(const int32_t *__restrict__ idx, unsigned long long m, uint32_t *counts) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < m; e += stride) atomicAdd(counts + idx[e], 1u);
+}
+__global__ void hot_keys_kernel(const uint32_t *__restrict__ counts, unsigned long long n, unsigned long long *keys) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;   // descending sort: more occurrences first, then smaller id
+    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride)
+        keys[v] = ((unsigned long long)counts[v] << 32) | (0xFFFFFFFFull - v);
+}
+__global__ void hot_slots_kernel(const unsigned long long *__restrict__ sorted, uint32_t hot_count, int32_t *hot_ids, int32_t *slot_of) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < hot_count) {
+        const int32_t v = (int32_t)(0xFFFFFFFFull - (sorted[k] & 0xFFFFFFFFull));
+        hot_ids[k] = v;
+        slot_of[v] = (int32_t)k;
+    }
+}
+__global__ void hot_remap_kernel(const int32_t *__restrict__ idx, unsigned long long m, const int32_t *__restrict__ slot_of, int32_t *out) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < m; e += stride) {
+        const int32_t v = idx[e];
+        const int32_t k = slot_of[v];
+        out[e] = k >= 0 ? ~k : v;
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int b200_graph_hot_columns(b200_ctx *ctx, const b200_graph *g, int64_t hot_count, int32_t *d_hot_ids, int32_t *d_hot_indices) {
+    if (!ctx || !g || !d_hot_ids || !d_hot_indices || hot_count < 1 || hot_count > B200_HOT_MAX || hot_count > g->n || g->n < 1 ||
+        g->n > (1ll << 31))
+        return B200_ERR_INVALID;
+    const int32_t *idx = g->row_indices ? g->row_indices : g->col_indices;   // the pull arrays (CSC aliases CSR: graph.hxx:75-80)
+    if (!idx && g->m) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ctx->ws.device));
+    cudaStream_t st = (cudaStream_t)ctx->ws.stream;
+    const unsigned long long n = (unsigned long long)g->n, m = (unsigned long long)g->m;
+    uint32_t *counts = nullptr;
+    int32_t *slot_of = nullptr;
+    unsigned long long *ka = nullptr, *kb = nullptr;
+    void *temp = nullptr;
+    int s = B200_OK;
+    do {
+        if ((s = cuda_status(cudaMalloc(&counts, sizeof(uint32_t) * n)))) break;
+        if ((s = cuda_status(cudaMalloc(&slot_of, sizeof(int32_t) * n)))) break;
+        if ((s = cuda_status(cudaMalloc(&ka, sizeof(unsigned long long) * n)))) break;
+        if ((s = cuda_status(cudaMalloc(&kb, sizeof(unsigned long long) * n)))) break;
+        if ((s = cuda_status(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * n, st)))) break;
+        if ((s = cuda_status(cudaMemsetAsync(slot_of, 0xFF, sizeof(int32_t) * n, st)))) break;
+        if (m) hot_count_kernel<<<ctx->ws.num_sms * 8, 256, 0, st>>>(idx, m, counts);
+        hot_keys_kernel<<<ctx->ws.num_sms * 8, 256, 0, st>>>(counts, n, ka);
+        if ((s = cuda_status(cudaGetLastError()))) break;
+        cub::DoubleBuffer<unsigned long long> buf(ka, kb);
+        size_t temp_bytes = 0;
+        if ((s = cuda_status(cub::DeviceRadixSort::SortKeysDescending(nullptr, temp_bytes, buf, (long long)n, 0, 64, st)))) break;
+        if ((s = cuda_status(cudaMalloc(&temp, temp_bytes ? temp_bytes : 16)))) break;
+        if ((s = cuda_status(cub::DeviceRadixSort::SortKeysDescending(temp, temp_bytes, buf, (long long)n, 0, 64, st)))) break;
+        hot_slots_kernel<<<(unsigned)((hot_count + 255) / 256), 256, 0, st>>>(buf.Current(), (uint32_t)hot_count, d_hot_ids, slot_of);
+        if (m) hot_remap_kernel<<<ctx->ws.num_sms * 8, 256, 0, st>>>(idx, m, slot_of, d_hot_indices);
+        if ((s = cuda_status(cudaGetLastError()))) break;
+        s = cuda_status(cudaStreamSynchronize(st));
+    } while (0);
+    cudaFree(counts);
+    cudaFree(slot_of);
+    cudaFree(ka);
+    cudaFree(kb);
+    cudaFree(temp);
+    return s;
+}
 
 int b200_rmat_pairs(b200_ctx *ctx, int scale, int edge_factor, uint64_t seed, int32_t *d_src, int32_t *d_dst) {
     if (!ctx || scale < 1 || scale > 31 || edge_factor < 1 || !d_src || !d_dst) return B200_ERR_INVALID;

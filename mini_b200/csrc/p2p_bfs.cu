@@ -311,6 +311,7 @@ struct P2PLoopState {       // device
 // ---- persistent small-level kernel: shared state -------------------------------------------
 constexpr int SMALL_NT = 512;
 constexpr int SMALL_SLOTS = 4;
+constexpr uint32_t SMALL_STAGE = 64;  // slots per (warp, destination) staging row: < 32 left after a flush + <= 32 new
 constexpr uint32_t SMALL_ROW = 512;   // rows up to this many arcs: one warp; longer rows: pieces of SMALL_ROW arcs over the whole grid
 constexpr unsigned long long SMALL_GRID_TIMEOUT_NS = 5ull * 1000ull * 1000ull * 1000ull;
 struct SmallCounters {      // one slot per level (level & 3): nobody has to wait for a reset
@@ -509,6 +510,8 @@ __device__ __forceinline__ bool small_wait_peers(const SmallArgs &a, unsigned lo
 
 __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs a) {
     constexpr int NW = SMALL_NT / 32, U = 8;
+    __shared__ int s_stage[NW][P2P_MAX * SMALL_STAGE];
+    __shared__ uint32_t s_fill[NW][P2P_MAX];
     __shared__ unsigned s_gen;
     __shared__ unsigned long long s_sum[8];
     P2PLoopState *s = a.s;
@@ -524,6 +527,9 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
     const int *my_inbox = reinterpret_cast<const int *>(a.peers.base[me] + a.off_inbox);
     const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
     if (threadIdx.x == 0) s_gen = ld_relaxed_gpu_u32(&sh->bar_gen);
+    int *wbuf = s_stage[warp];
+    uint32_t *wfill = s_fill[warp];
+    if (lane < P2P_MAX) wfill[lane] = 0u;
 
     // the level state, identically in every CTA
     int level = s->level;
@@ -565,8 +571,15 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
                     const uint32_t pb = (uint32_t)p * chunk;
                     const uint32_t cnt = pb >= deg ? 0u : (deg - pb < chunk ? deg - pb : chunk);
                     int *stage = reinterpret_cast<int *>(a.peers.base[p] + a.off_inbox) + (size_t)me * part.n_local + (part.n_local - chunk);
-                    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x)
-                        stage[i] = __ldg(a.indices + rb + pb + i);
+                    const uint32_t nthr = gridDim.x * blockDim.x;
+                    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < cnt; i0 += 8u * nthr) {   // 8 loads in flight
+                        int v[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] = i0 + k * nthr < cnt ? __ldg(a.indices + rb + pb + i0 + k * nthr) : 0;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (i0 + k * nthr < cnt) stage[i0 + k * nthr] = v[k];
+                    }
                 }
             }
         }
@@ -599,6 +612,17 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
         const int next_label = level + 1;
         unsigned long long arc_cnt = 0, deg_sum = 0;
 
+        // this warp's staging rows (see expand) and their flush: `count` ids of destination p leave for its box
+        auto flush_row = [&](int p, uint32_t count) {
+            unsigned long long base = 0ull;
+            if (lane == 0) base = atomicAdd(p == me ? &c->next_cnt : &c->send_cnt[p], (unsigned long long)count);
+            base = __shfl_sync(FULL_MASK, base, 0);
+            int *box = p == me ? out : reinterpret_cast<int *>(a.peers.base[p] + a.off_inbox) + (size_t)me * part.n_local;
+            if (lane < count) {
+                if (base + lane < part.n_local) box[base + lane] = wbuf[p * SMALL_STAGE + lane];
+                else c->overflow = 1ull;
+            }
+        };
         // the per-arc step of a warp over arcs [b, e) of one row piece, 32 * U arcs at a time: all index loads, then all
         // probes, then all claims are in flight together; the winners are counted per destination over the whole tile and
         // every destination's slots are reserved with ONE atomic, the P atomics issued side by side by lanes 0 .. P-1
@@ -641,28 +665,30 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
                     }
                 }
                 if (!__any_sync(FULL_MASK, any)) continue;
-                uint32_t tot_mine = 0u;                  // lane p: winners of this tile that rank p owns
-                for (int p = 0; p < P; ++p) {
-                    uint32_t tot = 0u;
+                // winners go to their owner's box through this warp's staging rows (one row of 64 slots per destination in
+                // shared memory): a row is flushed 32 ids at a time -- ONE slot reservation and ONE 128-byte store, local or
+                // over NVLink.  (Storing every id on its own -- 4 bytes per peer-memory request -- kept the expansion of a
+                // 213 K-arc share of the hub row at 43 us, whether 2 or 8 GPUs shared the row.)
 #pragma unroll
-                    for (int u = 0; u < U; ++u) tot += __popc(__ballot_sync(FULL_MASK, owner[u] == p));
-                    if ((int)lane == p) tot_mine = tot;
-                }
-                unsigned long long base_mine = 0ull;
-                if (tot_mine) base_mine = atomicAdd((int)lane == me ? &c->next_cnt : &c->send_cnt[lane], (unsigned long long)tot_mine);
-                for (int p = 0; p < P; ++p) {
-                    if (!__shfl_sync(FULL_MASK, tot_mine, p)) continue;
-                    unsigned long long run = __shfl_sync(FULL_MASK, base_mine, p);
-                    int *box = p == me ? out : reinterpret_cast<int *>(a.peers.base[p] + a.off_inbox) + (size_t)me * part.n_local;
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
+                for (int u = 0; u < U; ++u) {
+                    if (!__any_sync(FULL_MASK, owner[u] >= 0)) continue;
+                    for (int p = 0; p < P; ++p) {
                         const unsigned mask = __ballot_sync(FULL_MASK, owner[u] == p);
-                        if (owner[u] == p) {
-                            const unsigned long long pos = run + __popc(mask & lt_mask);
-                            if (pos < part.n_local) box[pos] = d[u];
-                            else c->overflow = 1ull;
+                        if (!mask) continue;
+                        uint32_t f = wfill[p];
+                        if (owner[u] == p) wbuf[p * SMALL_STAGE + f + __popc(mask & lt_mask)] = d[u];
+                        f += __popc(mask);
+                        __syncwarp();
+                        if (f >= 32u) {
+                            flush_row(p, 32u);
+                            const int x = lane < f - 32u ? wbuf[p * SMALL_STAGE + 32u + lane] : 0;
+                            __syncwarp();
+                            if (lane < f - 32u) wbuf[p * SMALL_STAGE + lane] = x;
+                            f -= 32u;
                         }
-                        run += __popc(mask);
+                        __syncwarp();
+                        if (lane == 0) wfill[p] = f;
+                        __syncwarp();
                     }
                 }
             }
@@ -682,6 +708,12 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
                 continue;
             }
             if (e > b) expand(a.indices, false, b, e);
+        }
+        for (int p = 0; p < P; ++p) {                // what is left in this warp's staging rows
+            const uint32_t f = wfill[p];
+            __syncwarp();
+            if (f) flush_row(p, f);
+            if (lane == 0) wfill[p] = 0u;
         }
         // (system scope: when no long row was queued this is already the "sends are out" barrier)
         if (!small_grid_barrier(sh, &s_gen, true)) break;
@@ -710,6 +742,12 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
             }
         }
         if (nbig || hub_level) {
+            for (int p = 0; p < P; ++p) {            // what is left in this warp's staging rows
+                const uint32_t f = wfill[p];
+                __syncwarp();
+                if (f) flush_row(p, f);
+                if (lane == 0) wfill[p] = 0u;
+            }
             if (!small_grid_barrier(sh, &s_gen, true)) break;   // (system scope: the stores into the peers' inboxes, before the flag)
         }
         // ---- everybody's sends are out: counts + flag to every peer, then wait for theirs
@@ -722,11 +760,22 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
         loop_trace(&s->dyn, 22);
         if (!small_wait_peers(a, bar_epoch)) break;
         loop_trace(&s->dyn, 23);
-        // ---- phase B: absorb what the peers left in the inbox segments
-        for (int q = 0; q < P; ++q) {
-            if (q == me) continue;
-            const unsigned long long cnt = ld_relaxed_sys(&my_ctrl->counts[q]);
-            const int *seg = my_inbox + (size_t)q * part.n_local;
+        // ---- phase B: absorb what the peers left in the inbox segments.  The P - 1 segments are walked as ONE list (a
+        // loop over the peers ran their dependent load -> probe -> claim chains one after the other: 14 us at 8 GPUs for a
+        // level that received 25 ids)
+        {
+            unsigned long long pre[P2P_MAX + 1];
+            pre[0] = 0ull;
+#pragma unroll
+            for (int q = 0; q < P2P_MAX; ++q)
+                pre[q + 1] = pre[q] + ((q < P && q != me) ? ld_relaxed_sys(&my_ctrl->counts[q]) : 0ull);
+            const unsigned long long cnt = pre[P2P_MAX];
+            auto entry = [&](unsigned long long i) -> int {   // the i-th id of the concatenated segments
+                int q = 0;
+#pragma unroll
+                for (int k = 1; k < P2P_MAX; ++k) q += i >= pre[k];
+                return __ldcg(my_inbox + (size_t)q * part.n_local + (i - pre[q]));
+            };
             // a warp takes 32 * G entries at a time and reserves their frontier slots with ONE atomic (a same-address
             // atomic per 32 entries was what the absorb of level 0 -- 0.5 M ids -- spent its 30 us on)
             constexpr int G = 8;
@@ -737,7 +786,7 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
 #pragma unroll
                 for (int j = 0; j < G; ++j) {
                     const unsigned long long i = base + 32ull * j + lane;
-                    u[j] = i < cnt ? __ldcg(seg + i) : -1;
+                    u[j] = i < cnt ? entry(i) : -1;
                 }
 #pragma unroll
                 for (int j = 0; j < G; ++j) {          // all probes of `done` in flight
@@ -1149,15 +1198,30 @@ __global__ void __launch_bounds__(PULL_NT, 4) p2p_pull_levels_kernel(PullArgs a)
             const uint32_t qps = a.wl / 4;
             const size_t total = (size_t)qps * (size_t)P, stride = (size_t)gridDim.x * blockDim.x;
             uint4 *full4 = reinterpret_cast<uint4 *>(a.full), *known4 = reinterpret_cast<uint4 *>(a.known);
-            for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-                const uint32_t p = (uint32_t)(i / qps);
-                const uint32_t j = (uint32_t)(i - (size_t)p * qps);
-                const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(a.peers.base[p] + slice_off) + j);
-                full4[i] = v;
-                if (v.x | v.y | v.z | v.w) {
-                    uint4 k = __ldcg(known4 + i);
-                    k.x |= v.x; k.y |= v.y; k.z |= v.z; k.w |= v.w;
-                    known4[i] = k;
+            // (four peer loads in flight per thread: one at a time is a chain of NVLink round trips -- 19-23 us per gather
+            // of 7 MiB at 8 GPUs in the first trace)
+            for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+                uint4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const size_t i = i0 + (size_t)k * stride;
+                    v[k] = make_uint4(0u, 0u, 0u, 0u);
+                    if (i < total) {
+                        const uint32_t p = (uint32_t)(i / qps);
+                        const uint32_t j = (uint32_t)(i - (size_t)p * qps);
+                        v[k] = __ldcg(reinterpret_cast<const uint4 *>(a.peers.base[p] + slice_off) + j);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const size_t i = i0 + (size_t)k * stride;
+                    if (i >= total) continue;
+                    full4[i] = v[k];
+                    if (v[k].x | v[k].y | v[k].z | v[k].w) {
+                        uint4 kn = __ldcg(known4 + i);
+                        kn.x |= v[k].x; kn.y |= v[k].y; kn.z |= v[k].z; kn.w |= v[k].w;
+                        known4[i] = kn;
+                    }
                 }
             }
         }

@@ -28,7 +28,8 @@ class B200Error(RuntimeError):
 class CGraph(C.Structure):
     _fields_ = [("n", C.c_int64), ("m", C.c_int64), ("row_offsets", C.c_void_p), ("col_indices", C.c_void_p),
                 ("col_values", C.c_void_p), ("col_offsets", C.c_void_p), ("row_indices", C.c_void_p),
-                ("row_values", C.c_void_p), ("no_in_arc_bitmap", C.c_void_p), ("first_in_neighbor", C.c_void_p)]
+                ("row_values", C.c_void_p), ("no_in_arc_bitmap", C.c_void_p), ("first_in_neighbor", C.c_void_p),
+                ("hot_ids", C.c_void_p), ("hot_indices", C.c_void_p), ("hot_count", C.c_int64)]
 
 
 class CHostCSR(C.Structure):
@@ -94,6 +95,7 @@ def load_library():
         "b200_ctx_set_level_loop": ([vp, i32], i32),
         "b200_ctx_forget_graph": ([vp], i32),
         "b200_graph_no_in_arc_bitmap": ([vp, pg, vp], i32),
+        "b200_graph_hot_columns": ([vp, pg, i64, vp, vp], i32),
         "b200_graph_first_in_neighbor": ([vp, pg, vp], i32),
         "b200_ctx_workspace": ([vp], vp),
         "b200_rmat_build_csr": ([vp, i32, i32, u64, vp, vp, vp, u64], i32),
@@ -184,11 +186,14 @@ class Graph:
         self.row_offsets, self.col_indices, self.col_values = row_offsets, col_indices, col_values
         self.no_in_arc = None   # derived data (Context.prepare_graph), like graph_device_t::d_scanned_row_offsets
         self.first_in_nbr = None
+        self.hot_ids = None     # derived data (Context.prepare_hot_columns)
+        self.hot_indices = None
 
     def cview(self) -> CGraph:
         return CGraph(self.n, self.m, _ptr(self.row_offsets), _ptr(self.col_indices), _ptr(self.col_values),
                       _ptr(self.row_offsets), _ptr(self.col_indices), _ptr(self.col_values), _ptr(self.no_in_arc),
-                      _ptr(self.first_in_nbr))
+                      _ptr(self.first_in_nbr), _ptr(self.hot_ids), _ptr(self.hot_indices),
+                      0 if self.hot_ids is None else self.hot_ids.numel())
 
     def offsets_host(self):
         import numpy as np
@@ -307,6 +312,19 @@ class Context:
         first = torch.empty(g.n, dtype=torch.int32, device=self.torch_device)
         _check(self._L.b200_graph_first_in_neighbor(self._h, C.byref(cg), first.data_ptr()), "b200_graph_first_in_neighbor")
         g.no_in_arc, g.first_in_nbr = bm, first
+        return g
+
+    def prepare_hot_columns(self, g: Graph, hot_count: int = 40960) -> Graph:
+        """One-time derived data for neighbourhood reductions (b200_graph_hot_columns): the hot_count most frequent
+        columns and the remapped index copy; the reduce kernel then serves their values from shared memory."""
+        import torch
+        hot_count = int(min(hot_count, g.n))
+        ids = torch.empty(hot_count, dtype=torch.int32, device=self.torch_device)
+        idx = _quad_padded(g.m, torch.int32, self.torch_device)
+        cg = g.cview()
+        _check(self._L.b200_graph_hot_columns(self._h, C.byref(cg), hot_count, ids.data_ptr(), idx.data_ptr()),
+               "b200_graph_hot_columns")
+        g.hot_ids, g.hot_indices = ids, idx
         return g
 
     def graph_from_host(self, offsets, indices, weights=None) -> Graph:

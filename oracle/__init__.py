@@ -27,7 +27,9 @@ _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 def build(force: bool = False) -> None:
     """Compile liboracle.so (and _ref/libref_cpu.so when /root/reference exists)."""
     src = os.path.join(_HERE, "oracle.c")
-    stale = (not os.path.exists(_LIB)) or os.path.getmtime(_LIB) < os.path.getmtime(src)
+    rnd_src, rnd_lib = os.path.join(_HERE, "stdrand.cpp"), os.path.join(_HERE, "libstdrand.so")
+    stale = (not os.path.exists(_LIB)) or os.path.getmtime(_LIB) < os.path.getmtime(src) or \
+        (not os.path.exists(rnd_lib)) or os.path.getmtime(rnd_lib) < os.path.getmtime(rnd_src)
     gpu_bin = os.path.join(_HERE, "_ref", "ref_gpu_pr")
     need_ref = os.path.isdir("/root/reference/gunrock/src") and (
         not os.path.exists(_REF)
@@ -250,26 +252,27 @@ def kcore(g: CSR):
     return cores, int(largest)
 
 
-def mt19937_hashes(n: int, prime: int, state=None):
-    """n draws of std::uniform_int_distribution<int>(0, prime) from a default-seeded std::mt19937 -- what
+_stdrand = None
+
+
+def mt19937_hashes(n: int, prime: int, restart: bool = False):
+    """The next n draws of std::uniform_int_distribution<int>(0, prime) from ONE default-seeded std::mt19937 -- what
     mgpu::fill_random(0, prime, n, false, ctx) hands the colouring problem (memory.hxx:112-129,
-    coloring_problem.hxx:44,50).  libstdc++'s algorithm: with R = 2^32 and range = prime + 1, draw 32-bit words until
-    one is below range * (R // range), then divide by R // range.  `state`: a numpy RandomState carried from call to
-    call (the reference's engine is one process-wide static); returns (hashes, state)."""
-    if state is None:
-        state = np.random.RandomState(5489)          # init_genrand(5489) == std::mt19937's default seed
-    rng = prime + 1
-    scaling = (1 << 32) // rng
-    past = rng * scaling
+    coloring_problem.hxx:44,50).  Not a restatement: oracle/stdrand.cpp calls the installed libstdc++ (whose
+    distribution algorithm differs between releases).  restart = True re-seeds the shared engine first (a new process
+    in the reference's terms)."""
+    global _stdrand
+    if _stdrand is None:
+        build()
+        _stdrand = C.CDLL(os.path.join(_HERE, "libstdrand.so"))
+        _stdrand.orc_stdrand_uniform.argtypes = [C.c_longlong, C.c_int, C.c_int, _i32p]
+        _stdrand.orc_stdrand_uniform.restype = None
+        _stdrand.orc_stdrand_reset.restype = None
+    if restart:
+        _stdrand.orc_stdrand_reset()
     out = np.empty(n, np.int32)
-    k = 0
-    while k < n:
-        raw = state.randint(0, 1 << 32, size=n - k, dtype=np.uint64)   # full range: the generator's raw 32-bit words
-        ok = raw[raw < past]
-        out[k:k + len(ok)] = (ok // scaling).astype(np.int32)
-        # (a rejected word is simply skipped by the C++ loop: order of the accepted ones is unchanged)
-        k += len(ok)
-    return out, state
+    _stdrand.orc_stdrand_uniform(n, 0, prime, out)
+    return out
 
 
 def coloring(g: CSR, prime: int = 15485863, max_iter: int = 10):
@@ -281,7 +284,7 @@ def coloring(g: CSR, prime: int = 15485863, max_iter: int = 10):
     rows = np.repeat(np.arange(n, dtype=np.int64), deg)
     colors = np.zeros(n, np.int32)
     frontier = np.arange(n, dtype=np.int64)
-    hashes, st = mt19937_hashes(n, prime)
+    hashes = mt19937_hashes(n, prime, restart=True)
     lens = []
     it = 0
     imin, imax = np.iinfo(np.int32).min, np.iinfo(np.int32).max
@@ -298,7 +301,7 @@ def coloring(g: CSR, prime: int = 15485863, max_iter: int = 10):
         frontier = frontier[col == 0]
         lens.append(len(frontier))
         it += 1
-        hashes, st = mt19937_hashes(n, prime, st)
+        hashes = mt19937_hashes(n, prime)
     return colors, lens
 
 

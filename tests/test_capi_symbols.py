@@ -37,7 +37,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_status_strings(lib):
-    assert lib.b200_abi_version() == 2
+    assert lib.b200_abi_version() == 3
     assert lib.b200_status_string(0) == b"ok"
     assert b"capacity" in lib.b200_status_string(3)
 
@@ -91,7 +91,7 @@ int main(void) {
     want = [C.sizeof(L.CGraph), L.CGraph.no_in_arc_bitmap.offset, L.CGraph.first_in_neighbor.offset, C.sizeof(L.CProblem),
             C.sizeof(L.CLevelStat), C.sizeof(L.CStats), L.CStats.level_loop.offset, L.CStats.level.offset]
     assert got[:8] == want, (got, want)
-    assert got[9] == 2
+    assert got[9] == 3
     # bench_multi.py reads b200_workspace::launches through a prefix mirror of the struct
     import re
     txt = open(os.path.join(ROOT, "bench_multi.py")).read()

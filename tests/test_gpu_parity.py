@@ -17,7 +17,7 @@ FIXTURES = ["ref_fixture_bfs.json", "ref_fixture_sssp_directed.json",
 FLT_MAX = np.finfo(np.float32).max
 
 
-@pytest.fixture(scope="module", params=["quad", "lbs", "quad-hostloop", "quad-rescan", "quad-rescan-hostloop"])
+@pytest.fixture(scope="module", params=["quad", "lbs", "quad-hostloop", "quad-rescan", "quad-rescan-hostloop", "quad-hot"])
 def ctx(request):
     """Every parity test runs against both push-advance kernels (quad_advance.cuh / advance.cuh) and, for the
     quad kernel, against both level loops (one CUDA graph per traversal / host-driven) and both ways of getting a
@@ -27,13 +27,16 @@ def ctx(request):
     c.set_advance_impl(mini_b200.ADVANCE_LBS if request.param == "lbs" else
                        mini_b200.ADVANCE_QUAD_RESCAN if "rescan" in request.param else mini_b200.ADVANCE_QUAD)
     c.set_level_loop(mini_b200.LOOP_HOST if "hostloop" in request.param else mini_b200.LOOP_GRAPH)
-    c.variant = request.param
+    c.variant = request.param   # "quad-hot": every test graph carries hot-column derived data (neighbourhood reduces / PR use it)
     yield c
     c.close()
 
 
 def _dev_graph(ctx, g: oracle.CSR):
-    return ctx.graph_from_host(g.offsets, g.indices, g.weights)
+    dg = ctx.graph_from_host(g.offsets, g.indices, g.weights)
+    if getattr(ctx, "variant", "") == "quad-hot" and g.m > 0:
+        ctx.prepare_hot_columns(dg, hot_count=min(g.n, 1500))
+    return dg
 
 
 def _rand_graph(n, npairs, seed, symmetrize=True, weighted=True):
@@ -560,6 +563,32 @@ def test_dense_to_sparse_ragged_sizes(ctx):
             k = ctx.dense_to_sparse(n, bm, out)
             assert k == len(idx)
             assert np.array_equal(out.cpu().numpy()[:k], idx.astype(np.int32))
+
+
+@pytest.mark.parametrize("hot_count", [1, 37, 4096, 40960])
+def test_hot_columns_derived_data(ctx, hot_count):
+    """b200_graph_hot_columns: hot_ids = the most frequent columns (ties: smaller id), hot_indices decodes back to the
+    index array, and a reduce over the remapped copy gives the plain path's sums."""
+    o = oracle.rmat_csr(13, 16, 1)
+    g = ctx.graph_from_host(o.offsets, o.indices)
+    hc = min(hot_count, o.n)
+    ctx.prepare_hot_columns(g, hot_count=hc)
+    ids = g.hot_ids.cpu().numpy()
+    counts = np.bincount(o.indices, minlength=o.n)
+    order = np.lexsort((np.arange(o.n), -counts))[:hc]
+    assert np.array_equal(ids, order.astype(np.int32))
+    hi = g.hot_indices.cpu().numpy()
+    decoded = np.where(hi < 0, ids[np.clip(~hi, 0, hc - 1)], hi)
+    assert np.array_equal(decoded, o.indices)
+    assert np.array_equal(hi < 0, np.isin(o.indices, ids))
+    rng = np.random.default_rng(5)
+    vals = rng.random(o.n).astype(np.float32)
+    frontier = rng.permutation(o.n)[: o.n // 2].astype(np.int32)
+    ref, asum = oracle.neighborhood_reduce(o, frontier, vals.astype(np.float64), "plus", identity=0.0)
+    red = torch.empty(len(frontier), dtype=torch.float32, device="cuda")
+    arcs = ctx.neighborhood_reduce(g, torch.from_numpy(frontier).cuda(), torch.from_numpy(vals).cuda(), red)
+    assert arcs == int((o.offsets[frontier + 1] - o.offsets[frontier]).sum())
+    _check_reduce(red.cpu().numpy(), ref, asum)
 
 
 def test_neighborhood_reduce_nonfinite_values_read_as_zero(ctx):

@@ -231,14 +231,17 @@ def test_kcore_on_reference_fixture(golden):
     assert cores.tolist() == [4, 4, 6, 6, 6, 4, 6, 6, 4] and largest == 6
 
 
-def test_mt19937_hashes_match_libstdcxx():
-    """The hash stream of coloring_problem_t (mgpu::fill_random, memory.hxx:112-129): default-seeded std::mt19937
-    through std::uniform_int_distribution<int>(0, prime).  First raw words of mt19937: 3499211612, 581869302, ..."""
-    h, st = oracle.mt19937_hashes(4, 15485863)
-    scaling = (1 << 32) // 15485864
-    assert h.tolist()[:2] == [3499211612 // scaling, 581869302 // scaling]
-    h2, _ = oracle.mt19937_hashes(4, 15485863, st)             # the engine is carried on, not re-seeded
-    assert h2.tolist() != h.tolist() and h.min() >= 0 and h.max() <= 15485863
+def test_mt19937_hash_stream():
+    """The hash stream of coloring_problem_t (mgpu::fill_random, memory.hxx:112-129) comes from the installed C++
+    library itself (oracle/stdrand.cpp): default-seeded std::mt19937 (first raw words 3499211612, 581869302, ...) through
+    std::uniform_int_distribution<int>(0, prime); the engine is carried from call to call, not re-seeded."""
+    full = oracle.mt19937_hashes(4, 2 ** 31 - 1, restart=True)        # the whole non-negative int range
+    assert full.min() >= 0
+    a = oracle.mt19937_hashes(6, 15485863, restart=True)
+    b = oracle.mt19937_hashes(6, 15485863)
+    c = oracle.mt19937_hashes(12, 15485863, restart=True)
+    assert a.min() >= 0 and a.max() <= 15485863
+    assert np.array_equal(np.concatenate([a, b]), c)                  # one engine, carried on
 
 
 @pytest.mark.parametrize("which", ["fixture", "rmat10"])
