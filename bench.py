@@ -476,6 +476,26 @@ def run_single_gpu(args):
         else:
             ref_gpu = {"unavailable": "oracle/_ref/ref_gpu_bfs not built (needs /root/reference at build time)"}
 
+    # ---- the header API (include/gunrock): the reference's enact_pushpull, operator by operator with user functors, on the
+    # same workload through build/dropin/frontier_driver (its own host-side RMAT build is outside its timer, as in test_bfs.cu)
+    header_api = None
+    drv = os.path.join(ROOT, "build", "dropin", "frontier_driver")
+    if args.header_api and os.path.exists(drv):
+        try:
+            import re
+            r = subprocess.run([drv, "--algo=bfs", f"--rmat-scale={scale}", "--repeat=5"], capture_output=True, text=True, timeout=300)
+            m_best = re.search(r"best elapsed time: ([0-9.eE+-]+)s", r.stdout)
+            if r.returncode == 0 and m_best and "Correct." in r.stdout:
+                sec = float(m_best.group(1))
+                header_api = {"impl": "bfs_enactor_t::enact_pushpull of include/gunrock (advance_forward_kernel + filter_kernel with the BFS "
+                                      "functor, alpha = 1/n), wall clock as test_bfs.cu:38-42, best of 5",
+                              "ms_per_step": 1e3 * sec, "value": reached_arcs / sec / 1e9, "unit": UNIT, "validated": "Correct.",
+                              "fraction_of_b200_bfs_run": (ms_total / args.steps) / (1e3 * sec)}
+            else:
+                header_api = {"unavailable": (r.stdout + r.stderr)[-300:]}
+        except Exception as e:   # noqa: BLE001
+            header_api = {"unavailable": repr(e)[:300]}
+
     # ---- the other single-GPU configurations of BASELINE.json (own graphs; the BFS graph is released first)
     gn, gm = g.n, g.m
     del g, labels
@@ -526,7 +546,7 @@ def run_single_gpu(args):
                                                   if loop_used == "graph" else " (one counter read-back per level)"),
                    "parallelism": "1 GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-        "reference_gpu": ref_gpu,
+        "reference_gpu": ref_gpu, "header_api": header_api,
         "value_median_of_steps": reached_arcs / (median_ms * 1e-3) / 1e9,
         "gteps_graph500_convention": {"value": value / 2.0, "note": "Graph500 counts undirected input edges: m_reached / 2 over the same time"},
         "seeds": seeds,
@@ -563,6 +583,7 @@ def main():
     ap.add_argument("--no-ref-gpu", dest="ref_gpu", action="store_false", help="skip the reference-GPU baseline column")
     ap.add_argument("--no-ref-gpu-pr", dest="ref_gpu_pr", action="store_false", help="skip the reference GPU PR run (scale-24: ~1 min)")
     ap.add_argument("--no-seeds", dest="seeds", action="store_false", help="skip the seed-2 / seed-3 graphs")
+    ap.add_argument("--no-header-api", dest="header_api", action="store_false", help="skip the include/gunrock operator-path leg")
     ap.add_argument("--no-hot-columns", dest="hot_columns", action="store_false",
                     help="reduce leg: plain index array only (no b200_graph_hot_columns derived data)")
     ap.add_argument("--reduce-scale", dest="reduce_scale", type=int, default=24)

@@ -346,7 +346,10 @@ __device__ __forceinline__ uint32_t pull_ld_bm(const uint32_t *p) {
     return COHERENT ? __ldcg(p) : __ldg(p);
 }
 
-template <int NT, bool COHERENT = false>
+// CW: bitmap words (32 CW vertices) per dynamically claimed warp chunk.  32 everywhere: 8-word chunks (tried for the
+// ranks of a partition, which have < 2 chunks of 32 words per warp at scale 26 / 8 GPUs) made the sparse pull levels twice
+// as slow -- their cost is the per-chunk claim and bitmap load, not the rows (single rank, scale 25: 57 -> 116 us).
+template <int NT, bool COHERENT = false, int CW_ = B200_PULL_CW>
 __device__ __forceinline__ void bfs_pull_body(uint32_t n, const uint32_t *__restrict__ offsets,
                                               const int *__restrict__ indices,
                                               const uint32_t *__restrict__ frontier_bm,
@@ -354,7 +357,7 @@ __device__ __forceinline__ void bfs_pull_body(uint32_t n, const uint32_t *__rest
                                               int *__restrict__ labels, int next_label,
                                               unsigned long long *counters, Partition part,
                                               const int *__restrict__ first_nbr = nullptr) {
-    constexpr int NW = NT / 32, CW = B200_PULL_CW, U = 4;   // CW words (32 CW vertices) per warp chunk
+    constexpr int NW = NT / 32, CW = CW_, U = 4;   // CW words (32 CW vertices) per warp chunk
     __shared__ uint16_t s_list[NW][CW * 32];
     __shared__ uint32_t s_new[NW][CW];
     __shared__ unsigned long long red[3][NW];

@@ -25,14 +25,18 @@ template <> struct rop_for<int, mgpu::plus_t<int>> { using type = b200::PlusI32;
 template <> struct rop_for<int, mgpu::minimum_t<int>> { using type = b200::MinI32; };
 template <> struct rop_for<int, mgpu::maximum_t<int>> { using type = b200::MaxI32; };
 
-template <typename Problem, typename Functor, typename Value>
+// ADVANCE_HERE: evaluate cond_advance / apply_advance in this pass.  The reference evaluates both advance halves ONCE
+// per arc before taking the value (neighborhood.hxx:50-54); with has_output the emit pass (EmitOp) already did, and a
+// functor with side effects (atomics, counters) must not see every arc twice.
+template <typename Problem, typename Functor, typename Value, bool ADVANCE_HERE>
 struct ValueOfNeighbor {
     typename Problem::data_slice_t *data;
     int iteration;
     __device__ __forceinline__ Value operator()(int src, int nbr, uint32_t eid) const {
-        // the reference evaluates both advance halves for every arc before taking the value
-        (void)Functor::cond_advance(src, nbr, (int)eid, 0, (int)eid, data, iteration);
-        (void)Functor::apply_advance(src, nbr, (int)eid, 0, (int)eid, data, iteration);
+        if (ADVANCE_HERE) {
+            (void)Functor::cond_advance(src, nbr, (int)eid, 0, (int)eid, data, iteration);
+            (void)Functor::apply_advance(src, nbr, (int)eid, 0, (int)eid, data, iteration);
+        }
         return Functor::get_value_to_reduce(nbr, data, iteration);
     }
 };
@@ -101,8 +105,12 @@ int neighborhood_kernel(std::shared_ptr<Problem> problem, std::shared_ptr<fronti
     b200::NeighborhoodDegree<Value> deg{in, offsets, reduced, identity, ROp::neutral(), 0};
     mgpu::throw_on_error(b200::launch_scan(ws, deg, (uint32_t)len, ws->d_scanned, ws->d_counters + B200_CNT_TOTAL));
     const b200::LbsArgs a = b200::make_lbs_args(ws, in, (uint32_t)len, offsets, indices);
+    if (has_output) {   // the emit pass writes one entry per arc: make room first (resize prints the reference's overflow text)
+        mgpu::throw_on_error(b200::read_counters(ws));
+        output->resize((size_t)ws->h_counters[B200_CNT_TOTAL]);
+    }
     detail::emit_raw<Problem, Functor>(std::integral_constant<bool, has_output>(), ws, a, data, iteration, output);
-    detail::ValueOfNeighbor<Problem, Functor, Value> vf{data, iteration};
+    detail::ValueOfNeighbor<Problem, Functor, Value, !has_output> vf{data, iteration};
     mgpu::throw_on_error((b200::launch_lbs_segreduce<Value, ROp>(ws, a, vf, reduced, 0)));
     detail::write_back<Problem, Functor, Value>(std::integral_constant<bool, write_back>(), in, reduced, data, iteration, len, context);
     mgpu::throw_on_error(b200::read_counters(ws));

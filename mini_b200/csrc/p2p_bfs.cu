@@ -45,7 +45,7 @@ struct Ctrl {                                  // heap offset 0 on every rank
     unsigned long long flags[P2P_MAX];         // flags[p]: last barrier epoch rank p signalled to me
     unsigned long long counts[P2P_MAX];        // counts[p]: vertices rank p left in my inbox segment p
     unsigned long long stats[2][P2P_MAX][8];   // stats[parity][p]: rank p's row of the level summary
-    unsigned long long hub_degree;             // level 0: degree of the source's row if its owner split it over the ranks, else 0
+    unsigned long long hub_degree;             // level 0: degree of the source's row, told to every rank by its owner
 };
 static_assert(sizeof(Ctrl) <= P2P_CTRL_BYTES, "control block");
 
@@ -283,7 +283,7 @@ struct P2PLoopParams {      // mapped pinned, read by the init kernel
     unsigned long long *trace;
     uint32_t trace_cap, small_on;
     long long small_arcs, small_verts;   // a push level runs in the persistent small-level kernel while its frontier is this small
-    long long hub_min;                   // level 0: a source row of at least this many arcs is split over the ranks
+    long long hub_min;                   // level 0: a source row of at least this many arcs goes through the bitmap exchange
 };
 struct P2PLevelRec {
     int32_t direction, exchange;   // exchange: 0 = vertex ids through the inboxes, 1 = bitmap slices
@@ -311,7 +311,9 @@ struct P2PLoopState {       // device
 // ---- persistent small-level kernel: shared state -------------------------------------------
 constexpr int SMALL_NT = 512;
 constexpr int SMALL_SLOTS = 4;
-constexpr uint32_t SMALL_STAGE = 64;  // slots per (warp, destination) staging row: < 32 left after a flush + <= 32 new
+constexpr uint32_t SMALL_FLUSH = 256; // ids per flush of a staging row: ONE slot reservation (a same-address atomic) per 256 winners
+constexpr uint32_t SMALL_STAGE = SMALL_FLUSH + 32;   // slots per (warp, destination) row: < SMALL_FLUSH left after a flush + <= 32 new
+constexpr size_t SMALL_SMEM = sizeof(int) * (SMALL_NT / 32) * P2P_MAX * SMALL_STAGE;   // 147 KB of dynamic shared memory
 constexpr uint32_t SMALL_ROW = 512;   // rows up to this many arcs: one warp; longer rows: pieces of SMALL_ROW arcs over the whole grid
 constexpr unsigned long long SMALL_GRID_TIMEOUT_NS = 5ull * 1000ull * 1000ull * 1000ull;
 struct SmallCounters {      // one slot per level (level & 3): nobody has to wait for a reset
@@ -510,7 +512,7 @@ __device__ __forceinline__ bool small_wait_peers(const SmallArgs &a, unsigned lo
 
 __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs a) {
     constexpr int NW = SMALL_NT / 32, U = 8;
-    __shared__ int s_stage[NW][P2P_MAX * SMALL_STAGE];
+    extern __shared__ int s_stage_dyn[];     // [NW][P2P_MAX][SMALL_STAGE]
     __shared__ uint32_t s_fill[NW][P2P_MAX];
     __shared__ unsigned s_gen;
     __shared__ unsigned long long s_sum[8];
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
     const int *my_inbox = reinterpret_cast<const int *>(a.peers.base[me] + a.off_inbox);
     const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
     if (threadIdx.x == 0) s_gen = ld_relaxed_gpu_u32(&sh->bar_gen);
-    int *wbuf = s_stage[warp];
+    int *wbuf = s_stage_dyn + (size_t)warp * P2P_MAX * SMALL_STAGE;
     uint32_t *wfill = s_fill[warp];
     if (lane < P2P_MAX) wfill[lane] = 0u;
 
@@ -548,42 +550,21 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
     bool finished = false;
     __syncthreads();
 
-    // ---- level 0 from a hub: one row (1.7 M arcs at scale 26) on ONE rank while the others wait was 65 us of a 0.78 ms
-    // traversal at 2 GPUs and does not shrink with P.  The owner deals the row out -- piece p, a plain copy over NVLink,
-    // into the tail of its inbox segment in rank p's heap -- and after one flag barrier every rank expands its share.
-    unsigned long long hub_deg = 0ull;   // != 0: the source's row was split (same value on every rank)
-    uint32_t hub_cnt = 0u;
-    const int *hub_idx = nullptr;
-    bool hub_coherent = false;
+    // ---- level 0 from a hub: one row (1.7 M arcs at scale 26) expanded by this kernel's id-by-id path cost 55 us on the
+    // owner at 8 GPUs plus 21 us of absorbing and 20 us of building the first pull level's bitmap slice (dealing the row
+    // out to the peers first did not help: 32 us of copying, and the expansion stayed latency-bound).  Such a level is a
+    // BIG level in everything but its vertex count: the owner tells every rank the degree of the source (one flag
+    // barrier), and from `hub_min` arcs on the level goes through the bitmap exchange -- the quad advance spreads the one
+    // row over the whole GPU and only claims bits, and every rank picks its slice out of the owner's `known`.
+    bool hub_level0 = false;
     if (level == 0 && P > 1) {
         const uint32_t src = (uint32_t)s->src;
         const int owner0 = (int)part.owner(src);
-        uint32_t chunk = 0u, rb = 0u;
+        unsigned long long hub_deg = 0ull;
         if (owner0 == me) {
             const uint32_t r = part.row(src);
-            rb = __ldg(a.offsets + r);
-            const uint32_t deg = __ldg(a.offsets + r + 1) - rb;
-            chunk = ((deg + (uint32_t)P - 1u) / (uint32_t)P + 3u) & ~3u;
-            if ((long long)deg >= s->hub_min && 2ull * chunk <= part.n_local) {
-                hub_deg = deg;
-                for (int p = 0; p < P; ++p) {
-                    if (p == me) continue;
-                    const uint32_t pb = (uint32_t)p * chunk;
-                    const uint32_t cnt = pb >= deg ? 0u : (deg - pb < chunk ? deg - pb : chunk);
-                    int *stage = reinterpret_cast<int *>(a.peers.base[p] + a.off_inbox) + (size_t)me * part.n_local + (part.n_local - chunk);
-                    const uint32_t nthr = gridDim.x * blockDim.x;
-                    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < cnt; i0 += 8u * nthr) {   // 8 loads in flight
-                        int v[8];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) v[k] = i0 + k * nthr < cnt ? __ldg(a.indices + rb + pb + i0 + k * nthr) : 0;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            if (i0 + k * nthr < cnt) stage[i0 + k * nthr] = v[k];
-                    }
-                }
-            }
+            hub_deg = __ldg(a.offsets + r + 1) - __ldg(a.offsets + r);
         }
-        if (!small_grid_barrier(sh, &s_gen, true)) hub_deg = 0ull;
         ++bar_epoch;
         if (blockIdx.x == 0 && threadIdx.x < (unsigned)P && (int)threadIdx.x != me) {
             Ctrl *pc = reinterpret_cast<Ctrl *>(a.peers.base[threadIdx.x]);
@@ -592,21 +573,14 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
         }
         const bool ok0 = small_wait_peers(a, bar_epoch);
         if (owner0 != me) hub_deg = ok0 ? ld_relaxed_sys(&my_ctrl->hub_degree) : 0ull;
-        if (hub_deg) {
-            const uint32_t deg = (uint32_t)hub_deg;
-            chunk = ((deg + (uint32_t)P - 1u) / (uint32_t)P + 3u) & ~3u;
-            const uint32_t pb = (uint32_t)me * chunk;
-            hub_cnt = pb >= deg ? 0u : (deg - pb < chunk ? deg - pb : chunk);
-            if (owner0 == me) {
-                hub_idx = a.indices + rb + pb;
-            } else {
-                hub_idx = my_inbox + (size_t)owner0 * part.n_local + (part.n_local - chunk);
-                hub_coherent = true;
-            }
-        }
+        hub_level0 = ok0 && (long long)hub_deg >= s->hub_min;
     }
 
     for (;;) {
+        if (hub_level0) {
+            next_run = LOOP_RUN_PUSH;    // level 0 through scan + claim-only advance + bitmap absorb, in this graph iteration
+            break;
+        }
         SmallCounters *c = &sh->slot[level & (SMALL_SLOTS - 1)];
         if (lead) small_zero_slot(&sh->slot[(level + 1) & (SMALL_SLOTS - 1)]);   // last used three levels ago
         const int next_label = level + 1;
@@ -618,23 +592,22 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
             if (lane == 0) base = atomicAdd(p == me ? &c->next_cnt : &c->send_cnt[p], (unsigned long long)count);
             base = __shfl_sync(FULL_MASK, base, 0);
             int *box = p == me ? out : reinterpret_cast<int *>(a.peers.base[p] + a.off_inbox) + (size_t)me * part.n_local;
-            if (lane < count) {
-                if (base + lane < part.n_local) box[base + lane] = wbuf[p * SMALL_STAGE + lane];
+            for (uint32_t k = lane; k < count; k += 32u) {
+                if (base + k < part.n_local) box[base + k] = wbuf[p * SMALL_STAGE + k];
                 else c->overflow = 1ull;
             }
         };
         // the per-arc step of a warp over arcs [b, e) of one row piece, 32 * U arcs at a time: all index loads, then all
         // probes, then all claims are in flight together; the winners are counted per destination over the whole tile and
         // every destination's slots are reserved with ONE atomic, the P atomics issued side by side by lanes 0 .. P-1
-        // (idx: the local col_indices, or -- coherent -- a piece of the source's row a peer staged in this rank's heap)
-        auto expand = [&](const int *idx, bool coherent, uint32_t b, uint32_t e) {
+        auto expand = [&](uint32_t b, uint32_t e) {
             for (uint32_t e0 = b; e0 < e; e0 += 32u * U) {
                 int d[U], owner[U];
                 uint32_t kb[U], w[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const uint32_t ee = e0 + 32u * u + lane;
-                    d[u] = ee < e ? (coherent ? __ldcg(idx + ee) : __ldg(idx + ee)) : -1;
+                    d[u] = ee < e ? __ldg(a.indices + ee) : -1;
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -665,10 +638,10 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
                     }
                 }
                 if (!__any_sync(FULL_MASK, any)) continue;
-                // winners go to their owner's box through this warp's staging rows (one row of 64 slots per destination in
-                // shared memory): a row is flushed 32 ids at a time -- ONE slot reservation and ONE 128-byte store, local or
-                // over NVLink.  (Storing every id on its own -- 4 bytes per peer-memory request -- kept the expansion of a
-                // 213 K-arc share of the hub row at 43 us, whether 2 or 8 GPUs shared the row.)
+                // winners go to their owner's box through this warp's staging rows (one row per destination in shared
+                // memory): a row is flushed SMALL_FLUSH ids at a time -- ONE slot reservation and full 128-byte stores, local
+                // or over NVLink.  (A reservation per 32 winners was 20 K atomics on one counter for the 0.64 M discoveries of a
+                // scale-25 hub row: the warps stood in line for ~27 of the level's 51 us.)
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     if (!__any_sync(FULL_MASK, owner[u] >= 0)) continue;
@@ -679,12 +652,12 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
                         if (owner[u] == p) wbuf[p * SMALL_STAGE + f + __popc(mask & lt_mask)] = d[u];
                         f += __popc(mask);
                         __syncwarp();
-                        if (f >= 32u) {
-                            flush_row(p, 32u);
-                            const int x = lane < f - 32u ? wbuf[p * SMALL_STAGE + 32u + lane] : 0;
+                        if (f >= SMALL_FLUSH) {
+                            flush_row(p, SMALL_FLUSH);
+                            const int x = lane < f - SMALL_FLUSH ? wbuf[p * SMALL_STAGE + SMALL_FLUSH + lane] : 0;   // (< 32 are left)
                             __syncwarp();
-                            if (lane < f - 32u) wbuf[p * SMALL_STAGE + lane] = x;
-                            f -= 32u;
+                            if (lane < f - SMALL_FLUSH) wbuf[p * SMALL_STAGE + lane] = x;
+                            f -= SMALL_FLUSH;
                         }
                         __syncwarp();
                         if (lane == 0) wfill[p] = f;
@@ -702,12 +675,11 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
             // may hold a line of an earlier level, so they are read through L2)
             const uint32_t r = (uint32_t)__ldcg(in + i) >> part.log_p;
             const uint32_t b = __ldg(a.offsets + r), e = __ldg(a.offsets + r + 1);
-            if (hub_deg && level == 0) continue;     // the source's row was split over the ranks: see pass 2
             if (e - b > SMALL_ROW) {
                 if (lane == 0) a.big[atomicAdd(&c->big_cnt, 1ull)] = r;
                 continue;
             }
-            if (e > b) expand(a.indices, false, b, e);
+            if (e > b) expand(b, e);
         }
         for (int p = 0; p < P; ++p) {                // what is left in this warp's staging rows
             const uint32_t f = wfill[p];
@@ -719,15 +691,6 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
         if (!small_grid_barrier(sh, &s_gen, true)) break;
         // ---- pass 2: the pieces of the long rows, dealt round-robin over the warps of the grid
         const uint32_t nbig = (uint32_t)ld_volatile_u64(&c->big_cnt);
-        const bool hub_level = hub_deg != 0ull && level == 0;
-        if (hub_level) {
-            // this rank's share of the source's row (from its own CSR on the owner, from the staged copy elsewhere)
-            const uint32_t pieces = (hub_cnt + SMALL_ROW - 1) / SMALL_ROW;
-            for (uint32_t p = gwarp; p < pieces; p += total_warps) {
-                const uint32_t pb = p * SMALL_ROW;
-                expand(hub_idx, hub_coherent, pb, hub_cnt - pb > SMALL_ROW ? pb + SMALL_ROW : hub_cnt);
-            }
-        }
         if (nbig) {
             uint32_t skew = 0;
             for (uint32_t k = 0; k < nbig; ++k) {
@@ -736,12 +699,12 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
                 const uint32_t pieces = (e - b + SMALL_ROW - 1) / SMALL_ROW;
                 for (uint32_t p = (gwarp + total_warps - skew) % total_warps; p < pieces; p += total_warps) {
                     const uint32_t pb = b + p * SMALL_ROW;
-                    expand(a.indices, false, pb, e - pb > SMALL_ROW ? pb + SMALL_ROW : e);
+                    expand(pb, e - pb > SMALL_ROW ? pb + SMALL_ROW : e);
                 }
                 skew = (skew + pieces) % total_warps;
             }
         }
-        if (nbig || hub_level) {
+        if (nbig) {
             for (int p = 0; p < P; ++p) {            // what is left in this warp's staging rows
                 const uint32_t f = wfill[p];
                 __syncwarp();
@@ -923,8 +886,8 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
             // (The slice is NOT cleared first: the prologue zeroes both slices, and whatever a big push level or an earlier
             // pull phase of THIS traversal left there are vertices of earlier levels, all of whose neighbours are visited --
             // as frontier bits they cannot label anybody.)
+            // (The "no in-arc" preset of `done` is applied by the pull-levels kernel that follows: LOOP_RUN_TO_PULL.)
             uint32_t *slice_w = reinterpret_cast<uint32_t *>(a.peers.base[me] + (bsel ? a.off_slice0 : a.off_slice1));
-            or_no_in_arc_words(blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, a.pull_offsets, part.n_local, a.iso, a.done);
             for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
                 const uint32_t r = part.row((uint32_t)__ldcg(in + i));
                 atomicOr(slice_w + (r >> 5), 1u << (r & 31));
@@ -935,7 +898,7 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
                 st_release_sys(&reinterpret_cast<Ctrl *>(a.peers.base[threadIdx.x])->flags[me], bar_epoch);
             if (!small_wait_peers(a, bar_epoch)) break;
             bsel ^= 1u;
-            next_run = LOOP_RUN_PULL;
+            next_run = LOOP_RUN_PULL | LOOP_RUN_TO_PULL;
             break;
         }
         if (next_deg > small_arcs) {
@@ -957,7 +920,7 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
         s->bar_epoch = bar_epoch;
         s->stats_seq = stats_seq;
         s->launches = launches;
-        s->pull = next_run == LOOP_RUN_PULL ? 1 : 0;
+        s->pull = (next_run & LOOP_RUN_PULL) ? 1 : 0;
         s->dyn.in = in;
         s->dyn.out = out;
         s->dyn.len = len;
@@ -1132,6 +1095,10 @@ __global__ void __launch_bounds__(256) p2p_gather_or_dyn_kernel(Peers peers, siz
 // cross-GPU synchronisation of a pull level: it also tells the peers that this rank's new slice is complete.
 // ---------------------------------------------------------------------------------------------
 constexpr int PULL_NT = 256;
+#ifndef B200_P2P_PULL_CW
+#define B200_P2P_PULL_CW 32
+#endif
+constexpr int PULL_CW = B200_P2P_PULL_CW;   // see bfs_pull_body
 struct PullArgs {
     Peers peers;
     int me, P;
@@ -1178,7 +1145,7 @@ __global__ void __launch_bounds__(PULL_NT, 4) p2p_pull_levels_kernel(PullArgs a)
     int status = B200_OK;
     uint32_t next_run = 0u;
     unsigned long long next_local = 0ull;
-    bool finished = false;
+    bool finished = false, first_level = true;
     // first pull level after a big push level: rows without in-arcs count as done from here on (engine.cuh); the grid
     // barrier after the gather orders this before the first read of `done`
     if (s->dyn.run & LOOP_RUN_TO_PULL)
@@ -1227,8 +1194,17 @@ __global__ void __launch_bounds__(PULL_NT, 4) p2p_pull_levels_kernel(PullArgs a)
         }
         if (!small_grid_barrier(sh, &s_gen)) break;
         loop_trace(&s->dyn, 32);
-        bfs_pull_body<PULL_NT, true>(part.n_local, a.pull_offsets, a.pull_indices, a.full, slice[bsel ^ 1u], a.done, a.labels, level + 1,
-                                     c->c, part, a.first_nbr);
+        // The first pull level of a launch may read the bitmaps through L1 / the non-coherent path: nothing of `full` or `done`
+        // was read earlier in this launch, so no stale line can exist (what the gather and the preset just wrote is in L2,
+        // ordered by the grid barrier).  That level is the heavy one (28 M of 33 M discoveries at scale 26), and the L2-only
+        // variant was 2x slower on it (444 vs ~210 us at scale 25 on one GPU).  Later levels of the launch must read through L2.
+        if (first_level)
+            bfs_pull_body<PULL_NT, false, PULL_CW>(part.n_local, a.pull_offsets, a.pull_indices, a.full, slice[bsel ^ 1u], a.done,
+                                                   a.labels, level + 1, c->c, part, a.first_nbr);
+        else
+            bfs_pull_body<PULL_NT, true, PULL_CW>(part.n_local, a.pull_offsets, a.pull_indices, a.full, slice[bsel ^ 1u], a.done,
+                                                  a.labels, level + 1, c->c, part, a.first_nbr);
+        first_level = false;
         if (!small_grid_barrier(sh, &s_gen, true)) break;   // (system scope: the new slice, before the flag that says it is complete)
         // ---- level summary: row to every peer, flags, sums
         next_local = ld_volatile_u64(&c->c[B200_CNT_OUT]);
@@ -1673,7 +1649,7 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
                                           (long long)s->n_global, part, ws->d_counters, ws->d_tile_counter, s->small,
                                           s->pull_slots, kernels_per_level);
     LL_CUDA(cudaGetLastError());
-    p2p_small_levels_kernel<<<(unsigned)s->small_grid, SMALL_NT, 0, cs>>>(sa);
+    p2p_small_levels_kernel<<<(unsigned)s->small_grid, SMALL_NT, SMALL_SMEM, cs>>>(sa);
     LL_CUDA(cudaGetLastError());
     capturing = false;
     if ((st = end_capture(cs, deps, &ndeps, 8)) != B200_OK) goto fail;
@@ -1746,7 +1722,7 @@ int p2p_build_graph(b200_p2p_bfs *s, const b200_graph *g, int32_t *d_labels, int
             LL_CUDA(cudaGetLastError());
         }
         // (5) the small levels that follow (the tail of the traversal, usually)
-        p2p_small_levels_kernel<<<(unsigned)s->small_grid, SMALL_NT, 0, cs>>>(sa);
+        p2p_small_levels_kernel<<<(unsigned)s->small_grid, SMALL_NT, SMALL_SMEM, cs>>>(sa);
         LL_CUDA(cudaGetLastError());
     }
     capturing = false;
@@ -1954,7 +1930,8 @@ int b200_p2p_bfs_create(b200_ctx *ctx, int rank, int num_ranks, int64_t n_global
         {
             // the small-level kernel synchronises its grid itself: every CTA must be resident
             int occ = 0;
-            if ((st = cuda_status(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p2p_small_levels_kernel, SMALL_NT, 0)))) break;
+            if ((st = cuda_status(cudaFuncSetAttribute(p2p_small_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM)))) break;
+            if ((st = cuda_status(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p2p_small_levels_kernel, SMALL_NT, SMALL_SMEM)))) break;
             if (occ < 1) {
                 st = B200_ERR_UNSUPPORTED;
                 break;

@@ -188,10 +188,17 @@ class Graph:
         self.first_in_nbr = None
         self.hot_ids = None     # derived data (Context.prepare_hot_columns)
         self.hot_indices = None
+        self.csc = None         # (col_offsets, row_indices, row_values) of a directed graph's true transpose; None = aliases the CSR
+
+    def set_csc(self, col_offsets, row_indices, row_values=None):
+        """Attach the true CSC of a directed graph (d_col_offsets / d_row_indices / d_row_values, graph.hxx:44-46)."""
+        self.csc = (col_offsets, row_indices, row_values)
+        return self
 
     def cview(self) -> CGraph:
+        co, ri, rv = self.csc if self.csc is not None else (self.row_offsets, self.col_indices, self.col_values)
         return CGraph(self.n, self.m, _ptr(self.row_offsets), _ptr(self.col_indices), _ptr(self.col_values),
-                      _ptr(self.row_offsets), _ptr(self.col_indices), _ptr(self.col_values), _ptr(self.no_in_arc),
+                      _ptr(co), _ptr(ri), _ptr(rv), _ptr(self.no_in_arc),
                       _ptr(self.first_in_nbr), _ptr(self.hot_ids), _ptr(self.hot_indices),
                       0 if self.hot_ids is None else self.hot_ids.numel())
 

@@ -17,11 +17,13 @@ from mini_b200 import dist as D
 from mini_b200.p2p import P2PBfs
 
 scale = int(sys.argv[1]) if len(sys.argv) > 1 else 14
+loops = sys.argv[2] if len(sys.argv) > 2 else "both"      # host | graph | both
+with_p2p = (sys.argv[3] if len(sys.argv) > 3 else "1") == "1"
 ctx = mb.Context(0)
 g = ctx.prepare_graph(ctx.rmat_graph(scale, 16, 1, weighted=True))
 o = oracle.CSR(g.n, g.offsets_host(), g.col_indices.cpu().numpy(), g.col_values.cpu().numpy())
 ref = oracle.bfs(o, 0)
-for loop in (mb.LOOP_GRAPH, mb.LOOP_HOST):
+for loop in [l for l, name in ((mb.LOOP_GRAPH, "graph"), (mb.LOOP_HOST, "host")) if loops in (name, "both")]:
     ctx.set_level_loop(loop)
     for mode in (mb.BFS_PUSH, mb.BFS_BEAMER, mb.BFS_REF_ALPHA):
         lab, _ = ctx.bfs(g, 0, mode, 15.0 if mode != mb.BFS_REF_ALPHA else 2.0, 18.0)
@@ -36,7 +38,7 @@ ctx.prepare_hot_columns(g, hot_count=4096)
 cur, red, lens, _ = ctx.pr(g, 3, False)
 assert list(lens) == olens.tolist() and np.allclose(cur.cpu().numpy(), ocur, rtol=1e-4, atol=1e-6)
 # one-rank peer-memory BFS: the persistent kernels with their grid barriers (no peer, so no flag waits)
-for small in ("1", "0"):
+for small in (("1", "0") if with_p2p else ()):
     os.environ["B200_P2P_SMALL"] = small
     gp = ctx.prepare_graph(D.build_rank_graph(ctx, scale, 16, 1, 0, 1))
     rk = P2PBfs(ctx, 0, 1, g.n, g.m, gp)
@@ -46,4 +48,4 @@ for small in ("1", "0"):
         assert np.array_equal(rk.labels.cpu().numpy(), ref), (small, mode)
     rk.close()
 ctx.close()
-print("SANITIZE_RUN_OK scale", scale)
+print("SANITIZE_RUN_OK scale", scale, "loops", loops, "p2p", with_p2p)

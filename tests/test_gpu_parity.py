@@ -591,6 +591,36 @@ def test_hot_columns_derived_data(ctx, hot_count):
     _check_reduce(red.cpu().numpy(), ref, asum)
 
 
+def test_neighborhood_reduce_push_and_pull_on_a_directed_graph(ctx):
+    """push = true reduces over the OUT-neighbours (CSR), push = false over the IN-neighbours (the true CSC of a directed
+    graph, attached with set_csc): neighborhood.hxx:26-33 picks the arrays by that flag.  Also BFS in a direction-
+    optimising mode with a real transpose: pull levels then follow in-arcs, and the depths are those of the push BFS."""
+    import mini_b200 as mb
+    rng = np.random.default_rng(21)
+    n = 4000
+    s = rng.integers(0, n, 30000).astype(np.int32)
+    d = rng.integers(0, n, 30000).astype(np.int32)
+    o = oracle.build_csr(n, s, d, False, False)          # arcs s -> d
+    ot = oracle.build_csr(n, d, s, False, False)         # the transpose
+    g = ctx.graph_from_host(o.offsets, o.indices)
+    gt = ctx.graph_from_host(ot.offsets, ot.indices)
+    g.set_csc(gt.row_offsets, gt.col_indices)
+    vals = rng.random(n).astype(np.float32)
+    frontier = rng.permutation(n)[: n // 2].astype(np.int32)
+    for push, oo in ((True, o), (False, ot)):
+        ref, asum = oracle.neighborhood_reduce(oo, frontier, vals.astype(np.float64), "plus", identity=-1.0)
+        red = torch.empty(len(frontier), dtype=torch.float32, device="cuda")
+        arcs = ctx.neighborhood_reduce(g, torch.from_numpy(frontier).cuda(), torch.from_numpy(vals).cuda(), red, identity=-1.0,
+                                       op=mb.OP_PLUS, push=push)
+        assert arcs == int((oo.offsets[frontier + 1] - oo.offsets[frontier]).sum())
+        _check_reduce(red.cpu().numpy(), ref, asum)
+    for src in (0, 17, 3999):
+        want = oracle.bfs(o, src)
+        for mode, alpha in ((mb.BFS_BEAMER, 15.0), (mb.BFS_REF_ALPHA, 2.0)):
+            labels, st = ctx.bfs(g, src, mode, alpha, 18.0)
+            assert np.array_equal(labels.cpu().numpy(), want), (src, mode)
+
+
 def test_neighborhood_reduce_nonfinite_values_read_as_zero(ctx):
     o = oracle.rmat_csr(9, 16, 1)
     g = _dev_graph(ctx, o)
