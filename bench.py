@@ -158,10 +158,29 @@ def run_sssp_leg(ctx, mb, args, peak):
     roof = _per_level(lambda: ctx.sssp(g, 0, dist=dist, timing=True)[1], 5, sssp_level_bytes, peak)
     roof["kernel"] = "quad_advance_kernel<SsspRelaxQ,COMPACT> (heaviest iteration)"
     out = {"workload": f"SSSP from vertex 0, RMAT scale-{scale} ef16 symmetrised, uniform integer weights [1,64] "
-                       "as fp32, LB advance with the per-iteration de-duplicating stamp (Bellman-Ford frontier iterations)",
+                       "as fp32, LB advance with the per-iteration de-duplicating stamp; frontier iterations in near-far "
+                       "order (buckets taken from the distance array, automatic width; SURVEY 8f-4)",
            "value": reached_arcs / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "steps": steps,
            "iterations": st.num_levels, "relaxed_arcs": st.total_arcs, "reached_arcs": reached_arcs,
+           "relaxed_over_reached": st.total_arcs / max(reached_arcs, 1),
            "gpu_launches": launches, "roofline": roof}
+    # the reference's order (every improved vertex expanded in the next iteration, sssp_enactor.hxx:51-70), same kernels
+    ctx.set_sssp_delta(float("inf"))
+    try:
+        for _ in range(2):
+            ctx.sssp(g, 0, dist=dist)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            _, st_bf = ctx.sssp(g, 0, dist=dist)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_bf = e0.elapsed_time(e1) / steps
+        out["bellman_ford_order"] = {"ms_per_step": ms_bf, "value": reached_arcs / (ms_bf * 1e-3) / 1e9, "unit": UNIT,
+                                     "iterations": st_bf.num_levels, "relaxed_arcs": st_bf.total_arcs,
+                                     "relaxed_over_reached": st_bf.total_arcs / max(reached_arcs, 1)}
+    finally:
+        ctx.set_sssp_delta(0.0)
     if args.parity:
         # full-size parity: distances memcmp-equal to the CPU oracle (Dijkstra under sssp_functor.hxx:20-29) on the
         # device-built CSR; and, when it was built, to the reference's own GPU enactor

@@ -49,6 +49,41 @@ __device__ __forceinline__ void loop_trace(const LoopDyn *dyn, unsigned id) {
 // kernel checks its bit.
 enum : uint32_t { LOOP_RUN_PUSH = 1u, LOOP_RUN_PULL = 2u, LOOP_RUN_TO_PULL = 4u, LOOP_RUN_TO_PUSH = 8u,
                   LOOP_RUN_SCAN = 16u,     // the push level's frontier has no scan yet (first level, after a hand-over)
-                  LOOP_RUN_SMALL = 32u };  // multi-GPU: the next push levels are small -- one persistent kernel runs them (p2p_bfs.cu)
+                  LOOP_RUN_SMALL = 32u,    // multi-GPU: the next push levels are small -- one persistent kernel runs them (p2p_bfs.cu)
+                  LOOP_RUN_TAKE = 64u };   // near-far SSSP: the near frontier ran dry -- open the next bucket (near_far.cuh)
+
+// Device-resident state of the near-far SSSP loop (b200_sssp_run).  The reference's enactor is
+// frontier Bellman-Ford (sssp_enactor.hxx:40-72): every improved vertex is expanded in the next iteration, however
+// far from final its distance is.  Here a vertex improved to a distance >= cutoff is NOT appended to the next
+// frontier; it stays pending (its distance array entry is the only record) until the near frontier runs dry, then
+// every vertex with a distance in the next bucket [lo, lo + delta) -- none of which can have been expanded yet,
+// weights being non-negative -- becomes the near frontier.  Distances are the same fixed point either way.
+struct NearFar {
+    float cutoff;                // an improved vertex joins the next near frontier iff its new distance is below this
+    float lo;                    // the open bucket is [lo, cutoff)
+    float delta, delta0;         // bucket width now / at the start (widened once buckets get small, see near_far.cuh)
+    unsigned int pending_min;    // bits of the smallest finite distance >= cutoff (distances are >= 0: bits order as floats)
+    unsigned int taken;          // vertices the take pass moved into the near frontier
+    unsigned int ticket[2];      // last-CTA-done tickets of the two passes
+    long long bucket_arcs;       // arcs expanded since the bucket was opened
+    long long total_arcs;        // ... in the buckets closed so far
+    long long m;
+    int buckets, done, peaked, pad;
+};
+
+__device__ __forceinline__ void near_far_reset(NearFar *nf, float delta0, long long m) {
+    nf->cutoff = delta0;         // the first bucket is [0, delta0): the source is its only member
+    nf->lo = 0.f;
+    nf->delta = nf->delta0 = delta0;
+    nf->pending_min = 0x7f7fffffu;   // FLT_MAX: nothing pending
+    nf->taken = 0u;
+    nf->ticket[0] = nf->ticket[1] = 0u;
+    nf->bucket_arcs = 0;
+    nf->total_arcs = 0;
+    nf->m = m;
+    nf->buckets = 1;
+    nf->done = 0;
+    nf->peaked = 0;
+}
 
 }  // namespace b200

@@ -613,6 +613,7 @@ struct SsspRelaxQ {
     int *preds;
     int *stamp;      // nullable => idempotent output (duplicates kept)
     int iteration;
+    const NearFar *nf;   // nullable => every improved vertex is emitted (the reference's Bellman-Ford iterations)
     static constexpr bool WEIGHTED = true;
     using SrcVal = float;
     using Token = float;
@@ -634,6 +635,7 @@ struct SsspRelaxQ {
     __device__ __forceinline__ int finish(Token old, const Cand &c) const {
         if (!(__int_as_float((int)c.w[1]) < old)) return -1;
         if (preds) preds[c.w[0]] = (int)c.w[2];
+        if (nf && !(__int_as_float((int)c.w[1]) < nf->cutoff)) return -1;   // pending: its bucket will take it
         if (stamp && atomicExch(stamp + c.w[0], iteration) == iteration) return -1;
         return (int)c.w[0];
     }
@@ -645,6 +647,7 @@ struct SsspRelaxQDyn : SsspRelaxQ {
     __device__ __forceinline__ int finish(Token old, const Cand &c) const {
         if (!(__int_as_float((int)c.w[1]) < old)) return -1;
         if (preds) preds[c.w[0]] = (int)c.w[2];
+        if (nf && !(__int_as_float((int)c.w[1]) < nf->cutoff)) return -1;
         const int it = dyn->next_label - 1;
         if (stamp && atomicExch(stamp + c.w[0], it) == it) return -1;
         return (int)c.w[0];

@@ -283,6 +283,14 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
  * d_dist [n] overwritten; d_preds nullable. */
 int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist, int32_t *d_preds,
                   b200_stats *stats /* nullable */);
+/* Order of the frontier iterations inside b200_sssp_run.  The reference expands every improved vertex
+ * in the next iteration (Bellman-Ford frontiers, sssp_enactor.hxx:51-70); b200_sssp_run holds back vertices whose new
+ * distance is >= a moving cutoff until every smaller distance is final ("near-far": buckets of width delta taken from
+ * the distance array itself, mini_b200/csrc/near_far.cuh), which relaxes ~1.0x instead of ~1.8x the reached arcs on
+ * RMAT-22.  Distances are identical for any width (the same fixed point); weights must be non-negative.
+ *   delta = 0 (default): 3.5 * mean weight / mean degree, sampled once per graph;  delta = INFINITY: the reference's
+ *   order;  else: the first bucket width.  stats->num_levels counts advance iterations in every case. */
+int b200_ctx_set_sssp_delta(b200_ctx *ctx, float delta);
 
 /* pr_enactor_t::enact (pr_enactor.hxx:41-79) + pr_problem_t ctor (pr_problem.hxx:34-44).
  * scatter = 0 reproduces the reference's slot-indexed reduced[],

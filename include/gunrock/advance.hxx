@@ -12,6 +12,7 @@
 // Either way a following filter_kernel yields the same frontier, so enactors written
 // against the reference work unchanged.
 #pragma once
+#include <type_traits>
 #include "b200/operators.cuh"
 #include "frontier.hxx"
 #include "intrinsics.hxx"
@@ -71,6 +72,42 @@ struct RefFunctorQ {
     __device__ __forceinline__ int finish(Token accepted, const Cand &c) const { return accepted ? (int)c.w[0] : -1; }
 };
 
+// Opt-in functor trait: `static constexpr bool cond_advance_guards_apply = true;` states that cond_advance has no side
+// effect and that apply_advance cannot succeed (and changes nothing) for an arc whose cond_advance is false -- the BFS
+// pair "label still -1?" / atomicCAS(label, -1, depth) is the model case (bfs_functor.hxx:26-35).  For such a functor
+// `cond && apply` (advance.hxx:57-60) may short-circuit: cond_advance becomes the quad kernel's stage-1 probe (one
+// cached load per arc, issued a pipeline stage ahead) and only the survivors reach apply_advance in stage 2, instead of
+// one atomic per arc.  Functors without the member keep the evaluate-both adapter above.
+template <typename F, typename = void>
+struct cond_guards_apply : std::false_type {};
+template <typename F>
+struct cond_guards_apply<F, std::void_t<decltype(F::cond_advance_guards_apply)>> : std::integral_constant<bool, F::cond_advance_guards_apply> {};
+
+template <typename Problem, typename Functor>
+struct RefFunctorGuardQ {
+    typename Problem::data_slice_t *data;
+    int iteration;
+    const int *offsets;
+    static constexpr bool WEIGHTED = false;
+    using SrcVal = b200::NoSrc;
+    using Evidence = bool;
+    using Token = bool;
+    using Cand = b200::CandWords<3>;   // dst, src, arc id
+    __device__ __forceinline__ SrcVal load_src(int) const { return SrcVal(); }
+    __device__ __forceinline__ Evidence probe_load(bool on, SrcVal, int src, int dst, uint32_t eid) const {
+        return on && Functor::cond_advance(src, dst, (int)eid, (int)eid - offsets[src], (int)eid, data, iteration);
+    }
+    __device__ __forceinline__ bool probe_eval(Evidence ok, SrcVal, int, float) const { return ok; }
+    __device__ __forceinline__ Cand make_cand(SrcVal, int src, int dst, uint32_t eid, float) const {
+        return Cand{{(uint32_t)dst, (uint32_t)src, eid}};
+    }
+    __device__ __forceinline__ Token claim(const Cand &c) const {
+        const int src = (int)c.w[1], dst = (int)c.w[0], eid = (int)c.w[2];
+        return Functor::apply_advance(src, dst, eid, eid - offsets[src], eid, data, iteration);
+    }
+    __device__ __forceinline__ int finish(Token accepted, const Cand &c) const { return accepted ? (int)c.w[0] : -1; }
+};
+
 // degree scan of `input` over `offsets`; also mirrors the scan into the graph's
 // d_scanned_row_offsets like the reference does (advance.hxx:40).
 inline void scan_frontier(b200_workspace *ws, const int *frontier, size_t len, const int *offsets, int *mirror,
@@ -105,7 +142,10 @@ int advance_forward_kernel(std::shared_ptr<Problem> problem, std::shared_ptr<fro
         detail::check(b200::reset_counters(ws));
         detail::check(b200::launch_quad_scan(ws, in, (uint32_t)len, off));
         const b200::QuadArgs qa = b200::make_quad_args(ws, in, (uint32_t)len, off, g.d_col_indices.data(), nullptr);
-        detail::RefFunctorQ<Problem, Functor, idempotence> qop{problem->d_data_slice.data(), iteration, g.d_row_offsets.data()};
+        using QOp = typename std::conditional<!idempotence && detail::cond_guards_apply<Functor>::value,
+                                              detail::RefFunctorGuardQ<Problem, Functor>,
+                                              detail::RefFunctorQ<Problem, Functor, idempotence>>::type;
+        QOp qop{problem->d_data_slice.data(), iteration, g.d_row_offsets.data()};
         if (has_output) detail::check((b200::launch_quad_advance<b200::OUT_COMPACT, false>(ws, qa, qop, out, cap)));
         else detail::check((b200::launch_quad_advance<b200::OUT_NONE, false>(ws, qa, qop, nullptr, 0ull)));
         detail::check(b200::read_counters(ws));

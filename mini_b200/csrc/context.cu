@@ -6,6 +6,7 @@
 #include <new>
 #include "engine.cuh"
 #include "b200/device_utils.cuh"
+#include "b200/loop_dyn.cuh"
 
 namespace b200 {
 thread_local int g_last_cuda_error = 0;
@@ -151,6 +152,9 @@ int b200_ctx_create(b200_ctx **out, int device, void *stream) {
     B200_CUDA(cudaMemset(ctx->ws.d_counters, 0, sizeof(unsigned long long) * B200_NUM_COUNTERS));
     B200_CUDA(cudaMallocHost(&ctx->ws.h_counters, sizeof(unsigned long long) * B200_NUM_COUNTERS));
     B200_CUDA(cudaMalloc(&ctx->ws.d_tile_counter, 64));
+    B200_CUDA(cudaMalloc(&ctx->d_nf, sizeof(b200::NearFar)));
+    B200_CUDA(cudaMemset(ctx->d_nf, 0, sizeof(b200::NearFar)));
+    B200_CUDA(cudaMalloc(&ctx->d_nf_sum, sizeof(double)));
     B200_CUDA(cudaMemset(ctx->ws.d_tile_counter, 0, 64));
     B200_CUDA(cudaEventCreate(&ctx->ev_run[0]));
     B200_CUDA(cudaEventCreate(&ctx->ev_run[1]));
@@ -224,6 +228,13 @@ int b200_ctx_set_level_loop(b200_ctx *ctx, int impl) {
 int b200_ctx_forget_graph(b200_ctx *ctx) {
     if (!ctx) return B200_ERR_INVALID;
     level_loop_invalidate(ctx);
+    ctx->nf_key_w = nullptr;
+    return B200_OK;
+}
+
+int b200_ctx_set_sssp_delta(b200_ctx *ctx, float delta) {
+    if (!ctx || !(delta >= 0.f)) return B200_ERR_INVALID;
+    ctx->sssp_delta = delta;
     return B200_OK;
 }
 
@@ -292,6 +303,8 @@ int b200_ctx_destroy(b200_ctx *ctx) {
     if (ctx->ws.h_counters) cudaFreeHost(ctx->ws.h_counters);
     if (ctx->ws.d_tile_counter) cudaFree(ctx->ws.d_tile_counter);
     if (ctx->hot_vals) cudaFree(ctx->hot_vals);
+    if (ctx->d_nf) cudaFree(ctx->d_nf);
+    if (ctx->d_nf_sum) cudaFree(ctx->d_nf_sum);
     if (ctx->own_stream) cudaStreamDestroy((cudaStream_t)ctx->ws.stream);
     delete ctx;
     return B200_OK;

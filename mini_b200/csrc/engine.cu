@@ -8,6 +8,7 @@
 #include <new>
 #include "b200/operators.cuh"
 #include "engine.cuh"
+#include "near_far.cuh"
 
 using namespace b200;
 
@@ -583,6 +584,38 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
     return B200_OK;
 }
 
+// First bucket width of the near-far loop (near_far.cuh): what b200_ctx_set_sssp_delta chose, else 3.5 * mean weight
+// / mean degree from a strided sample of <= 65536 weights, computed once per (weights array, n, m).
+static int sssp_delta0(b200_ctx *ctx, const b200_graph *g, float *out) {
+    if (ctx->sssp_delta > 0.f) {
+        *out = ctx->sssp_delta;
+        return B200_OK;
+    }
+    if (ctx->nf_key_w != g->col_values || ctx->nf_key_n != g->n || ctx->nf_key_m != g->m) {
+        float delta = INFINITY;
+        if (g->m > 0) {
+            cudaStream_t st = ws_stream(&ctx->ws);
+            const unsigned long long m = (unsigned long long)g->m;
+            const unsigned long long step = m > 65536ull ? m / 65536ull : 1ull;
+            const unsigned int samples = (unsigned int)((m + step - 1) / step);
+            double sum = 0.0;
+            B200_CUDA(cudaMemsetAsync(ctx->d_nf_sum, 0, sizeof(double), st));
+            nf_weight_sample_kernel<<<(samples + 255) / 256, 256, 0, st>>>(g->col_values, m, step, samples, ctx->d_nf_sum);
+            B200_CUDA(cudaGetLastError());
+            B200_CUDA(cudaMemcpyAsync(&sum, ctx->d_nf_sum, sizeof(double), cudaMemcpyDeviceToHost, st));
+            B200_CUDA(cudaStreamSynchronize(st));
+            const double d = 3.5 * (sum / (double)samples) * (double)g->n / (double)g->m;
+            if (d > 0.0 && d < 1e30) delta = (float)d;   // all-zero (or non-finite) weights: one bucket = Bellman-Ford
+        }
+        ctx->nf_key_w = g->col_values;
+        ctx->nf_key_n = g->n;
+        ctx->nf_key_m = g->m;
+        ctx->nf_auto_delta = delta;
+    }
+    *out = ctx->nf_auto_delta;
+    return B200_OK;
+}
+
 int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist, int32_t *d_preds, b200_stats *stats) {
     if (!ctx || !g || !d_dist || !g->col_values || g->n < 1 || src < 0 || src >= g->n || g->n > (1ll << 31))
         return B200_ERR_INVALID;
@@ -601,12 +634,16 @@ int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist
     int64_t next_quads = 0;
     int wsel = 0;
     int sel = 0, it = 0;
-    int64_t flen = 1, total_arcs = 0;
+    int64_t flen = 1, total_arcs = 0, bucket_arcs = 0;
+    // near-far ordering of the frontier iterations (near_far.cuh); the arc-wise kernel keeps the reference's order
+    float delta0 = INFINITY;
+    if (quad) B200_TRY(sssp_delta0(ctx, g, &delta0));
+    const NearFar *nf = (quad && delta0 < INFINITY) ? ctx->d_nf : nullptr;
     if (quad && !timing && ctx->loop_impl == B200_LOOP_GRAPH) {
         // the frontier iterations as one CUDA graph (level_loop.cu); the predecessor pass follows below
         b200_stats *gst = stats ? stats : new (std::nothrow) b200_stats;
         if (!gst) return B200_ERR_NOMEM;
-        const int gs = sssp_run_graph(ctx, g, src, d_dist, gst);
+        const int gs = sssp_run_graph(ctx, g, src, d_dist, delta0, gst);
         if (gs == B200_OK) {
             graph_done = true;
             it = gst->num_levels;
@@ -624,6 +661,10 @@ int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist
     sssp_init_kernel<<<ws->num_sms * 4, 256, 0, st>>>(d_dist, d_preds, ctx->stamp, (unsigned long long)n);
     sssp_seed_kernel<<<1, 1, 0, st>>>(d_dist, ctx->frontier[0], src);
     ws->launches += 2;
+    if (nf) {
+        nf_init_kernel<<<1, 1, 0, st>>>(ctx->d_nf, delta0, (long long)g->m);
+        ws->launches++;
+    }
     B200_CUDA(cudaGetLastError());
     for (;;) {
         b200_level_stat *ls = (stats && it < B200_MAX_LEVELS) ? &stats->level[it] : nullptr;
@@ -647,7 +688,7 @@ int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist
                 a.scanned_next = sc[wsel ^ 1];
                 a.rows_next = rw[wsel ^ 1];
             }
-            SsspRelaxQ op{d_dist, nullptr, ctx->stamp, it};   // preds: one exact pass at the end
+            SsspRelaxQ op{d_dist, nullptr, ctx->stamp, it, nf};   // preds: one exact pass at the end
             if (tl) B200_CUDA(cudaEventRecord(ev[3 * it + 1], st));
             B200_CUDA((launch_quad_advance<OUT_COMPACT, false>(ws, a, op, ctx->frontier[sel ^ 1], (unsigned long long)n)));
         } else {
@@ -675,7 +716,23 @@ int b200_sssp_run(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist
             ls->discovered = found;
         }
         total_arcs += arcs;
+        bucket_arcs += arcs;
         ++it;
+        if (found == 0 && nf) {
+            // the near frontier ran dry: every distance below the cutoff is final; open the next bucket
+            NearFar h_nf;
+            const NearFarHostHook hook{ctx->frontier[sel ^ 1], (long long)bucket_arcs};
+            const unsigned grid = nf_grid(ws->num_sms, n);
+            sssp_pending_min_kernel<<<grid, NF_NT, 0, st>>>(d_dist, (uint32_t)n, ctx->d_nf, hook);
+            sssp_take_kernel<<<grid, NF_NT, 0, st>>>(d_dist, (uint32_t)n, ctx->d_nf, hook);
+            ws->launches += 2;
+            B200_CUDA(cudaGetLastError());
+            B200_CUDA(cudaMemcpyAsync(&h_nf, ctx->d_nf, sizeof(NearFar), cudaMemcpyDeviceToHost, st));
+            B200_CUDA(cudaStreamSynchronize(st));
+            bucket_arcs = 0;
+            have_scan = false;           // a list nobody has scanned
+            if (!h_nf.done) found = (int64_t)h_nf.taken;
+        }
         if (tl) B200_CUDA(cudaEventRecord(ev[3 * it], st));
         if (found == 0) break;
         sel ^= 1;

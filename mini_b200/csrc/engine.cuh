@@ -5,7 +5,7 @@
 #include "b200/workspace.h"
 #include "b200_frontier.h"
 
-namespace b200 { struct LevelLoop; }
+namespace b200 { struct LevelLoop; struct NearFar; }
 
 struct b200_ctx {
     b200_workspace ws;
@@ -25,6 +25,12 @@ struct b200_ctx {
     int adv_impl;              // B200_ADVANCE_QUAD | B200_ADVANCE_LBS
     int loop_impl;             // B200_LOOP_GRAPH | B200_LOOP_HOST
     b200::LevelLoop *loop;     // graph-driven level loop (level_loop.cu), created on first use
+    b200::NearFar *d_nf;       // near-far SSSP state (near_far.cuh); d_nf_sum: scratch of the weight sample
+    double *d_nf_sum;
+    float sssp_delta;          // b200_ctx_set_sssp_delta: 0 = automatic, +inf = Bellman-Ford iterations, else the first bucket width
+    const void *nf_key_w;      // the automatic width is computed once per (weights array, n, m)
+    int64_t nf_key_n, nf_key_m;
+    float nf_auto_delta;
     float *hot_vals;           // [B200_HOT_MAX] values of a graph's hot columns, refreshed by every hot neighbourhood reduce
     uint64_t scratch_gen;      // bumped whenever workspace / traversal scratch is reallocated: cached traversal graphs
                                // (level_loop.cu, p2p_bfs.cu) hold those addresses and are rebuilt when it changes
@@ -90,7 +96,7 @@ cudaError_t preload_no_in_arc_kernel();   // lazy module loading vs. spinning pe
 // level_loop.cu
 int bfs_run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, float alpha, float beta, int32_t *d_labels,
                   b200_stats *stats);
-int sssp_run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist, b200_stats *stats);
+int sssp_run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist, float delta0, b200_stats *stats);
 void level_loop_invalidate(b200_ctx *ctx);
 void level_loop_destroy(b200_ctx *ctx);
 

@@ -19,11 +19,14 @@
 // Per-level statistics and the result land in mapped pinned memory; the host synchronises once.
 // Invariant: frontier bitmap 0 is all-zero during push levels (prologue memset; the bitmap -> list
 // compaction clears it again), so the list -> bitmap transition is a plain scatter.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "b200/operators.cuh"
 #include "engine.cuh"
 #include "graph_util.cuh"
+#include "near_far.cuh"
 
 using namespace b200;
 
@@ -33,7 +36,10 @@ struct LoopParams {      // mapped pinned: run parameters, read by the init kern
     int32_t src, mode;
     float alpha, beta;
     long long m;
-    uint32_t epoch0, pad;
+    uint32_t epoch0;
+    float delta0;        // SSSP: first bucket width of the near-far loop (+inf: the reference's Bellman-Ford iterations)
+    unsigned long long *trace;   // B200_LOOP_TRACE: kernel-entry timeline buffer (NULL = off), see loop_dyn.cuh
+    uint32_t trace_cap, pad;
 };
 
 struct LoopLevelRec {
@@ -58,6 +64,7 @@ struct LevelLoop {
     LoopState *d_state;
     LoopParams *h_params, *d_params;
     LoopResult *h_result, *d_result;
+    unsigned long long *d_trace;   // [LOOP_TRACE_CAP], allocated by the first traced run
     cudaStream_t cap_stream;
     // one cached graph per primitive (rebuilt when its key changes)
     struct Slot {
@@ -71,7 +78,7 @@ struct LevelLoop {
     } slot[2];
     int failed;          // status of the last failed build (the caller falls back to the host loop)
 };
-enum { SLOT_BFS = 0, SLOT_SSSP = 1, MODE_SSSP = 100 };
+enum { SLOT_BFS = 0, SLOT_SSSP = 1, MODE_SSSP = 100, LOOP_TRACE_CAP = 4096 };
 
 }  // namespace b200
 
@@ -113,7 +120,7 @@ __global__ void sssp_loop_fill_kernel(float *dist, int32_t *stamp, unsigned long
 template <bool SSSP>
 __global__ void loop_init_kernel(const LoopParams *p, LoopState *s, int32_t *labels, uint32_t *visited, int32_t *f0,
                                  int32_t *f1, long long n, unsigned long long *counters, unsigned int *tile_counters,
-                                 ScanPairs sp) {
+                                 ScanPairs sp, NearFar *nf) {
     const int src = p->src;
     labels[src] = 0;                         // depth 0 / +0.0f
     if (!SSSP) visited[src >> 5] |= 1u << (src & 31);
@@ -129,8 +136,9 @@ __global__ void loop_init_kernel(const LoopParams *p, LoopState *s, int32_t *lab
     s->dyn.rows_in = sp.rw0;
     s->dyn.scanned_out = sp.sc1;
     s->dyn.rows_out = sp.rw1;
-    s->dyn.trace = nullptr;
-    s->dyn.trace_cap = 0u;
+    s->dyn.trace = p->trace;
+    s->dyn.trace_cap = p->trace_cap;
+    if (p->trace) p->trace[0] = 0ull;
     s->level = 0;
     s->pull = 0;
     s->mode = p->mode;
@@ -146,11 +154,14 @@ __global__ void loop_init_kernel(const LoopParams *p, LoopState *s, int32_t *lab
     for (int i = 0; i < B200_NUM_COUNTERS; ++i) counters[i] = 0ull;
     tile_counters[0] = 0u;
     tile_counters[1] = 0u;
+    if (SSSP) near_far_reset(nf, p->delta0, p->m);
 }
 
 // The host loop's per-level bookkeeping (engine.cu b200_bfs_run), on the device.
 __global__ void loop_decide_kernel(LoopState *s, unsigned long long *counters, unsigned int *tile_counters, LoopResult *res,
-                                   cudaGraphConditionalHandle h_while) {
+                                   cudaGraphConditionalHandle h_while, NearFar *nf) {
+    if (nf && !(s->dyn.run & LOOP_RUN_PUSH)) return;   // (a near-far iteration always runs the advance; defensive)
+    loop_trace(&s->dyn, 9);
     const bool was_pull = s->pull != 0;
     const bool work_create = s->dyn.scanned_in != nullptr;
     long long found = (long long)counters[B200_CNT_OUT];
@@ -173,17 +184,19 @@ __global__ void loop_decide_kernel(LoopState *s, unsigned long long *counters, u
         r->discovered = found;
     }
     s->total_arcs += arcs;
-    s->launches += (s->mode == B200_BFS_PUSH || s->mode == MODE_SSSP) ? 3 : 6;   // kernel nodes of the flat body (some return at once)
+    s->launches += s->mode == MODE_SSSP ? 5 : s->mode == B200_BFS_PUSH ? 3 : 6;   // kernel nodes of the flat body (some return at once)
+    if (nf) nf->bucket_arcs += arcs;
     ++level;
     s->level = level;
-    bool done = false;
+    bool done = false, take = false;
     uint32_t trans = 0u;
     int status = B200_OK;
     if (overflow) {
         status = B200_ERR_OVERFLOW;
         done = true;
     } else if (found == 0) {
-        done = true;
+        if (nf) take = true;    // the near frontier ran dry: sssp_pending_min_kernel ends the traversal or opens a bucket
+        else done = true;
     } else {
         const long long flen = s->flen, n = s->n;
         s->reached += found;
@@ -235,9 +248,38 @@ __global__ void loop_decide_kernel(LoopState *s, unsigned long long *counters, u
         res->launches = s->launches;
         __threadfence_system();
     }
-    s->dyn.run = done ? 0u : ((pull ? LOOP_RUN_PULL : LOOP_RUN_PUSH | (need_scan ? LOOP_RUN_SCAN : 0u)) | trans);
+    loop_trace(&s->dyn, 64u + (unsigned)((level - 1) & 63));   // level closed
+    s->dyn.run = done ? 0u : take ? (uint32_t)LOOP_RUN_TAKE : ((pull ? LOOP_RUN_PULL : LOOP_RUN_PUSH | (need_scan ? LOOP_RUN_SCAN : 0u)) | trans);
     cudaGraphSetConditional(h_while, done ? 0u : 1u);
 }
+
+// near_far.cuh's passes inside the graph: they run when the decide step found the near frontier empty; the min pass
+// ends the traversal (what the decide step does for BFS) or opens a bucket, the take pass hands the level loop its
+// next frontier -- a list nobody has scanned.
+struct NearFarGraphHook {
+    LoopState *s;
+    LoopResult *res;
+    cudaGraphConditionalHandle h_while;
+    __device__ __forceinline__ bool enabled() const { return (s->dyn.run & LOOP_RUN_TAKE) != 0u; }
+    __device__ __forceinline__ void trace(unsigned id) const { loop_trace(&s->dyn, id); }
+    __device__ __forceinline__ void pre(NearFar *) const {}
+    __device__ __forceinline__ void on_done(NearFar *) const {
+        res->status = B200_OK;
+        res->num_levels = s->level;
+        res->reached = s->reached;
+        res->total_arcs = s->total_arcs;
+        res->launches = s->launches;
+        __threadfence_system();
+        s->dyn.run = 0u;
+        cudaGraphSetConditional(h_while, 0u);
+    }
+    __device__ __forceinline__ int *out() const { return const_cast<int *>(s->dyn.in); }
+    __device__ __forceinline__ void on_taken(NearFar *, uint32_t count) const {
+        s->flen = count;
+        s->dyn.len = count;
+        s->dyn.run = LOOP_RUN_PUSH | LOOP_RUN_SCAN;
+    }
+};
 
 void drop_slot(LevelLoop::Slot *S) {
     if (S->exec) cudaGraphExecDestroy(S->exec);
@@ -289,13 +331,13 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
         sssp_loop_fill_kernel<<<ws->num_sms * 4, 256, 0, cs>>>(reinterpret_cast<float *>(d_labels), ctx->stamp, (unsigned long long)n);
         LL_CUDA(cudaGetLastError());
         loop_init_kernel<true><<<1, 1, 0, cs>>>(L->d_params, L->d_state, d_labels, nullptr, ctx->frontier[0], ctx->frontier[1],
-                                                (long long)n, ws->d_counters, ws->d_tile_counter, sp);
+                                                (long long)n, ws->d_counters, ws->d_tile_counter, sp, ctx->d_nf);
     } else {
         LL_CUDA(cudaMemsetAsync(d_labels, 0xFF, sizeof(int32_t) * (size_t)n, cs));
         LL_CUDA(cudaMemsetAsync(ctx->bm_visited, 0, sizeof(uint32_t) * words, cs));
         if (mode != B200_BFS_PUSH) LL_CUDA(cudaMemsetAsync(ctx->bm_frontier[0], 0, sizeof(uint32_t) * words, cs));   // frontier bitmap 0 starts clean
         loop_init_kernel<false><<<1, 1, 0, cs>>>(L->d_params, L->d_state, d_labels, ctx->bm_visited, ctx->frontier[0],
-                                                 ctx->frontier[1], (long long)n, ws->d_counters, ws->d_tile_counter, sp);
+                                                 ctx->frontier[1], (long long)n, ws->d_counters, ws->d_tile_counter, sp, nullptr);
     }
     LL_CUDA(cudaGetLastError());
     capturing = false;
@@ -324,7 +366,7 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
         QuadArgs a = make_quad_args(ws, ctx->frontier[0], 0u, g->row_offsets, g->col_indices, sssp ? g->col_values : nullptr);
         a.dyn = dyn;
         if (sssp) {
-            SsspRelaxQDyn op{{reinterpret_cast<float *>(d_labels), nullptr, ctx->stamp, 0}, dyn};   // preds: one exact pass at the end
+            SsspRelaxQDyn op{{reinterpret_cast<float *>(d_labels), nullptr, ctx->stamp, 0, ctx->d_nf}, dyn};   // preds: one exact pass at the end
             LL_CUDA((launch_quad_advance<OUT_COMPACT, false>(ws, a, op, ctx->frontier[1], (unsigned long long)n)));
         } else {
             BfsPushQDyn op{{ctx->bm_visited, d_labels, 0}, dyn};
@@ -340,8 +382,17 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
                                                                   g->first_in_neighbor);
         LL_CUDA(cudaGetLastError());
     }
-    loop_decide_kernel<<<1, 1, 0, cs>>>(L->d_state, ws->d_counters, ws->d_tile_counter, L->d_result, h_while);
+    loop_decide_kernel<<<1, 1, 0, cs>>>(L->d_state, ws->d_counters, ws->d_tile_counter, L->d_result, h_while,
+                                        sssp ? ctx->d_nf : nullptr);
     LL_CUDA(cudaGetLastError());
+    if (sssp) {
+        const NearFarGraphHook hook{L->d_state, L->d_result, h_while};
+        const unsigned grid = nf_grid(ws->num_sms, n);
+        sssp_pending_min_kernel<<<grid, NF_NT, 0, cs>>>(reinterpret_cast<const float *>(d_labels), (uint32_t)n, ctx->d_nf, hook);
+        LL_CUDA(cudaGetLastError());
+        sssp_take_kernel<<<grid, NF_NT, 0, cs>>>(reinterpret_cast<const float *>(d_labels), (uint32_t)n, ctx->d_nf, hook);
+        LL_CUDA(cudaGetLastError());
+    }
     if (has_pull) {
         // transitions: list -> bitmap 0 (all-zero by invariant) | bitmap -> list (+ clears bitmap 0)
         // (+ vertices without in-arcs count as visited from the switch on, engine.cuh)
@@ -401,6 +452,7 @@ void level_loop_destroy(b200_ctx *ctx) {
     drop_graph(L);
     if (L->cap_stream) cudaStreamDestroy(L->cap_stream);
     if (L->d_state) cudaFree(L->d_state);
+    if (L->d_trace) cudaFree(L->d_trace);
     if (L->h_params) cudaFreeHost(L->h_params);
     if (L->h_result) cudaFreeHost(L->h_result);
     delete L;
@@ -430,7 +482,7 @@ static int level_loop_get(b200_ctx *ctx) {
 // b200_bfs_run / b200_sssp_run through the graph.  Returns B200_ERR_UNSUPPORTED when the graph cannot be built on this
 // driver (the caller then runs the host-driven loop and reports level_loop = host in the stats).
 static int run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, float alpha, float beta, int32_t *d_labels,
-                     b200_stats *stats) {
+                     b200_stats *stats, float delta0 = 0.f) {
     B200_TRY(level_loop_get(ctx));
     LevelLoop *L = ctx->loop;
     LevelLoop::Slot *S = &L->slot[mode == MODE_SSSP ? SLOT_SSSP : SLOT_BFS];
@@ -463,12 +515,26 @@ static int run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, 
     L->h_params->beta = beta;
     L->h_params->m = g->m;
     L->h_params->epoch0 = ws->epoch + 1;
+    L->h_params->delta0 = delta0;
+    const bool want_trace = getenv("B200_LOOP_TRACE") != nullptr;   // (read per run)
+    if (want_trace && !L->d_trace) B200_CUDA(cudaMalloc(&L->d_trace, sizeof(unsigned long long) * LOOP_TRACE_CAP));
+    L->h_params->trace = want_trace ? L->d_trace : nullptr;
+    L->h_params->trace_cap = want_trace ? (uint32_t)LOOP_TRACE_CAP : 0u;
     L->h_result->status = -1;
     L->h_result->num_levels = 0;
     B200_CUDA(cudaEventRecord(ctx->ev_run[0], st));
     B200_CUDA(cudaGraphLaunch(S->exec, st));
     B200_CUDA(cudaEventRecord(ctx->ev_run[1], st));
     B200_CUDA(cudaEventSynchronize(ctx->ev_run[1]));
+    if (want_trace) {   // same line format as the peer-memory BFS (profiles/format_trace.py)
+        static thread_local unsigned long long h_trace[LOOP_TRACE_CAP];
+        B200_CUDA(cudaMemcpy(h_trace, L->d_trace, sizeof h_trace, cudaMemcpyDeviceToHost));
+        const unsigned long long cnt = h_trace[0] < LOOP_TRACE_CAP - 1 ? h_trace[0] : LOOP_TRACE_CAP - 1;
+        fprintf(stderr, "B200_LOOP_TRACE rank0 %llu entries (us since first, kernel id):", cnt);
+        for (unsigned long long i = 1; i <= cnt; ++i)
+            fprintf(stderr, " %.1f:%llu", (double)((h_trace[i] >> 8) - (h_trace[1] >> 8)) * 1e-3, h_trace[i] & 0xffull);
+        fprintf(stderr, "\n");
+    }
     const LoopResult *r = L->h_result;
     if (r->status < 0) return B200_ERR_CUDA;    // the graph ended without the decide kernel reporting
     const int levels = r->num_levels;
@@ -506,10 +572,10 @@ int bfs_run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, flo
     return run_graph(ctx, g, src, mode, alpha, beta, d_labels, stats);
 }
 
-// The Bellman-Ford frontier iterations of b200_sssp_run (sssp_enactor.hxx:40-72) through the graph: distances final at
-// return; the caller adds the predecessor pass.  ev_run[0] is recorded at the start of the traversal.
-int sssp_run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist, b200_stats *stats) {
-    return run_graph(ctx, g, src, MODE_SSSP, 0.f, 0.f, reinterpret_cast<int32_t *>(d_dist), stats);
+// The frontier iterations of b200_sssp_run (sssp_enactor.hxx:40-72; near-far ordering, near_far.cuh) through the graph:
+// distances final at return; the caller adds the predecessor pass.  ev_run[0] is recorded at the start of the traversal.
+int sssp_run_graph(b200_ctx *ctx, const b200_graph *g, int32_t src, float *d_dist, float delta0, b200_stats *stats) {
+    return run_graph(ctx, g, src, MODE_SSSP, 0.f, 0.f, reinterpret_cast<int32_t *>(d_dist), stats, delta0);
 }
 
 }  // namespace b200

@@ -94,6 +94,7 @@ def load_library():
         "b200_ctx_set_advance_impl": ([vp, i32], i32),
         "b200_ctx_set_level_loop": ([vp, i32], i32),
         "b200_ctx_forget_graph": ([vp], i32),
+        "b200_ctx_set_sssp_delta": ([vp, C.c_float], i32),
         "b200_graph_no_in_arc_bitmap": ([vp, pg, vp], i32),
         "b200_graph_hot_columns": ([vp, pg, i64, vp, vp], i32),
         "b200_graph_first_in_neighbor": ([vp, pg, vp], i32),
@@ -268,6 +269,11 @@ class Context:
     def set_level_loop(self, impl: int):
         """LOOP_GRAPH (default: one CUDA graph per traversal, device-side decisions) or LOOP_HOST."""
         _check(self._L.b200_ctx_set_level_loop(self._h, impl), "b200_ctx_set_level_loop")
+
+    def set_sssp_delta(self, delta: float):
+        """First bucket width of the near-far order inside sssp(): 0 = automatic, float('inf') = the reference's
+        Bellman-Ford frontier iterations.  Distances do not depend on it."""
+        _check(self._L.b200_ctx_set_sssp_delta(self._h, float(delta)), "b200_ctx_set_sssp_delta")
 
     def l2_pin(self, tensor):
         if tensor is None:

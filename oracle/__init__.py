@@ -60,6 +60,8 @@ def lib():
         L.orc_sssp_ref_preds.restype = None
         L.orc_sssp_dist.argtypes = [C.c_int64, _i64p, _i32p, _f32p, C.c_int32, _f32p]
         L.orc_sssp_dist.restype = None
+        L.orc_sssp_dist_f32.argtypes = [C.c_int64, _i64p, _i32p, _f32p, C.c_int32, _f32p]
+        L.orc_sssp_dist_f32.restype = None
         L.orc_neighborhood_reduce_f64.argtypes = [C.c_int64, _i32p, _i64p, _i32p, _f64p, C.c_int,
                                                   C.c_double, _f64p, C.c_void_p]
         L.orc_neighborhood_reduce_f64.restype = None
@@ -233,6 +235,13 @@ def bfs_timed(g: CSR, src: int = 0):
 def sssp_dist(g: CSR, src: int = 0) -> np.ndarray:
     out = np.empty(g.n, np.float32)
     lib().orc_sssp_dist(g.n, g.offsets, g.indices, g.weights, src, out)
+    return out
+
+
+def sssp_dist_f32(g: CSR, src: int = 0) -> np.ndarray:
+    """orc_sssp_dist for weights that are not integers: Dijkstra in fp32 under the functor's rounding."""
+    out = np.empty(g.n, np.float32)
+    lib().orc_sssp_dist_f32(g.n, g.offsets, g.indices, g.weights, src, out)
     return out
 
 

@@ -251,6 +251,37 @@ ORC_API void orc_sssp_dist(int64_t n, const int64_t *row_offsets, const int32_t 
     free(dist); free(h.a);
 }
 
+/* The same rule in fp32 for weights that are not integers: new = fl(labels[src] + w[e]) exactly as the functor      */
+/* computes it (sssp_functor.hxx:22), strict <.  fl(a + w) is monotone in a and >= a for w >= 0, so label-setting in  */
+/* key order reaches the least fixed point -- the one every relaxation order of the GPU enactor converges to.       */
+/* Non-negative floats order like their bit patterns, which are the heap keys.                                      */
+ORC_API void orc_sssp_dist_f32(int64_t n, const int64_t *row_offsets, const int32_t *col_indices,
+                               const float *col_values, int32_t src, float *dist_out) {
+    orc_heap h = { 0, 0, 0 };
+    for (int64_t i = 0; i < n; ++i) dist_out[i] = FLT_MAX;
+    dist_out[src] = 0.0f;
+    hpush(&h, 0, src);
+    while (h.n) {
+        orc_hent t = hpop(&h);
+        int32_t u = t.v;
+        float du = dist_out[u];
+        uint32_t bits;
+        memcpy(&bits, &du, sizeof bits);
+        if (t.key > (int64_t)bits) continue;
+        for (int64_t i = row_offsets[u]; i < row_offsets[u + 1]; ++i) {
+            int32_t v = col_indices[i];
+            volatile float nd = du + col_values[i];   /* (volatile: no excess precision, no contraction) */
+            float ndf = nd;
+            if (ndf < dist_out[v]) {
+                dist_out[v] = ndf;
+                memcpy(&bits, &ndf, sizeof bits);
+                hpush(&h, (int64_t)bits, v);
+            }
+        }
+    }
+    free(h.a);
+}
+
 /* ------------------------------------------------------------------------- */
 /* neighborhood_reduce: gunrock/src/neighborhood.hxx:47-58.  For frontier slot */
 /* i holding vertex v: reduced[i] = op over u in N(v) of value[u]; `identity`  */

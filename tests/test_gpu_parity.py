@@ -333,6 +333,56 @@ def test_sssp_random_graphs(ctx):
             assert dist.cpu().numpy().tobytes() == oracle.sssp_dist(o, src).tobytes()
 
 
+@pytest.mark.parametrize("delta", [0.0, float("inf"), 1e-3, 1.0, 7.5, 64.0, 1e9])
+def test_sssp_near_far_any_bucket_width_gives_the_same_distances(ctx, delta):
+    """b200_ctx_set_sssp_delta: the order in which improved vertices are expanded never changes the
+    fixed point.  0 = automatic width, inf = the reference's Bellman-Ford order (sssp_enactor.hxx:51-70); a width far
+    below the smallest weight makes every distinct distance its own bucket, a huge one a single bucket."""
+    ctx.set_sssp_delta(delta)
+    try:
+        for (scale, ef, seed, src) in [(10, 16, 1, 0), (14, 16, 2, 3)]:
+            g = ctx.rmat_graph(scale, ef, seed, weighted=True)
+            o = oracle.rmat_csr(scale, ef, seed, weighted=True)
+            preds = torch.empty(o.n, dtype=torch.int32, device="cuda")
+            dist, st = ctx.sssp(g, src, preds=preds)
+            want = oracle.sssp_dist(o, src)
+            assert dist.cpu().numpy().tobytes() == want.tobytes()
+            p = preds.cpu().numpy()
+            assert p[src] == -1 and ((p >= 0) == ((want < FLT_MAX) & (np.arange(o.n) != src))).all()
+        # fractional weights (distances are sums of fp32 roundings: still one fixed point), isolated vertices, a source
+        # whose component is tiny
+        rng = np.random.default_rng(11)
+        o = _rand_graph(5000, 12000, 5)
+        o = oracle.CSR(o.n, o.offsets, o.indices, (rng.random(o.m, dtype=np.float32) * 3.0 + 0.01).astype(np.float32))
+        g = _dev_graph(ctx, o)
+        for src in (0, 4999, 17):
+            dist, _ = ctx.sssp(g, src)
+            assert dist.cpu().numpy().tobytes() == oracle.sssp_dist_f32(o, src).tobytes()
+    finally:
+        ctx.set_sssp_delta(0.0)
+
+
+def test_sssp_near_far_relaxes_fewer_arcs_than_bellman_ford(ctx):
+    """SURVEY 8f-4's bar: relaxed arcs <= 1.2x the arcs of the reached vertices (the reference's order needs ~2x on
+    RMAT with weights 1..64).  The arc-wise kernel keeps the reference's order."""
+    g = ctx.rmat_graph(16, 16, 1, weighted=True)
+    o = oracle.rmat_csr(16, 16, 1, weighted=True)
+    want = oracle.sssp_dist(o, 0)
+    reached_arcs = int(np.diff(o.offsets)[want < FLT_MAX].sum())
+    dist, st = ctx.sssp(g, 0)
+    assert dist.cpu().numpy().tobytes() == want.tobytes()
+    ctx.set_sssp_delta(float("inf"))
+    try:
+        dist_bf, st_bf = ctx.sssp(g, 0)
+    finally:
+        ctx.set_sssp_delta(0.0)
+    assert dist_bf.cpu().numpy().tobytes() == want.tobytes()
+    assert st_bf.total_arcs >= reached_arcs
+    if ctx.variant != "lbs":
+        assert reached_arcs <= st.total_arcs <= 1.2 * reached_arcs, (st.total_arcs, reached_arcs, st_bf.total_arcs)
+        assert st.total_arcs < st_bf.total_arcs
+
+
 # ------------------------------------------------------------------ operators, one call at a time
 def test_advance_filter_operator_level(ctx):
     """bfs_enactor.hxx:50-71 driven from the host through the operator entry points."""

@@ -269,3 +269,30 @@ def test_push_level_restates_bfs():
         f = oracle.bfs_push_level(g, f, it, labels)
         it += 1
     assert np.array_equal(labels, oracle.bfs(g, 0))
+
+
+def test_sssp_fp32_oracle_is_the_fixed_point_of_the_relax_rule():
+    """orc_sssp_dist_f32 (Dijkstra under fl(dist[src] + w), sssp_functor.hxx:20-29) equals the integer oracle on integer
+    weights and, on fractional weights, the fixed point of synchronous fp32 relaxation sweeps (what any order of the
+    GPU enactor's atomicMin relaxations converges to)."""
+    rng = np.random.default_rng(3)
+    n = 3000
+    s = rng.integers(0, n, 9000).astype(np.int32)
+    d = rng.integers(0, n, 9000).astype(np.int32)
+    g = oracle.build_csr(n, s, d, True, True)
+    gf = oracle.CSR(n, g.offsets, g.indices, (rng.random(g.m, dtype=np.float32) * 3.0 + 0.01).astype(np.float32))
+    big = np.finfo(np.float32).max
+    src_of = np.repeat(np.arange(n), np.diff(g.offsets))
+    for src in (0, 2999):
+        assert oracle.sssp_dist_f32(g, src).tobytes() == oracle.sssp_dist(g, src).tobytes()
+        want = oracle.sssp_dist_f32(gf, src)
+        dist = np.full(n, big, np.float32)
+        dist[src] = 0
+        while True:
+            nd = dist[src_of] + gf.weights
+            nd[dist[src_of] == big] = big
+            old = dist.copy()
+            np.minimum.at(dist, gf.indices, nd)
+            if np.array_equal(old, dist):
+                break
+        assert dist.tobytes() == want.tobytes()
