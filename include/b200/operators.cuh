@@ -212,6 +212,10 @@ cudaError_t launch_quad_advance(b200_workspace *ws, const QuadArgs &a, Op op, in
     if (!(opted_in >> (ws->device & 63) & 1ull)) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+#ifdef B200_QUAD_CARVEOUT   // tuning builds: shared-memory share of the SM's SRAM in percent (default: the driver's choice)
+        e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, B200_QUAD_CARVEOUT);
+        if (e != cudaSuccess) return e;
+#endif
         opted_in |= 1ull << (ws->device & 63);
     }
     RoutedOut r;

@@ -467,6 +467,16 @@ template <int N> struct CandWords {
     uint32_t w[N];
 };
 
+// Label stores are scattered 4-byte writes nobody in this launch reads back: tuning builds can keep them out of L1
+// (-DB200_LABEL_STCG), which belongs to the visited bitmap.
+__device__ __forceinline__ void store_label(int *p, int v) {
+#ifdef B200_LABEL_STCG
+    __stcg(p, v);
+#else
+    *p = v;
+#endif
+}
+
 // BFS push (bfs_functor.hxx:26-33): cond_advance = bit test (L1-resident bitmap word),
 // apply_advance = atomicOr wins exactly once.
 struct BfsPushQ {
@@ -481,7 +491,11 @@ struct BfsPushQ {
     __device__ __forceinline__ SrcVal load_src(int) const { return NoSrc(); }
     __device__ __forceinline__ Evidence probe_load(bool on, SrcVal, int, int dst, uint32_t) const {
         uint32_t word = 0xffffffffu;
+#ifdef B200_PROBE_EVICT_LAST
+        if (on) asm volatile("ld.global.L1::evict_last.u32 %0, [%1];" : "=r"(word) : "l"(visited + ((uint32_t)dst >> 5)));
+#else
         if (on) word = visited[(uint32_t)dst >> 5];
+#endif
         return word;
     }
     __device__ __forceinline__ bool probe_eval(Evidence word, SrcVal, int dst, float) const {
@@ -493,7 +507,7 @@ struct BfsPushQ {
     }
     __device__ __forceinline__ int finish(Token old, const Cand &c) const {
         if ((old >> (c.w[0] & 31)) & 1u) return -1;
-        labels[c.w[0]] = next_label;
+        store_label(labels + c.w[0], next_label);
         return (int)c.w[0];
     }
 };
@@ -503,7 +517,7 @@ struct BfsPushQDyn : BfsPushQ {
     const LoopDyn *dyn;
     __device__ __forceinline__ int finish(Token old, const Cand &c) const {
         if ((old >> (c.w[0] & 31)) & 1u) return -1;
-        labels[c.w[0]] = dyn->next_label;
+        store_label(labels + c.w[0], dyn->next_label);
         return (int)c.w[0];
     }
 };

@@ -124,7 +124,10 @@ int advance_forward_kernel(std::shared_ptr<Problem> problem, std::shared_ptr<fro
                            std::shared_ptr<frontier_t<int>> &output, int iteration, standard_context_t &context) {
     const size_t len = input->size();
     if (!len) {
-        if (has_output) output->resize(0);
+        if (has_output) {
+            output->resize(0);
+            output->set_hole_free(true);
+        }
         return 0;
     }
     graph_device_t &g = *problem->gslice;
@@ -152,6 +155,7 @@ int advance_forward_kernel(std::shared_ptr<Problem> problem, std::shared_ptr<fro
         if (!has_output) return 0;
         const size_t produced = (size_t)ws->h_counters[B200_CNT_OUT];
         output->resize(produced);   // prints the reference's overflow message and exits if it does not fit
+        output->set_hole_free(true);
         return (int)produced;
     }
 #endif
@@ -173,6 +177,11 @@ int advance_forward_kernel(std::shared_ptr<Problem> problem, std::shared_ptr<fro
     if (!has_output) return 0;
     const size_t produced = (size_t)ws->h_counters[B200_CNT_OUT];
     output->resize(produced);   // prints the reference's overflow message and exits if it does not fit
+#ifdef B200_ADVANCE_RAW_OUTPUT
+    output->set_hole_free(false);
+#else
+    output->set_hole_free(true);
+#endif
     return (int)produced;
 }
 
@@ -182,6 +191,7 @@ void sparse_to_dense_kernel(std::shared_ptr<Problem> problem, std::shared_ptr<fr
                             std::shared_ptr<frontier_t<int>> &dense, int iteration, standard_context_t &context) {
     const int *items = sparse->data()->data();
     int *flags = dense->data()->data();
+    dense->set_hole_free(false);   // (per-vertex flags, not a list)
     typename Problem::data_slice_t *data = problem->d_data_slice.data();
     transform([=] __device__(int idx) {
         const int v = items[idx];
@@ -246,6 +256,7 @@ int gen_unvisited_kernel(std::shared_ptr<Problem> problem, std::shared_ptr<front
                                        ws->d_counters + B200_CNT_OUT, ws->d_counters + B200_CNT_OVERFLOW));
     detail::check(b200::read_counters(ws));
     unvisited->resize((size_t)ws->h_counters[B200_CNT_OUT]);
+    unvisited->set_hole_free(true);
     return (int)unvisited->size();
 }
 
@@ -258,6 +269,8 @@ int advance_backward_kernel(std::shared_ptr<Problem> problem, std::shared_ptr<fr
                             int iteration, standard_context_t &context) {
     const size_t len = unvisited->size();
     if (!len) return 0;
+    unvisited->set_hole_free(false);    // labelled entries become -1 below
+    bitmap_out->set_hole_free(false);
     graph_device_t &g = *problem->gslice;
     b200_workspace *ws = context.workspace();
     detail::check(b200::reset_counters(ws));

@@ -9,13 +9,18 @@ namespace bfs {
 
 struct bfs_problem_t : problem_t {
     // what bfs_functor_t reads and writes, as raw device pointers
+    // (d_visited is an addition: one bit per vertex, set together with the label.  The reference's functor tests and
+    // claims the 4-byte label itself, bfs_functor.hxx:26-33 -- 16 MB of random probes at scale 22 against 512 KB here,
+    // which is what lets the probes of advance_forward_kernel live in L1.)
     struct data_slice_t {
         int *d_labels, *d_preds;
+        unsigned int *d_visited;
     };
 
     int src = 0;
     std::vector<int> labels, preds;        // host copies (extract() refreshes labels)
     mem_t<int> d_labels, d_preds;
+    mem_t<unsigned int> d_visited;
     mem_t<data_slice_t> d_data_slice;
 
     bfs_problem_t() = default;
@@ -25,7 +30,10 @@ struct bfs_problem_t : problem_t {
         labels[source] = 0;                // the source is at depth 0, everything else unvisited
         d_labels = to_mem(labels, context);
         d_preds = to_mem(preds, context);
-        d_data_slice = publish_slice(data_slice_t{d_labels.data(), d_preds.data()}, context);
+        std::vector<unsigned int> bits(((size_t)graph->num_nodes + 31) / 32 + 1, 0u);
+        bits[source >> 5] |= 1u << (source & 31);
+        d_visited = to_mem(bits, context);
+        d_data_slice = publish_slice(data_slice_t{d_labels.data(), d_preds.data(), d_visited.data()}, context);
     }
 
     void extract() { mgpu::dtoh(labels, d_labels.data(), gslice->num_nodes); }
@@ -36,7 +44,7 @@ struct bfs_problem_t : problem_t {
         p.kind = B200_PROBLEM_BFS;
         p.labels = d_labels.data();
         p.preds = d_preds.data();
-        p.visited_bitmap = d_visited_bitmap;
+        p.visited_bitmap = d_visited_bitmap ? d_visited_bitmap : d_visited.data();
         return p;
     }
 

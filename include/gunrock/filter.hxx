@@ -3,6 +3,7 @@
 // (include/b200/tile_scan.cuh) instead of mgpu transform_compact's upsweep / scan /
 // pinned read-back / downsweep.
 #pragma once
+#include <type_traits>
 #include "b200/operators.cuh"
 #include "frontier.hxx"
 
@@ -46,6 +47,7 @@ struct UniquifyPred {
 
 template <typename Pred>
 int run_compact(Pred pred, size_t len, std::shared_ptr<frontier_t<int>> &output, standard_context_t &context) {
+    output->set_hole_free(true);
     if (!len) {
         output->resize(0);
         return 0;
@@ -59,11 +61,29 @@ int run_compact(Pred pred, size_t len, std::shared_ptr<frontier_t<int>> &output,
     output->resize((size_t)ws->h_counters[B200_CNT_OUT]);
     return (int)output->size();
 }
+// Opt-in functor trait: `static constexpr bool cond_filter_drops_only_holes = true;` states that cond_filter is
+// exactly `item != -1` with no side effect (bfs_functor.hxx:9-11: its only job is to drop the holes advance.hxx:60
+// leaves).  On a frontier the operators know to be hole-free (frontier_t::hole_free) such a filter keeps everything:
+// the list is copied on the stream and its length is already known on the host -- no kernel pass, no read-back.
+template <typename F, typename = void>
+struct filter_drops_only_holes : std::false_type {};
+template <typename F>
+struct filter_drops_only_holes<F, std::void_t<decltype(F::cond_filter_drops_only_holes)>>
+    : std::integral_constant<bool, F::cond_filter_drops_only_holes> {};
 }  // namespace detail
 
 template <typename Problem, typename Functor>
 int filter_kernel(std::shared_ptr<Problem> problem, std::shared_ptr<frontier_t<int>> &input,
                   std::shared_ptr<frontier_t<int>> &output, int iteration, standard_context_t &context) {
+    if (detail::filter_drops_only_holes<Functor>::value && input->hole_free()) {
+        const size_t len = input->size();
+        output->resize(len);   // (prints the reference's overflow message and exits if it does not fit)
+        if (len)
+            mgpu::throw_on_error(cudaMemcpyAsync(output->data()->data(), input->data()->data(), sizeof(int) * len,
+                                                 cudaMemcpyDeviceToDevice, context.stream()));
+        output->set_hole_free(true);
+        return (int)len;
+    }
     detail::CondFilterPred<Problem, Functor> pred{input->data()->data(), problem->d_data_slice.data(), iteration};
     return detail::run_compact(pred, input->size(), output, context);
 }

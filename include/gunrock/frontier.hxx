@@ -13,6 +13,7 @@ class frontier_t {
     size_t _size = 0;
     size_t _capacity = 1;
     frontier_type_t _type = node_frontier;
+    bool _hole_free = false;   // see hole_free()
     std::shared_ptr<mem_t<type_t>> _data;
 
     void overflow(const char *what, size_t wanted) const {
@@ -37,6 +38,7 @@ class frontier_t {
         std::swap(_size, rhs._size);
         std::swap(_capacity, rhs._capacity);
         std::swap(_type, rhs._type);
+        std::swap(_hole_free, rhs._hole_free);
         _data.swap(rhs._data);
     }
 
@@ -44,12 +46,14 @@ class frontier_t {
     cudaError_t load(mem_t<type_t> &target) {
         if (target.size() > _capacity) overflow("loading", target.size());
         _size = target.size();
+        _hole_free = false;
         return dtod(_data->data(), target.data(), target.size());
     }
     // host -> frontier
     cudaError_t load(std::vector<type_t> target) {
         if (target.size() > _capacity) overflow("loading", target.size());
         _size = target.size();
+        _hole_free = false;
         return htod(_data->data(), target);
     }
     void resize(size_t size) {
@@ -59,6 +63,12 @@ class frontier_t {
     size_t capacity() const { return _capacity; }
     size_t size() const { return _size; }
     frontier_type_t type() const { return _type; }
+    // Not in the reference: set by the operators that write a COMPACTED list (the default advance_forward_kernel, every
+    // filter) and cleared by load().  A filter whose functor only drops the -1 holes of an un-compacted advance
+    // (Functor::cond_filter_drops_only_holes) then has nothing to do but hand the list on.  A stale "true" after
+    // somebody wrote holes through data() is harmless to the operators: they skip negative items.
+    bool hole_free() const { return _hole_free; }
+    void set_hole_free(bool v) { _hole_free = v; }
     std::shared_ptr<mem_t<type_t>> data() const { return _data; }
 };
 

@@ -108,6 +108,7 @@ int neighborhood_kernel(std::shared_ptr<Problem> problem, std::shared_ptr<fronti
     if (has_output) {   // the emit pass writes one entry per arc: make room first (resize prints the reference's overflow text)
         mgpu::throw_on_error(b200::read_counters(ws));
         output->resize((size_t)ws->h_counters[B200_CNT_TOTAL]);
+        output->set_hole_free(false);   // raw layout: -1 where the functor rejected the arc
     }
     detail::emit_raw<Problem, Functor>(std::integral_constant<bool, has_output>(), ws, a, data, iteration, output);
     detail::ValueOfNeighbor<Problem, Functor, Value, !has_output> vf{data, iteration};

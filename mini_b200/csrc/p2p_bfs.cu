@@ -688,7 +688,9 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
             if (lane == 0) wfill[p] = 0u;
         }
         // (system scope: when no long row was queued this is already the "sends are out" barrier)
+        loop_trace(&s->dyn, 26);
         if (!small_grid_barrier(sh, &s_gen, true)) break;
+        loop_trace(&s->dyn, 27);
         // ---- pass 2: the pieces of the long rows, dealt round-robin over the warps of the grid
         const uint32_t nbig = (uint32_t)ld_volatile_u64(&c->big_cnt);
         if (nbig) {
@@ -792,6 +794,7 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
             }
         }
         // level totals of this CTA -> the slot
+        loop_trace(&s->dyn, 28);
         if (threadIdx.x < 2) s_sum[threadIdx.x] = 0ull;
         __syncthreads();
 #pragma unroll
@@ -806,6 +809,7 @@ __global__ void __launch_bounds__(SMALL_NT, 1) p2p_small_levels_kernel(SmallArgs
             if (s_sum[1]) atomicAdd(&c->deg, s_sum[1]);
         }
         if (!small_grid_barrier(sh, &s_gen)) break;
+        loop_trace(&s->dyn, 29);
         // ---- level summary: this rank's row into every heap, flags, sum of the rows
         const unsigned long long next_local = ld_volatile_u64(&c->next_cnt);
         const int parity = (int)(stats_seq & 1u);
@@ -1003,6 +1007,10 @@ __global__ void __launch_bounds__(NT) p2p_absorb_bits_kernel(Peers peers, size_t
     st.epoch = (dyn->epoch + 1u) & 0x3FFFFFFFu;
     st.num_tiles = (wl + TS::NV - 1) / TS::NV;
     unsigned long long deg_sum = 0;
+    // Level 0: the frontier was the source alone, so only its owner's `known` can hold new claims -- this rank reads its
+    // slice of that ONE map (and its own) instead of all P (8 GPUs, scale 26: 2 MB instead of 8 MB of the 40 us this
+    // kernel took at level 0, most of it over NVLink).
+    const int only = s->level == 0 ? (int)part.owner((uint32_t)s->src) : -1;
     for (;;) {
         if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
         __syncthreads();
@@ -1015,8 +1023,13 @@ __global__ void __launch_bounds__(NT) p2p_absorb_bits_kernel(Peers peers, size_t
             const uint32_t w = base + i * 32;
             uint32_t acc = 0u;
             if (w < wl) {
-                for (int q = 0; q < P; ++q)
-                    acc |= __ldcg(reinterpret_cast<const uint32_t *>(peers.base[q] + off_known) + (size_t)me * wl + w);
+                if (only >= 0) {
+                    acc = __ldcg(reinterpret_cast<const uint32_t *>(peers.base[only] + off_known) + (size_t)me * wl + w);
+                    if (only != me) acc |= known_own[w];
+                } else {
+                    for (int q = 0; q < P; ++q)
+                        acc |= __ldcg(reinterpret_cast<const uint32_t *>(peers.base[q] + off_known) + (size_t)me * wl + w);
+                }
                 const uint32_t d = done[w];
                 word[i] = acc & ~d;
                 if (word[i]) done[w] = d | word[i];

@@ -9,6 +9,8 @@ NAMES = {20: "small-level kernel: entry", 21: "small: level start (expand the lo
          13: "bitmap absorb: flag barrier passed", 9: "stats + decide (entry)", 12: "stats + decide: flag barrier passed",
          30: "pull-levels kernel: entry", 31: "pull: gather + OR of the frontier slices starts", 32: "pull: early-exit pull starts",
          33: "pull: stats row posted", 34: "pull: stats in, decision",
+         26: "small: CTA 0 done expanding (grid barrier follows)", 27: "small: grid barrier passed",
+         28: "small: CTA 0 done absorbing (grid barrier follows)", 29: "small: grid barrier passed",
          11: "bitmap -> list (entry)", 40: "near-far SSSP: pending-minimum pass", 41: "near-far SSSP: take pass"}
 SINGLE = {9: "decide (one thread: counters -> next level's state)"}   # ids whose meaning differs in the 1-GPU loop (level_loop.cu)
 if len(sys.argv) > 2 and sys.argv[2] == "single":
