@@ -4,6 +4,7 @@
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "b200/operators.cuh"
@@ -442,6 +443,10 @@ int b200_bfs_run(b200_ctx *ctx, const b200_graph *g, int32_t src, int mode, floa
         if (gs != B200_ERR_UNSUPPORTED) return gs;   // unsupported: the graph could not be built, run the host loop
     }
     if (stats) stats->level_loop = B200_LOOP_HOST;
+    {   // experiment knob (profiles/README.md): persisting-L2 access-policy window over the visited bitmap, host-driven loop
+        const char *pin = getenv("B200_L2_PIN_VISITED");
+        if (pin && pin[0] == '1' && !ctx->l2_window_set) B200_TRY(b200_ctx_l2_pin(ctx, ctx->bm_visited, (int64_t)(words * sizeof(uint32_t))));
+    }
     cudaEvent_t *ev = timing ? level_events(ctx) : nullptr;
     const int64_t launches0 = ws->launches;
     const uint32_t *pull_off = g->col_offsets ? g->col_offsets : g->row_offsets;

@@ -84,6 +84,15 @@ enum { SLOT_BFS = 0, SLOT_SSSP = 1, MODE_SSSP = 100, LOOP_TRACE_CAP = 4096 };
 
 namespace {
 
+#ifndef B200_LOOP_UNROLL
+#define B200_LOOP_UNROLL 3
+#endif
+inline int loop_unroll() {   // levels per pass of the WHILE body (the B200_LOOP_UNROLL environment variable overrides the build's default)
+    const char *e = getenv("B200_LOOP_UNROLL");
+    const int v = e ? atoi(e) : B200_LOOP_UNROLL;
+    return v < 1 ? 1 : v > 8 ? 8 : v;
+}
+
 constexpr int DYN_SCAN_CTAS_PER_SM = 8;   // 256-thread CTAs: the whole SM, as many tiles in flight as a count-sized grid has
 
 struct FrontierQuadsDyn {   // FrontierQuads over the device-selected frontier list
@@ -160,7 +169,8 @@ __global__ void loop_init_kernel(const LoopParams *p, LoopState *s, int32_t *lab
 // The host loop's per-level bookkeeping (engine.cu b200_bfs_run), on the device.
 __global__ void loop_decide_kernel(LoopState *s, unsigned long long *counters, unsigned int *tile_counters, LoopResult *res,
                                    cudaGraphConditionalHandle h_while, NearFar *nf) {
-    if (nf && !(s->dyn.run & LOOP_RUN_PUSH)) return;   // (a near-far iteration always runs the advance; defensive)
+    if (!(s->dyn.run & (LOOP_RUN_PUSH | LOOP_RUN_PULL))) return;   // no level ran in this pass of the (unrolled) body: the
+                                                                   // traversal is over, or the near-far passes just ran
     loop_trace(&s->dyn, 9);
     const bool was_pull = s->pull != 0;
     const bool work_create = s->dyn.scanned_in != nullptr;
@@ -354,6 +364,10 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
     // ---- the flat body: every kernel returns at once unless its LOOP_RUN_* bit is set
     LL_CUDA(cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
     capturing = true;
+    // The body holds loop_unroll() levels: an iteration of the WHILE node costs ~4 us between the last kernel of one
+    // pass and the first of the next (B200_LOOP_TRACE), an idle kernel 1.1-1.8 us -- once the traversal is done the
+    // rest of the pass is idle kernels.
+    for (int rep = 0; rep < loop_unroll(); ++rep) {
     {
         // push level: quad scan + quad advance (fused uniquify filter)
         const int64_t max_tiles = (n + SCAN_NT * SCAN_VT - 1) / (SCAN_NT * SCAN_VT);
@@ -408,6 +422,7 @@ int build_graph(b200_ctx *ctx, const b200_graph *g, int32_t *d_labels, int mode,
             ws->d_counters + B200_CNT_AUX2, ws->d_counters + B200_CNT_OVERFLOW, ctx->bm_frontier[0]);
         LL_CUDA(cudaGetLastError());
     }
+    }   // loop_unroll()
     capturing = false;
     if ((st = end_capture(cs, deps, &ndeps, 8)) != B200_OK) goto fail;
 

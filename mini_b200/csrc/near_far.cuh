@@ -65,6 +65,7 @@ __device__ __forceinline__ bool nf_open_bucket(NearFar *nf) {
     const float lo = __uint_as_float(bits);
     float hi = lo + delta;
     if (!(hi > lo)) hi = __uint_as_float(bits + 1u);   // width below one ulp of lo: the bucket is {lo}
+    if (!(hi < 3.402823466e+38f)) hi = 3.402823466e+38f;   // never past "unreached" (FLT_MAX): the take pass must not pick those up
     nf->delta = delta;
     nf->lo = lo;
     nf->cutoff = hi;

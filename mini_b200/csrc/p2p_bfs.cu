@@ -1218,7 +1218,9 @@ __global__ void __launch_bounds__(PULL_NT, 4) p2p_pull_levels_kernel(PullArgs a)
             bfs_pull_body<PULL_NT, true, PULL_CW>(part.n_local, a.pull_offsets, a.pull_indices, a.full, slice[bsel ^ 1u], a.done,
                                                   a.labels, level + 1, c->c, part, a.first_nbr);
         first_level = false;
+        loop_trace(&s->dyn, 35);
         if (!small_grid_barrier(sh, &s_gen, true)) break;   // (system scope: the new slice, before the flag that says it is complete)
+        loop_trace(&s->dyn, 36);
         // ---- level summary: row to every peer, flags, sums
         next_local = ld_volatile_u64(&c->c[B200_CNT_OUT]);
         const int parity = (int)(stats_seq & 1u);

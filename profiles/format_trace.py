@@ -11,8 +11,10 @@ NAMES = {20: "small-level kernel: entry", 21: "small: level start (expand the lo
          33: "pull: stats row posted", 34: "pull: stats in, decision",
          26: "small: CTA 0 done expanding (grid barrier follows)", 27: "small: grid barrier passed",
          28: "small: CTA 0 done absorbing (grid barrier follows)", 29: "small: grid barrier passed",
+         35: "pull: CTA 0 out of chunks (grid barrier follows)", 36: "pull: grid barrier passed",
          11: "bitmap -> list (entry)", 40: "near-far SSSP: pending-minimum pass", 41: "near-far SSSP: take pass"}
-SINGLE = {9: "decide (one thread: counters -> next level's state)"}   # ids whose meaning differs in the 1-GPU loop (level_loop.cu)
+SINGLE = {2: "quad scan (entry; returns at once when the previous advance created this level's scan)", 3: "quad advance (entry)",
+          9: "decide (one thread: counters -> next level's state)", 11: "bitmap -> list (entry; returns at once unless pull -> push)"}   # ids whose meaning differs in the 1-GPU loop (level_loop.cu)
 if len(sys.argv) > 2 and sys.argv[2] == "single":
     NAMES.update(SINGLE)
 for line in open(sys.argv[1]):

@@ -24,5 +24,10 @@ for _ in range(a.runs):
     rk.run(0, a.mode)
     print("ms", rk.device_ms, [(round(t, 1), k) for t, k in rk.last_trace()])
     print([dict(d=l["direction"][:4], x=l["exchange"], F=l["frontier"], arcs=l["arcs"], found=l["discovered"]) for l in rk.levels])
+# the single-GPU engine on the same graph: per-level times of the host-driven loop (CUDA events)
+for _ in range(3):
+    _, st = ctx.bfs(g, 0, mb.BFS_BEAMER if a.mode == "beamer" else mb.BFS_PUSH, 15.0, 18.0, timing=True)
+print("engine", st.device_ms, [("pull" if l["direction"] else "push", l["frontier_len"], l["arcs"], l["discovered"],
+                               round(l["advance_ms"], 4), round(l["level_ms"], 4)) for l in st.levels])
 rk.close()
 ctx.close()

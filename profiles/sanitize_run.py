@@ -29,8 +29,11 @@ for loop in [l for l, name in ((mb.LOOP_GRAPH, "graph"), (mb.LOOP_HOST, "host"))
         lab, _ = ctx.bfs(g, 0, mode, 15.0 if mode != mb.BFS_REF_ALPHA else 2.0, 18.0)
         assert np.array_equal(lab.cpu().numpy(), ref)
     preds = torch.empty(g.n, dtype=torch.int32, device="cuda")
-    dist, _ = ctx.sssp(g, 0, preds=preds)
-    assert dist.cpu().numpy().tobytes() == oracle.sssp_dist(o, 0).tobytes()
+    for delta in (0.0, 1.0, float("inf")):   # near-far order: automatic bucket width, one bucket per distance, the reference's order
+        ctx.set_sssp_delta(delta)
+        dist, _ = ctx.sssp(g, 0, preds=preds)
+        assert dist.cpu().numpy().tobytes() == oracle.sssp_dist(o, 0).tobytes()
+    ctx.set_sssp_delta(0.0)
 cur, red, lens, _ = ctx.pr(g, 3, False)
 ocur, _, olens = oracle.pr(o, 3, False)
 assert list(lens) == olens.tolist() and np.allclose(cur.cpu().numpy(), ocur, rtol=1e-4, atol=1e-6)

@@ -362,6 +362,23 @@ def test_sssp_near_far_any_bucket_width_gives_the_same_distances(ctx, delta):
         ctx.set_sssp_delta(0.0)
 
 
+def test_sssp_degenerate_weights(ctx):
+    """All-zero weights (automatic bucket width degenerates to one bucket), weights whose sums overflow fp32 (a distance
+    of +inf never beats FLT_MAX under the functor's strict <, sssp_functor.hxx:24: such vertices stay "unreached") and a
+    mix of tiny and huge weights (bucket width far below / above the distances)."""
+    o0 = _rand_graph(3000, 9000, 9)
+    rng = np.random.default_rng(12)
+    cases = [np.zeros(o0.m, np.float32),
+             np.full(o0.m, 2.0e38, np.float32),
+             np.where(rng.random(o0.m) < 0.5, 1e-6, 1e6).astype(np.float32)]
+    for w in cases:
+        o = oracle.CSR(o0.n, o0.offsets, o0.indices, w)
+        g = _dev_graph(ctx, o)
+        for src in (0, 2999):
+            dist, _ = ctx.sssp(g, src)
+            assert dist.cpu().numpy().tobytes() == oracle.sssp_dist_f32(o, src).tobytes()
+
+
 def test_sssp_near_far_relaxes_fewer_arcs_than_bellman_ford(ctx):
     """SURVEY 8f-4's bar: relaxed arcs <= 1.2x the arcs of the reached vertices (the reference's order needs ~2x on
     RMAT with weights 1..64).  The arc-wise kernel keeps the reference's order."""
