@@ -44,9 +44,11 @@ def _mg_roofline(levels, level_ms, timeline, n, world, sent):
             if ident == 31:
                 k += 1
                 if k == pulls.index(top):
-                    seq = timeline[j:j + 3]
-                    if len(seq) == 3 and seq[1][1] == 32 and seq[2][1] == 33:
-                        t_gather, t_ms = (seq[1][0] - seq[0][0]) * 1e-3, (seq[2][0] - seq[1][0]) * 1e-3
+                    # (marks 35 / 36 -- CTA 0 out of chunks, grid barrier passed -- sit between 32 and 33)
+                    t32 = next((tt for tt, ii in timeline[j + 1:j + 6] if ii == 32), None)
+                    t33 = next((tt for tt, ii in timeline[j + 1:j + 6] if ii == 33), None)
+                    if t32 is not None and t33 is not None and t33 > t32:
+                        t_gather, t_ms = (t32 - t) * 1e-3, (t33 - t32) * 1e-3
                     break
     gbs = b / world / (t_ms * 1e-3) / 1e9
     out.update({"kernel": "p2p_pull_levels_kernel: bfs_pull_body of the heaviest pull level (per GPU: 1/P of the rows)",

@@ -45,3 +45,17 @@ def test_reference_arm_names_the_multi_gpu_metric_for_n_gt_1():
 def test_reference_arm_other_ranks_exit_quietly():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--gpus", "2")
     assert r.returncode == 0 and r.stdout.strip() == "", (r.stdout, r.stderr[-500:])
+
+
+def test_multi_gpu_roofline_reads_the_pull_marks_of_the_kernel_timeline():
+    """bench_multi._mg_roofline takes the pull body's time (marks 32 -> 33) and the allgather's (31 -> 32) from the
+    kernels' own timeline; the marks 35 / 36 the pull-levels kernel logs in between must not hide them."""
+    import bench_multi as bm
+    levels = [dict(direction="push", frontier=1, arcs=10, discovered=5, sent=0),
+              dict(direction="pull", frontier=5, arcs=1000, discovered=50, sent=0)]
+    tl = [(0.0, 20), (10.0, 64), (11.0, 30), (12.0, 31), (30.0, 32), (100.0, 35), (140.0, 36), (142.0, 33), (143.0, 34), (144.0, 65)]
+    r = bm._mg_roofline(levels, [0.01, 0.134], tl, 1 << 20, 8, 0)
+    assert abs(r["launch_ms"] - 0.112) < 1e-9 and abs(r["nvlink"]["gather_ms"] - 0.018) < 1e-9
+    assert r["frac"] is not None and r["nvlink"]["frac"] is not None
+    r = bm._mg_roofline(levels, [0.01, 0.134], [(0.0, 20)], 1 << 20, 8, 0)      # no marks: the whole level's time
+    assert abs(r["launch_ms"] - 0.134) < 1e-9 and r["nvlink"]["frac"] is None
