@@ -19,10 +19,10 @@
 // resets it to delta0; and once 60 % of the arcs have been expanded the rest is ONE bucket: the tail of the distance
 // distribution is sparse, every bucket change costs two passes plus an iteration of ~17 us whatever it holds, and the
 // reference's order on a remainder of low-degree vertices re-expands little.  Measured policy, not theory (B200,
-// RMAT-22, integer weights 1..64): Bellman-Ford order 8 iterations, 1.80x the reached arcs, 1.57 ms; buckets all the
-// way 19 iterations in 6 buckets, 1.006x, 1.28 ms; with the last-bucket rule 9-10 iterations (CPU model of the same
-// policy on RMAT-21: 9 iterations, 1.02x).  Any width gives the same distances.  Weights must be non-negative (as the
-// integer atomicMin of the relax already requires).
+// RMAT-22, integer weights 1..64; profiles/r02_sssp_near_far.txt): the reference's order 8-9 iterations, 1.80x the
+// reached arcs, 1.57 ms; buckets all the way 19 iterations in 6 buckets, 1.006x, 1.28 ms; with the last-bucket rule
+// 9 iterations in 2 buckets, 1.019x, 1.01 ms.  Any width gives the same distances.  Weights must be non-negative (as
+// the integer atomicMin of the relax already requires).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
