@@ -440,6 +440,23 @@ def run_single_gpu(args):
                                        advance_ms=round(ms, 4)) for l, ms in zip(lv, lv_ms)]},
     }
 
+    if WORK_CREATE:
+        # the same level with a scan kernel before it instead of the work-creating flush (B200_ADVANCE_QUAD_RESCAN): the
+        # launch SURVEY 8d's bytes describe verbatim.  (The whole BFS is slower this way: the scan kernels cost more than
+        # the flush adds.)
+        ctx.set_advance_impl(mb.ADVANCE_QUAD_RESCAN)
+        ms_r, bfs_r = 0.0, 0.0
+        for r in range(reps + 1):
+            _, st = ctx.bfs(g, 0, mb.BFS_PUSH, labels=labels, timing=True)
+            if r:
+                ms_r += st.levels[top]["advance_ms"] / reps
+                bfs_r += sum(l["level_ms"] for l in st.levels) / reps
+        ctx.set_advance_impl(mb.ADVANCE_QUAD)
+        gbs_r = push_level_bytes(lv[top]) / (ms_r * 1e-3) / 1e9
+        roofline["rescan_form"] = {"launch_ms": ms_r, "achieved": gbs_r, "frac": gbs_r / peak,
+                                   "note": "same kernel, same level, scan kernel before every level instead of the "
+                                           "work-creating flush; host-driven loop with CUDA events"}
+
     # ---- end to end through the host-buffer C-ABI call: H2D initial labels + BFS + D2H labels every step
     off_h = g.row_offsets.cpu().numpy().view(np.uint32)
     idx_h = g.col_indices.cpu().numpy()
