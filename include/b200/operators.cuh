@@ -164,7 +164,7 @@ cudaError_t launch_lbs_advance(b200_workspace *ws, const LbsArgs &a, Op op, int 
 #define B200_QUAD_VT 2
 #endif
 #ifndef B200_QUAD_WSEG
-#define B200_QUAD_WSEG 32
+#define B200_QUAD_WSEG 64
 #endif
 constexpr int QUAD_NT = B200_QUAD_NT, QUAD_WSEG = B200_QUAD_WSEG, QUAD_WSTAGE = 64 * QUAD_R;
 constexpr uint32_t QUAD_MIN_CHUNK = 64;            // work items per warp, lower bound
@@ -204,9 +204,13 @@ template <int OUT_MODE, bool DEG_SUM, class Op>
 cudaError_t launch_quad_advance(b200_workspace *ws, const QuadArgs &a, Op op, int *d_out, unsigned long long capacity,
                                 const RoutedOut *routed = nullptr) {
     constexpr int VT = Op::WEIGHTED ? 2 : B200_QUAD_VT;
+    // segments staged per warp window: 64 for the unweighted operators (round-2 A/B, scale-22 push BFS: the 2 M-vertex
+    // level 0.1522 -> 0.1446 ms, whole BFS -1.5 %; the heaviest level is unchanged), 32 for the weighted ones, whose
+    // 3-word candidates already take 152 KB of shared memory (SSSP was 17 % slower with 64)
+    constexpr int WSEG = Op::WEIGHTED ? (QUAD_WSEG < 32 ? QUAD_WSEG : 32) : QUAD_WSEG;
     constexpr bool STAGED = OUT_MODE == OUT_COMPACT || OUT_MODE == OUT_ROUTED;
-    auto k = quad_advance_kernel<Op, OUT_MODE, DEG_SUM, QUAD_NT, VT, QUAD_WSEG>;
-    constexpr size_t smem = sizeof(uint32_t) * (QUAD_NT / 32) * quad_warp_words<Op, STAGED, VT, QUAD_WSEG, QUAD_WSTAGE>();
+    auto k = quad_advance_kernel<Op, OUT_MODE, DEG_SUM, QUAD_NT, VT, WSEG>;
+    constexpr size_t smem = sizeof(uint32_t) * (QUAD_NT / 32) * quad_warp_words<Op, STAGED, VT, WSEG, QUAD_WSTAGE>();
     static_assert(smem <= 232448 - 64, "per-warp areas exceed the 227 KB opt-in shared memory of sm_100");
     static unsigned long long opted_in = 0;   // per <Op, OUT_MODE, DEG_SUM> instantiation, one bit per device
     if (!(opted_in >> (ws->device & 63) & 1ull)) {
