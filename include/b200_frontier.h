@@ -382,7 +382,11 @@ int b200_p2p_bfs_run(b200_p2p_bfs *s, const b200_graph *g_local, int64_t m_globa
 int b200_p2p_bfs_prepare(b200_p2p_bfs *s, const b200_graph *g_local, int mode, int32_t *d_labels_local);
 /* Timeline of the graph-driven loop (new; with no host between the levels there are no CUDA events to hang a
  * per-level time on): when on, the kernels of a run log (globaltimer ns << 8 | id) at their phase boundaries; ids
- * 64 + (level & 63) mark "level closed".  b200_p2p_bfs_last_trace copies the entries of the last traced run. */
+ * 64 + (level & 63) mark "level closed".  b200_p2p_bfs_last_trace copies the entries of the last traced run.
+ * Other ids (profiles/format_trace.py names them): 20-29 small-level kernel phases, 2 / 3 / 5 / 13 / 9 / 12 big push level
+ * (scan, claim-only advance, bitmap absorb, its flag barrier, stats + decide, its flag barrier), 30-36 pull-levels kernel
+ * phases.  The single-GPU loops (b200_bfs_run / b200_sssp_run) print the same kind of line to stderr when the environment
+ * variable B200_LOOP_TRACE is set (ids 2 scan, 3 advance, 9 decide, 11 bitmap -> list, 40 / 41 near-far passes). */
 int b200_p2p_bfs_set_trace(b200_p2p_bfs *s, int on);
 int b200_p2p_bfs_last_trace(b200_p2p_bfs *s, uint64_t *entries, int64_t capacity, int64_t *count);
 int b200_p2p_bfs_destroy(b200_p2p_bfs *s);
